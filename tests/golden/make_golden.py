@@ -1,0 +1,238 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REFERENCE itself.
+
+Runs only in the build container (needs /root/reference):
+  * imports the reference's Python (taiyaki.flipflopfings, taiyaki.layers,
+    taiyaki.loss) from /root/reference for index coding, the TorchScript
+    partition function + its autograd gradient, and FlipFlopLoss forward;
+  * calls the reference's own C (oracle/_ref/libctc_ref.so, built by
+    oracle/Makefile from /root/reference/taiyaki/ctc/*.c) for the
+    label-constrained DP;
+  * lifts the embedded known-answer tables out of the reference's C test mains
+    (c_crf_flipflop.c:520-695, c_cat_mod_flipflop.c:586-870) as DATA.
+
+The .npz files are committed; the GPU box never sees /root/reference.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+import torch  # noqa: E402
+from oracle import oracle  # noqa: E402
+from taiyaki import flipflopfings as ref_fff  # noqa: E402
+from taiyaki import layers as ref_layers  # noqa: E402
+from taiyaki import loss as ref_loss  # noqa: E402
+from taiyaki.constants import SMALL_VAL  # noqa: E402
+
+
+def c_array(src, name):
+    """Pull `name[...] = { ... };` out of a C file as a flat float list."""
+    m = re.search(r'\b' + name + r'\s*\[[^\]]*\]\s*=\s*\{(.*?)\};', src, re.S)
+    assert m, name
+    body = re.sub(r'//[^\n]*', '', m.group(1))
+    return [float(x) for x in re.findall(r'[-+]?\d*\.?\d+(?:[eE][-+]?\d+)?', body)]
+
+
+def kat_tables():
+    out = {}
+    src = open(os.path.join(REF, 'taiyaki/ctc/c_crf_flipflop.c')).read()
+    lp = np.log(np.array(c_array(src, 'test_logprob1'), dtype=np.float32)
+                ).reshape(7, 2, 40).astype(np.float32)
+    out['crf_logprob'] = lp
+    out['crf_seq'] = np.array(c_array(src, 'test_seq1'), dtype=np.int64)
+    out['crf_move'] = np.array(c_array(src, 'test_move1'), dtype=np.int64)
+    out['crf_stay'] = np.array(c_array(src, 'test_stay1'), dtype=np.int64)
+    out['crf_seqlen'] = np.array(c_array(src, 'test_seqlen1'), dtype=np.int64)
+    # c_crf_flipflop.c:520-530 packs move with 5 entries per chunk
+    mv = out['crf_move'][:10]
+    st = out['crf_stay']
+    sc, gr = oracle.c_crf_flipflop_grad(lp, mv, st, out['crf_seqlen'], 'ref')
+    out['crf_move'] = mv
+    out['crf_score'] = sc      # printed as -2.378088 -2.378088 by crf_test
+    out['crf_grad'] = gr
+
+    src = open(os.path.join(REF, 'taiyaki/ctc/c_cat_mod_flipflop.c')).read()
+    main = src[src.index('#ifdef CAT_MOD_FLIPFLOP_TEST'):]
+    names = re.findall(r'(\w+)\s*\[[^\]]*\]\s*=\s*\{', main)
+    return out, main, names
+
+
+def cat_mod_kat(main, names):
+    """The cat-mod test main: tables + how main() calls the library."""
+    out = {}
+    for n in names:
+        out['cm_' + n] = np.array(c_array(main, n))
+    # main() (c_cat_mod_flipflop.c:799-823) takes log of the table and passes
+    # the 12-entry index arrays as they are; the library offsets chunk 1's
+    # move/mod arrays by seqidx - 1 = 5.
+    lp = np.log(out['cm_test_logprob1'].astype(np.float32)).reshape(7, 2, 45)
+    lp = lp.astype(np.float32)
+    sl = out['cm_test_seqlen1'].astype(np.int64)
+    mv = out['cm_test_move1'].astype(np.int64)
+    st = out['cm_test_stay1'].astype(np.int64)
+    mm = out['cm_test_modmoveidx1'].astype(np.int64)
+    mf = out['cm_test_modmovefact1'].astype(np.float32)
+    sc, gr = oracle.c_cat_mod_flipflop_grad(lp, mv, st, mm, mf, sl, 'ref')
+    out = {'cm_logprob': lp, 'cm_seqlen': sl, 'cm_move': mv, 'cm_stay': st,
+           'cm_modmove': mm, 'cm_modfact': mf, 'cm_score': sc, 'cm_grad': gr}
+    # printed by cm_test as -52.354622 -195.435257
+    return out
+
+
+def ctc_loss_unit_case():
+    """test/unit/test_ctc_loss.py:24-103 -- scores whose path probabilities
+    are known: P(015) = P(237) = 0.5, P(510) ~ 0; logZ = 0."""
+    nbases, nblocks = 4, 4
+
+    def tc(f, t):
+        return t * 2 * nbases + f if t < nbases else 2 * nbases * nbases + f
+    paths = {'015': [0, 0, 1, 5, 5], '237': [2, 2, 3, 7, 7]}
+    weights = {'015': [1.0, 1.0, 0.5, 1.0], '237': [1.0, 0.5, 1.0, 1.0]}
+    outputs = torch.zeros(nblocks, 1, 40, dtype=torch.float)
+    for k in paths:
+        for blk in range(nblocks):
+            outputs[blk, 0, tc(paths[k][blk], paths[k][blk + 1])] = weights[k][blk]
+    outputs = torch.log(outputs + SMALL_VAL)
+    outputs = ref_layers.global_norm_flipflop(outputs)
+    logpart = float(ref_layers.log_partition_flipflop(outputs))
+    return {'unit_scores': outputs.numpy(),
+            'unit_logpart': np.float32(logpart),
+            'unit_seqs': np.array([[0, 1, 5], [2, 3, 7], [5, 1, 0]], dtype=np.int64),
+            'unit_probs': np.array([0.5, 0.5, 0.0], dtype=np.float64)}
+
+
+def ref_indices(seqs, seqlen, nbase):
+    parts = np.split(seqs.astype(np.int32), np.cumsum(seqlen[:-1]))
+    mv = np.concatenate([ref_fff.move_indices(s, nbase) for s in parts])
+    st = np.concatenate([ref_fff.stay_indices(s, nbase) for s in parts])
+    return mv.astype(np.int64), st.astype(np.int64)
+
+
+def random_case(tag, nblk, lengths, ntrans, seed, sharp=1.0, scale=1.0):
+    nbatch = len(lengths)
+    out = {}
+    scores = oracle.synth_scores(nblk, nbatch, ntrans, seed=seed) * np.float32(scale)
+    rng = np.random.RandomState(seed + 100)
+    raw = [rng.randint(0, 4, size=int(L)) for L in lengths]
+    seqs = np.concatenate([ref_fff.flipflop_code(r, 4) if len(r) else r.astype(np.int64)
+                           for r in raw]).astype(np.int64)
+    seqlen = np.array(lengths, dtype=np.int64)
+    mv, st = ref_indices(seqs, seqlen, 4)
+    out['scores'] = scores
+    out['seqs'] = seqs
+    out['seqlen'] = seqlen
+    out['move'] = mv
+    out['stay'] = st
+    out['sharp'] = np.float32(sharp)
+    if ntrans == 40:
+        lp = np.float32(sharp) * scores
+        sc, gr = oracle.c_crf_flipflop_grad(lp, mv, st, seqlen, 'ref')
+        out['score'] = sc
+        out['grad'] = gr
+        out['score_costonly'] = oracle.c_crf_flipflop_cost(lp, mv, st, seqlen, 'ref')
+        # secondary forward-only oracle: taiyaki/loss.py:113-173
+        if all(L > 0 for L in lengths):
+            try:
+                ffl = ref_loss.FlipFlopLoss(sharp=float(sharp))
+                Lmax = int(max(lengths))
+                pst = np.zeros((nbatch, Lmax), dtype=np.int64)
+                pmv = np.zeros((nbatch, Lmax - 1), dtype=np.int64)
+                for b, s in enumerate(np.split(seqs, np.cumsum(seqlen[:-1]))):
+                    pst[b, :len(s)] = ref_fff.stay_indices(s, 4)
+                    pmv[b, :len(s) - 1] = ref_fff.move_indices(s, 4)
+                with torch.no_grad():
+                    v = ffl(torch.tensor(scores), torch.tensor(pmv),
+                            torch.tensor(pst), torch.tensor(seqlen))
+                out['torch_flipfloploss'] = np.asarray(v, dtype=np.float32)
+            except Exception as e:  # informational only
+                out['torch_flipfloploss_err'] = np.array(str(e))
+    else:
+        can_mods_offsets = np.array([0, 1, 3, 4, 5], dtype=np.int32)
+        mod_cats = np.concatenate([
+            ((r == 1) & (rng.uniform(size=len(r)) < 0.5)).astype(np.int64)
+            for r in raw]).astype(np.int64)
+        w = np.array([1.0, 1.0, 0.7, 1.0, 1.0], dtype=np.float32)
+        trans_sharp = np.ones(ntrans, dtype=np.float32)
+        trans_sharp[:40] = sharp
+        lp = np.ascontiguousarray(scores * trans_sharp)
+        mm, mf = oracle.build_mod_indices(seqs, seqlen, mod_cats, can_mods_offsets, w, 4)
+        sc, gr = oracle.c_cat_mod_flipflop_grad(lp, mv, st, mm, mf, seqlen, 'ref')
+        out['mod_cats'] = mod_cats
+        out['can_mods_offsets'] = can_mods_offsets
+        out['mod_cat_weights'] = w
+        out['modmove'] = mm.astype(np.int64)
+        out['modfact'] = mf
+        out['score'] = sc
+        out['grad'] = gr
+        out['score_costonly'] = oracle.c_cat_mod_flipflop_cost(
+            lp, mv, st, mm, mf, seqlen, 'ref')
+    # partition function + autograd gradient from the reference's TorchScript
+    x = torch.tensor(scores[:, :, :40].copy(), requires_grad=True)
+    lz = ref_layers.log_partition_flipflop(x).squeeze(1)
+    lz.sum().backward()
+    out['logz'] = lz.detach().numpy()
+    out['logz_grad'] = x.grad.numpy()
+    return {tag + '_' + k: v for k, v in out.items()}
+
+
+def decodeutil_case():
+    """test/unit/test_decodeutil.py:16-31: seed 0xdeadbeef, randn(12,40)."""
+    np.random.seed(0xdeadbeef)
+    w = np.random.randn(12, 40).astype('f4')
+    lz = float(ref_layers.log_partition_flipflop(torch.tensor(w).unsqueeze(1)))
+    return {'du_weights': w, 'du_logz_flipstart': np.float32(lz),
+            'du_free_start_expected': np.float64(27.16876983642578)}
+
+
+def flipflop_code_cases():
+    rng = np.random.RandomState(5)
+    out = {}
+    ex = np.array([1, 3, 2, 3, 3, 3, 3, 1, 1])
+    out['code_in0'] = ex
+    out['code_out0'] = ref_fff.flipflop_code(ex)
+    x = rng.randint(0, 4, size=400)
+    x[50:60] = 2
+    out['code_in1'] = x
+    out['code_out1'] = ref_fff.flipflop_code(x)
+    out['code_move1'] = ref_fff.move_indices(out['code_out1'], 4)
+    out['code_stay1'] = ref_fff.stay_indices(out['code_out1'], 4)
+    return out
+
+
+def main():
+    oracle.build()
+    assert oracle.have_ref()
+    g = {}
+    kat, cm_main, cm_names = kat_tables()
+    g.update(kat)
+    g.update(cat_mod_kat(cm_main, cm_names))
+    g.update(ctc_loss_unit_case())
+    g.update(decodeutil_case())
+    g.update(flipflop_code_cases())
+    np.savez_compressed(os.path.join(HERE, 'kat.npz'), **g)
+
+    r = {}
+    r.update(random_case('a', 50, [20, 1, 27, 13, 0, 45, 2], 40, seed=11))
+    r.update(random_case('b', 64, [30, 35, 28], 40, seed=12, sharp=2.0))
+    r.update(random_case('c', 40, [18, 22, 1, 0, 9], 45, seed=13))
+    r.update(random_case('d', 33, [15, 17], 45, seed=14, sharp=1.5))
+    r.update(random_case('e', 120, [100, 64, 33, 120], 40, seed=15, scale=4.0))
+    np.savez_compressed(os.path.join(HERE, 'random.npz'), **r)
+    for f in ('kat.npz', 'random.npz'):
+        print(f, os.path.getsize(os.path.join(HERE, f)), 'bytes')
+    print('crf KAT score', g['crf_score'])
+    print('cat-mod tables:', cm_names)
+
+
+if __name__ == '__main__':
+    main()
