@@ -1,0 +1,148 @@
+/*
+ * taiyaki_b200.h -- C ABI of libtaiyaki_b200.so, the B200 (sm_100a) drop-in
+ * for the flip-flop CRF training hot path of nanoporetech/taiyaki v5.3.0.
+ *
+ * Two layers are exported:
+ *
+ *  (A) HOST-POINTER DROP-INS with the reference's exact names and signatures
+ *      (taiyaki/ctc/libctc.pxd:3-25, c_crf_flipflop.h, c_cat_mod_flipflop.h).
+ *      Linking taiyaki/ctc/ctc.pyx against this library instead of
+ *      c_crf_flipflop.c / c_cat_mod_flipflop.c needs no source change; the
+ *      copies to and from the device happen inside the call.
+ *
+ *  (B) DEVICE-POINTER entry points (`ty_*`), asynchronous on a caller-supplied
+ *      CUDA stream with caller-supplied workspace, used by the Python operator
+ *      layer (taiyaki_b200/ctc.py, layers.py) so that scores never leave HBM.
+ *      They replace, per function:
+ *        ty_crf_flipflop_*      c_crf_flipflop.c:255-290 (cost), :434-516 (grad)
+ *        ty_cat_mod_flipflop_*  c_cat_mod_flipflop.c:286-345, :493-582
+ *        ty_flipflop_indices    ctc.pyx:127-132, :287-292 (flipflopfings.py:6-31)
+ *        ty_flipflop_logz*      cupy_extensions/flipflop.py:10-368 and
+ *                               layers.py:1253-1299 (logZ and its gradient)
+ *        ty_lstm_* / ty_gru_*   the cuDNN calls behind layers.py:515 (nn.LSTM)
+ *                               and layers.py:633 (nn.GRU), bias_hh == 0
+ *
+ * All tensors are C-contiguous fp32 unless noted; score tensors are
+ * [nblk][nbatch][ntrans] exactly as the reference lays them out.  No function
+ * allocates device memory except the (A) layer, which keeps a grow-only pool.
+ *
+ * Return value of every ty_* function: 0 on success, else a TY_E* code.
+ */
+#ifndef TAIYAKI_B200_H
+#define TAIYAKI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TY_OK 0
+#define TY_EINVAL 1   /* bad shape / null pointer / unsupported size      */
+#define TY_EWORKSPACE 2 /* workspace too small                            */
+#define TY_ECUDA 3    /* CUDA runtime error (see ty_last_error_string)    */
+
+const char *ty_last_error_string(void);
+const char *ty_version(void);
+
+/* ---------------------------------------------------------------- (A) ---
+ * Reference ABI, host pointers.  Index arrays are size_t and packed as the
+ * reference packs them: stayidxs has sum(seqlen) entries, moveidxs (and the
+ * mod arrays) sum(seqlen) - nbatch, chunk b starting at sum(seqlen[:b]) (- b).
+ * score[b] = 0.5 * (forward + backward) log-score; grad rows sum to one.
+ */
+void crf_flipflop_grad(const float *logprob, size_t ntrans, size_t nblk,
+                       size_t nbatch, const size_t *moveidxs,
+                       const size_t *stayidxs, const int32_t *seqlen,
+                       float *score, float *grad);
+void crf_flipflop_cost(const float *logprob, size_t ntrans, size_t nblk,
+                       size_t nbatch, const size_t *moveidxs,
+                       const size_t *stayidxs, const int32_t *seqlen,
+                       float *score);
+void cat_mod_flipflop_grad(const float *logprob, size_t ntrans, size_t nblk,
+                           size_t nbatch, const size_t *moveidxs,
+                           const size_t *stayidxs, const size_t *modmoveidxs,
+                           const float *modmovefacts, const int32_t *seqlen,
+                           float *score, float *grad);
+void cat_mod_flipflop_cost(const float *logprob, size_t ntrans, size_t nblk,
+                           size_t nbatch, const size_t *moveidxs,
+                           const size_t *stayidxs, const size_t *modmoveidxs,
+                           const float *modmovefacts, const int32_t *seqlen,
+                           float *score);
+
+/* ---------------------------------------------------------------- (B) ---
+ * Label-constrained CRF, device pointers.
+ *
+ * moveidx/stayidx/modmoveidx are int32 in the reference packing.  seqlen is
+ * int32 [nbatch] ON THE DEVICE; max_seqlen (host value, >= every seqlen) only
+ * selects the launch configuration.  `sharp` multiplies columns < nsharp
+ * before use (ctc.pyx:119 and :265-269); pass nsharp = ntrans for the plain
+ * model.  score_out[b] = score_scale * score, grad_out = grad_scale * G, so
+ * the operator's -x/nblk (ctc.pyx:66,113) costs nothing extra.
+ * modmoveidx == NULL selects the plain model.  grad_out == NULL computes the
+ * forward score only (crf_flipflop_cost semantics: forward score, not the
+ * forward/backward average).
+ */
+size_t ty_crf_flipflop_workspace_bytes(int ntrans, int nblk, int nbatch,
+                                       int max_seqlen, int want_grad);
+
+int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int nbatch,
+                    const int32_t *moveidx, const int32_t *stayidx,
+                    const int32_t *modmoveidx, const float *modmovefact,
+                    const int32_t *seqlen, int max_seqlen,
+                    float sharp, int nsharp,
+                    float score_scale, float *score_out,
+                    float grad_scale, float *grad_out,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Flip-flop index build on the device.  seqs: int64 [total] concatenated
+ * flip-flop coded labels; seqlen int64 [nbatch]; outputs int32 in the
+ * reference packing plus seqlen32.  mod_cats (int64 [total]) / can_mods_offsets
+ * (int32 [nbase+1]) / mod_cat_weights (float [ncan+nmod]) may be NULL. */
+int ty_flipflop_indices(const int64_t *seqs, const int64_t *seqlen, int nbatch,
+                        int64_t total, int nbase,
+                        const int64_t *mod_cats, const int32_t *can_mods_offsets,
+                        const float *mod_cat_weights,
+                        int32_t *moveidx, int32_t *stayidx, int32_t *seqlen32,
+                        int32_t *modmoveidx, float *modmovefact, void *stream);
+
+/* Partition function over the 2*nbase-state lattice.
+ * scores: [nblk][nbatch] rows of `ld` floats of which the first
+ * S = 2*nbase*(nbase+1) are transition scores (ld >= S lets the cat-mod
+ * tensor be used in place, train_flipflop.py:175).
+ * logz_out[b] = logz_scale * logZ_b.  If grad_out != NULL it receives
+ * grad_scale * d logZ / d scores (rows of ld_grad floats; columns >= S are
+ * left untouched), optionally accumulated into what is already there. */
+size_t ty_flipflop_logz_workspace_bytes(int nbase, int nblk, int nbatch);
+
+int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatch,
+                     int nbase, float logz_scale, float *logz_out,
+                     float grad_scale, float *grad_out, int ld_grad,
+                     int accumulate, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ----------------------------------------------------------------------
+ * Recurrent layers (time-major [T][N][H], PyTorch gate order, b_hh == 0).
+ * See taiyaki_b200/csrc/rnn.cu for the data layout of `reserve`.
+ * xproj: [T][N][G*H] = x W_ih^T + b_ih computed by the caller (one large
+ * GEMM); w_hh: [G*H][H] fp32; reverse != 0 iterates t downward
+ * (layers.py:117-153 without the two flips).  G = 4 (LSTM) or 3 (GRU).
+ */
+size_t ty_rnn_reserve_bytes(int cell, int T, int N, int H);
+
+int ty_lstm_forward(const float *xproj, const float *w_hh, int T, int N, int H,
+                    int reverse, float *y, void *reserve, void *stream);
+int ty_lstm_backward(const float *dy, const float *w_hh, int T, int N, int H,
+                     int reverse, const float *y, const void *reserve,
+                     float *dxproj, void *stream);
+int ty_gru_forward(const float *xproj, const float *w_hh, int T, int N, int H,
+                   int reverse, float *y, void *reserve, void *stream);
+int ty_gru_backward(const float *dy, const float *w_hh, int T, int N, int H,
+                    int reverse, const float *y, const void *reserve,
+                    float *dxproj, float *dhproj, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAIYAKI_B200_H */

@@ -1,0 +1,126 @@
+"""ctypes binding of libtaiyaki_b200.so (include/taiyaki_b200.h).
+
+The library is built in-tree by `build()` (nvcc, sm_100a only) and loaded
+lazily.  There is deliberately no fallback: if the shared object is missing or
+a CUDA call fails the operators raise.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(_HERE, 'libtaiyaki_b200.so')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+              '-std=c++17', '-Xcompiler', '-fPIC', '-shared']
+
+c_void_p, c_int, c_float, c_size_t, c_int64 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_int64)
+
+_SIGNATURES = {
+    'ty_last_error_string': (ctypes.c_char_p, []),
+    'ty_version': (ctypes.c_char_p, []),
+    'ty_crf_flipflop_workspace_bytes': (c_size_t, [c_int] * 5),
+    'ty_crf_flipflop': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int, c_float, c_int, c_float, c_void_p,
+                                c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ty_flipflop_indices': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
+    'ty_flipflop_logz_workspace_bytes': (c_size_t, [c_int] * 3),
+    'ty_flipflop_logz': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                 c_float, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'ty_rnn_reserve_bytes': (c_size_t, [c_int] * 4),
+    'ty_lstm_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p]),
+    'ty_lstm_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    'ty_gru_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                               c_void_p, c_void_p]),
+    'ty_gru_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+# host-pointer drop-ins carrying the reference's own names (libctc.pxd:3-25)
+HOST_ABI = ['crf_flipflop_grad', 'crf_flipflop_cost', 'cat_mod_flipflop_grad',
+            'cat_mod_flipflop_cost']
+EXPORTS = sorted(_SIGNATURES) + HOST_ABI
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(_CSRC, '*.cu')))
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into taiyaki_b200/libtaiyaki_b200.so."""
+    srcs = sources()
+    deps = srcs + glob.glob(os.path.join(_CSRC, '*.cuh')) + [
+        os.path.join(os.path.dirname(_HERE), 'include', 'taiyaki_b200.h')]
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return LIB_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + srcs
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'taiyaki_b200: %s is missing -- run `python -c "import __graft_entry__ as g; '
+                'g.build()"`; there is no CPU fallback' % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+class TaiyakiB200Error(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ty_last_error_string().decode()
+        raise TaiyakiB200Error('%s failed (code %d): %s' % (what, rc, msg))
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise TaiyakiB200Error(
+            'taiyaki_b200: %s must be a CUDA tensor (got %s); this package has no CPU path'
+            % (name, t.device))
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per (device, stream); kernels are stream ordered."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf

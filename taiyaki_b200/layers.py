@@ -1,0 +1,533 @@
+"""Layers on the flip-flop training path -- mirror of the relevant part of
+taiyaki/layers.py (time-major [T, N, F] tensors, same class / attribute /
+parameter names so `state_dict`s and model-definition files carry over).
+
+  Lstm, GruMod              layers.py:491-725  recurrence in csrc/rnn.cu instead of cuDNN
+  Reverse                   layers.py:117-153  loop direction instead of two flips
+  Serial, Convolution       layers.py:944-982, :744-850
+  GlobalNormFlipFlop[CatMod] layers.py:1316-1640
+  flipflop_logpartition     layers.py:1875-1890 -> csrc/logz.cu (was CuPy / TorchScript)
+  global_norm_flipflop, log_partition_flipflop  layers.py:1277-1313
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from scipy import linalg
+from scipy.stats import truncnorm
+from torch import nn
+
+from . import _lib, activation, flipflopfings
+
+MODEL_VERSION = 3
+_CELL_LSTM, _CELL_GRU = 0, 1
+
+
+# ---------------------------------------------------------------------------
+# initialisers (layers.py:22-114)
+def init_(param, value):
+    value_as_tensor = torch.tensor(np.asarray(value), dtype=param.data.dtype)
+    with torch.no_grad():
+        param.set_(value_as_tensor.to(param.device))
+
+
+def random_orthonormal(n, m=None):
+    """QR of Gaussian noise with the sign fix of Mezzadri (layers.py:37-66)."""
+    m = n if m is None else m
+    assert m >= n
+    x = np.random.randn(m, m)
+    Q, r = linalg.qr(x, mode='economic')
+    flipper = np.diag(np.sign(np.diag(r)))
+    return Q.dot(flipper)[:n, :]
+
+
+def orthonormal_matrix(nrow, ncol):
+    """Block-orthonormal [nrow, ncol] matrix (layers.py:69-96)."""
+    nrep = nrow // ncol
+    out = np.zeros((nrow, ncol), dtype='f4')
+    for i in range(nrep):
+        out[i * ncol: i * ncol + ncol] = random_orthonormal(ncol)
+    remsize = nrow - nrep * ncol
+    if remsize > 0:
+        out[nrep * ncol:, :] = random_orthonormal(remsize, ncol)
+    return out
+
+
+def truncated_normal(size, sd):
+    """Normal truncated at +/-2 sd (layers.py:99-114)."""
+    res = sd * truncnorm.rvs(-2, 2, size=size)
+    return res.astype('f4')
+
+
+def _reshape(x, shape):
+    return x.reshape(shape)
+
+
+class _tf32_matmul:
+    """The dense input/weight-gradient projections run on the tensor cores with
+    TF32 operands and fp32 accumulation (what cuDNN does for the reference on
+    Ampere and later: torch.backends.cudnn.allow_tf32 defaults to True)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+# ---------------------------------------------------------------------------
+# recurrence
+class _Recurrence(torch.autograd.Function):
+    """y = RNN(x) with the sequential part in csrc/rnn.cu.
+
+    forward:  xproj = x W_ih^T + b_ih (one GEMM) -> ty_{lstm,gru}_forward
+    backward: ty_{lstm,gru}_backward gives d xproj (and the hidden-side n-gate
+              gradient for the GRU); weight / input gradients are dense GEMMs.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, cell, reverse):
+        _lib.require_cuda(x, 'x')
+        lib = _lib.lib()
+        T, N, I = x.shape
+        G = 4 if cell == _CELL_LSTM else 3
+        H = w_hh.shape[1]
+        x = x.contiguous().float()
+        w_hh_c = w_hh.detach().contiguous().float()
+        x2 = x.view(T * N, I)
+        with _tf32_matmul():
+            if b_ih is not None:
+                xproj = torch.addmm(b_ih.detach(), x2, w_ih.detach().t())
+            else:
+                xproj = x2 @ w_ih.detach().t()
+        y = torch.empty(T, N, H, dtype=torch.float32, device=x.device)
+        reserve = torch.empty(lib.ty_rnn_reserve_bytes(cell, T, N, H) // 4,
+                              dtype=torch.float32, device=x.device)
+        fn = lib.ty_lstm_forward if cell == _CELL_LSTM else lib.ty_gru_forward
+        rc = fn(_lib.ptr(xproj), _lib.ptr(w_hh_c), T, N, H, int(reverse), _lib.ptr(y),
+                _lib.ptr(reserve), _lib.stream_ptr(x.device))
+        _lib.check(rc, 'ty_rnn_forward')
+        ctx.save_for_backward(x, w_ih, w_hh_c, y, reserve)
+        ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, w_ih, w_hh_c, y, reserve = ctx.saved_tensors
+        cell, reverse, has_bias, G, H = ctx.cfg
+        T, N, I = x.shape
+        dy = dy.contiguous().float()
+        dxproj = torch.empty(T, N, G * H, dtype=torch.float32, device=x.device)
+        stream = _lib.stream_ptr(x.device)
+        if cell == _CELL_LSTM:
+            rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
+                                      _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj), stream)
+            dhn = None
+        else:
+            dhn = torch.empty(T, N, H, dtype=torch.float32, device=x.device)
+            rc = lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
+                                     _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
+                                     _lib.ptr(dhn), stream)
+        _lib.check(rc, 'ty_rnn_backward')
+        d2 = dxproj.view(T * N, G * H)
+        # h_{t-1} of every step is y shifted by one step along the loop direction
+        if reverse:
+            d_cur, h_prev = dxproj[:-1], y[1:]
+            dhn_cur = dhn[:-1] if dhn is not None else None
+        else:
+            d_cur, h_prev = dxproj[1:], y[:-1]
+            dhn_cur = dhn[1:] if dhn is not None else None
+        hp2 = h_prev.reshape(-1, H)
+        with _tf32_matmul():
+            dx = (d2 @ w_ih).view(T, N, I) if ctx.needs_input_grad[0] else None
+            dw_ih = d2.t() @ x.view(T * N, I)
+            if cell == _CELL_LSTM:
+                dw_hh = d_cur.reshape(-1, G * H).t() @ hp2
+            else:
+                dw_hh = torch.cat([
+                    d_cur[:, :, :2 * H].reshape(-1, 2 * H).t() @ hp2,
+                    dhn_cur.reshape(-1, H).t() @ hp2], 0)
+        db = d2.sum(0) if has_bias else None
+        return dx, dw_ih, dw_hh, db, None, None
+
+
+class Lstm(nn.Module):
+    """LSTM layer (layers.py:491-606).  `self.lstm` is kept as the parameter
+    container so checkpoints keep `lstm.weight_ih_l0` etc.; `bias_hh` stays
+    frozen at zero and hidden from `named_parameters`."""
+
+    def __init__(self, insize, size, has_bias=True):
+        super().__init__()
+        self.lstm = nn.LSTM(insize, size, bias=has_bias)
+        self.insize = insize
+        self.size = size
+        self.has_bias = has_bias
+        self._disable_state_bias()
+        self.reset_parameters()
+
+    def _disable_state_bias(self):
+        for name, param in self.lstm.named_parameters():
+            if 'bias_hh' in name:
+                param.requires_grad = False
+                param.data.zero_()
+
+    def reset_parameters(self):
+        for name, param in self.named_parameters():
+            shape = list(param.shape)
+            if 'weight_hh' in name or 'weight_ih' in name:
+                init_(param, orthonormal_matrix(*shape))
+            else:
+                init_(param, truncated_normal(shape, sd=0.5))
+
+    def named_parameters(self, prefix='', recurse=True):
+        for name, param in self.lstm.named_parameters(prefix=prefix, recurse=recurse):
+            if 'bias_hh' not in name:
+                yield name, param
+
+    def forward(self, x, reverse=False):
+        m = self.lstm
+        return _Recurrence.apply(x, m.weight_ih_l0, m.weight_hh_l0,
+                                 m.bias_ih_l0 if self.has_bias else None, _CELL_LSTM, reverse)
+
+    def json(self):
+        res = OrderedDict([('type', "LSTM"), ('activation', "tanh"), ('gate', "sigmoid"),
+                           ('size', self.size), ('insize', self.insize),
+                           ('bias', self.has_bias)])
+        res['params'] = OrderedDict([
+            ('iW', _reshape(self.lstm.weight_ih_l0, (4, self.size, self.insize))),
+            ('sW', _reshape(self.lstm.weight_hh_l0, (4, self.size, self.size))),
+            ('b', _reshape(self.lstm.bias_ih_l0, (4, self.size)))])
+        return res
+
+
+class GruMod(nn.Module):
+    """Guppy-compatible GRU (layers.py:609-725): cuDNN 'linear before reset'
+    form with the hidden bias frozen at zero."""
+
+    def __init__(self, insize, size, has_bias=True):
+        super().__init__()
+        self.cudnn_gru = nn.GRU(insize, size, bias=has_bias)
+        self.insize = insize
+        self.size = size
+        self.has_bias = has_bias
+        self._disable_state_bias()
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for name, param in self.named_parameters():
+            shape = list(param.shape)
+            if 'weight_hh' in name or 'weight_ih' in name:
+                init_(param, orthonormal_matrix(*shape))
+            else:
+                init_(param, truncated_normal(shape, sd=0.5))
+
+    def _disable_state_bias(self):
+        for name, param in self.cudnn_gru.named_parameters():
+            if 'bias_hh' in name:
+                param.requires_grad = False
+                param.data.zero_()
+
+    def named_parameters(self, prefix='', recurse=True):
+        prefix = prefix + ('.' if prefix else '')
+        for name, param in self.cudnn_gru.named_parameters(recurse=recurse):
+            if 'bias_hh' not in name:
+                yield prefix + name, param
+
+    def forward(self, x, reverse=False):
+        m = self.cudnn_gru
+        return _Recurrence.apply(x, m.weight_ih_l0, m.weight_hh_l0,
+                                 m.bias_ih_l0 if self.has_bias else None, _CELL_GRU, reverse)
+
+    def json(self):
+        res = OrderedDict([('type', "GruMod"), ('activation', "tanh"), ('gate', "sigmoid"),
+                           ('size', self.size), ('insize', self.insize),
+                           ('bias', self.has_bias)])
+        iW = _cudnn_to_guppy_gru(self.cudnn_gru.weight_ih_l0)
+        sW = _cudnn_to_guppy_gru(self.cudnn_gru.weight_hh_l0)
+        b = _cudnn_to_guppy_gru(self.cudnn_gru.bias_ih_l0)
+        res['params'] = OrderedDict([
+            ('iW', _reshape(iW, (3, self.size, self.insize))),
+            ('sW', _reshape(sW, (3, self.size, self.size))),
+            ('b', _reshape(b, (3, self.size)))])
+        return res
+
+
+def _cudnn_to_guppy_gru(p):
+    """cuDNN (r, z, n) -> Guppy (z, r, n) ordering (layers.py:728-741)."""
+    x, y, z = torch.chunk(p, 3)
+    return torch.cat([y, x, z], 0)
+
+
+class Reverse(nn.Module):
+    """Run the enclosed layer backwards in time (layers.py:117-153).  The
+    recurrent layers of this package take the direction as a flag, which saves
+    the two flipped copies of the activation tensor; any other layer is wrapped
+    between two flips as in the reference."""
+
+    def __init__(self, layer):
+        super().__init__()
+        self.layer = layer
+
+    def forward(self, x):
+        if isinstance(self.layer, (Lstm, GruMod)):
+            return self.layer(x, reverse=True)
+        return torch.flip(self.layer(torch.flip(x, (0,))), (0,))
+
+    def json(self):
+        return OrderedDict([('type', "reverse"), ('sublayers', self.layer.json())])
+
+
+class Serial(nn.Module):
+    """Apply layers one after the other (layers.py:944-982)."""
+
+    def __init__(self, layers):
+        super().__init__()
+        self.sublayers = nn.ModuleList(layers)
+
+    def forward(self, x):
+        for layer in self.sublayers:
+            x = layer(x)
+        return x
+
+    def json(self):
+        return OrderedDict([('type', "serial"),
+                            ('sublayers', [layer.json() for layer in self.sublayers])])
+
+
+class Convolution(nn.Module):
+    """1D convolution over time for [T, N, F] tensors (layers.py:744-850)."""
+
+    def __init__(self, insize, size, winlen, stride=1, pad=None, fun=activation.tanh,
+                 has_bias=True):
+        super().__init__()
+        self.has_bias = has_bias
+        self.insize = insize
+        self.size = size
+        self.stride = stride
+        self.winlen = winlen
+        if pad is None:
+            pad = (winlen // 2, (winlen - 1) // 2)
+        self.padding = pad
+        self.pad = nn.ConstantPad1d(pad, 0)
+        self.conv = nn.Conv1d(kernel_size=winlen, in_channels=insize, out_channels=size,
+                              stride=stride, bias=has_bias)
+        self.activation = fun
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        winit = orthonormal_matrix(self.conv.weight.shape[0],
+                                   int(np.prod(self.conv.weight.shape[1:])))
+        init_(self.conv.weight, winit.reshape(self.conv.weight.shape))
+        if self.has_bias:
+            init_(self.conv.bias, truncated_normal(list(self.conv.bias.shape), sd=0.5))
+
+    def forward(self, x):
+        x = x.permute(1, 2, 0)
+        out = self.activation(self.conv(self.pad(x)))
+        return out.permute(2, 0, 1)
+
+    def json(self):
+        res = OrderedDict([("type", "convolution"), ("insize", self.insize),
+                           ("size", self.size), ("bias", self.has_bias),
+                           ("winlen", self.conv.kernel_size[0]),
+                           ("stride", self.conv.stride[0]), ("padding", self.padding),
+                           ("activation", self.activation.__name__)])
+        res['params'] = OrderedDict(
+            [("W", self.conv.weight)] + [("b", self.conv.bias)] if self.has_bias else [])
+        return res
+
+
+class GlobalNormFlipFlop(nn.Module):
+    """scale * fun(x W + b) transition scores (layers.py:1316-1411); global
+    normalisation is the loss function's job."""
+
+    def __init__(self, insize, nbase, has_bias=True, fun=activation.tanh, scale=5.0):
+        super().__init__()
+        self.insize = insize
+        self.nbase = nbase
+        self.size = flipflopfings.nstate_flipflop(nbase)
+        self.activation = fun
+        self.has_bias = has_bias
+        self.linear = nn.Linear(insize, self.size, bias=has_bias)
+        self.reset_parameters()
+        self.scale = scale
+
+    def json(self):
+        res = OrderedDict([('type', 'GlobalNormTwoState'), ('size', self.size),
+                           ('insize', self.insize), ('bias', self.has_bias),
+                           ('scale', self.scale), ("activation", self.activation.__name__)])
+        res['params'] = OrderedDict(
+            [('W', self.linear.weight)] + [('b', self.linear.bias)] if self.has_bias else [])
+        return res
+
+    def reset_parameters(self):
+        init_(self.linear.weight, orthonormal_matrix(*list(self.linear.weight.shape)))
+        if self.has_bias:
+            init_(self.linear.bias, truncated_normal(list(self.linear.bias.shape), sd=0.5))
+
+    def forward(self, x):
+        return self.scale * self.activation(self.linear(x))
+
+
+class GlobalNormFlipFlopCatMod(nn.Module):
+    """Flip-flop transition scores plus a categorical modified-base stream
+    (layers.py:1414-1640).  Output columns: 2*ncan*(ncan+1) transition scores,
+    then per-canonical-base log-softmax groups (canonical first)."""
+
+    def compute_label_conversions(self):
+        can_labels, mod_labels = [], []
+        can_grouped_mods = dict((can_b, 0) for can_b in self.can_bases)
+        for b, can_b in zip(self.alphabet, self.collapse_alphabet):
+            can_labels.append(self.can_bases.find(can_b))
+            if b in self.can_bases:
+                mod_labels.append(0)
+            else:
+                can_grouped_mods[can_b] += 1
+                mod_labels.append(can_grouped_mods[can_b])
+        self.can_labels = np.array(can_labels)
+        self.mod_labels = np.array(mod_labels)
+
+    def compute_layer_mods_info(self):
+        self.output_alphabet = ''
+        for can_b in self.can_bases:
+            self.output_alphabet += can_b
+            for b, can_bi in zip(self.alphabet, self.collapse_alphabet):
+                if can_bi == can_b and b != can_b:
+                    self.output_alphabet += b
+        self.ordered_mod_long_names = (
+            None if self.mod_long_names is None else
+            [self.mod_name_conv[b] for b in self.alphabet if b in self.mod_bases])
+        self.can_nmods = np.array([
+            sum(b == can_b for b in self.collapse_alphabet) - 1 for can_b in self.can_bases])
+        self.can_mods_offsets = np.cumsum(np.concatenate(
+            [[0], self.can_nmods + 1])).astype(np.int32)
+        self.can_indices = []
+        curr_n_mods = 0
+        for bi_nmods in self.can_nmods:
+            self.can_indices.append(np.concatenate([
+                [0], np.arange(curr_n_mods + 1, curr_n_mods + 1 + bi_nmods)]))
+            curr_n_mods += bi_nmods
+
+    def __init__(self, insize, alphabet_info, has_bias=True):
+        super().__init__()
+        self.insize = insize
+        self.has_bias = has_bias
+        self.alphabet = alphabet_info.alphabet
+        self.collapse_alphabet = alphabet_info.collapse_alphabet
+        self.mod_long_names = alphabet_info.mod_long_names
+        self.mod_name_conv = alphabet_info.mod_name_conv
+        self.can_bases = alphabet_info.can_bases
+        self.mod_bases = alphabet_info.mod_bases
+        self.ncan_base = alphabet_info.ncan_base
+        self.nmod_base = alphabet_info.nmod_base
+        self.compute_label_conversions()
+        self.compute_layer_mods_info()
+        self.ntrans_states = 2 * self.ncan_base * (self.ncan_base + 1)
+        self.size = self.ntrans_states + 1 + self.nmod_base
+        self.lsm = nn.LogSoftmax(2)
+        self.linear = nn.Linear(insize, self.size, bias=self.has_bias)
+        self.reset_parameters()
+
+    @property
+    def nbase(self):
+        return self.ncan_base
+
+    def json(self):
+        res = OrderedDict([('type', 'GlobalNormTwoStateCatMod'), ('size', self.size),
+                           ('insize', self.insize), ('bias', self.has_bias),
+                           ('can_nmods', self.can_nmods),
+                           ('output_alphabet', self.output_alphabet),
+                           ('modified_base_long_names', self.ordered_mod_long_names)])
+        res['params'] = OrderedDict(
+            [('W', self.linear.weight)] + [('b', self.linear.bias)] if self.has_bias else [])
+        return res
+
+    def reset_parameters(self):
+        init_(self.linear.weight, orthonormal_matrix(*list(self.linear.weight.shape)))
+        if self.has_bias:
+            init_(self.linear.bias, truncated_normal(list(self.linear.bias.shape), sd=0.5))
+
+    def get_softmax_cat_mods(self, cat_mod_scores):
+        mod_layers = []
+        for lab_indices in self.can_indices:
+            mod_layers.append(self.lsm(cat_mod_scores[:, :, lab_indices]))
+        return torch.cat(mod_layers, dim=2)
+
+    def forward(self, x):
+        y = self.linear(x)
+        trans_scores = 5.0 * activation.tanh(y[:, :, :self.ntrans_states])
+        cat_mod_scores = y[:, :, self.ntrans_states:]
+        assert cat_mod_scores.shape[2] == self.nmod_base + 1, (
+            'Invalid scores provided to forward:  Expected: {}  got: {}'.format(
+                self.nmod_base + 1, cat_mod_scores.shape[2]))
+        cat_mod_scores = self.get_softmax_cat_mods(cat_mod_scores)
+        assert cat_mod_scores.shape[2] == self.nmod_base + self.ncan_base, (
+            'Invalid softmax categorical mod scores:  Expected: {}  got: {}'.format(
+                self.nmod_base + self.ncan_base, cat_mod_scores.shape[2]))
+        return torch.cat((trans_scores, cat_mod_scores), dim=2)
+
+
+def is_cat_mod_model(net):
+    """layers.py:1643-1656"""
+    assert isinstance(net, Serial)
+    return isinstance(net.sublayers[-1], GlobalNormFlipFlopCatMod)
+
+
+# ---------------------------------------------------------------------------
+# partition function
+class LogZ(torch.autograd.Function):
+    """log partition function of the flip-flop CRF and its gradient, one pass
+    over the scores (replaces cupy_extensions/flipflop.py:338-354)."""
+
+    @staticmethod
+    def forward(ctx, scores):
+        _lib.require_cuda(scores, 'scores')
+        lib = _lib.lib()
+        T, N, S = scores.shape
+        nbase = flipflopfings.nbase_flipflop(S)
+        x = scores.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        # a [:, :, :S] view of a wider contiguous tensor is used in place
+        if x.stride(2) == 1 and x.stride(0) == N * x.stride(1) and x.stride(1) >= S:
+            ld = x.stride(1)
+        else:
+            x = x.contiguous()
+            ld = S
+        device = x.device
+        logz = torch.empty(N, dtype=torch.float32, device=device)
+        want_grad = scores.requires_grad
+        grad = torch.empty(T, N, S, dtype=torch.float32, device=device) if want_grad else None
+        ws = _lib.workspace(lib.ty_flipflop_logz_workspace_bytes(nbase, T, N), device)
+        rc = lib.ty_flipflop_logz(_lib.ptr(x), ld, T, N, nbase, 1.0, _lib.ptr(logz), 1.0,
+                                  _lib.ptr(grad), S, 0, _lib.ptr(ws), ws.numel(),
+                                  _lib.stream_ptr(device))
+        _lib.check(rc, 'ty_flipflop_logz')
+        if want_grad:
+            ctx.save_for_backward(grad)
+        return logz
+
+    @staticmethod
+    def backward(ctx, g):
+        grad, = ctx.saved_tensors
+        return grad * g[:, None]
+
+
+def flipflop_logpartition(x, _never_use_cupy=False):
+    """Log-partition function of the flip-flop model, [T, N, S] -> [N]
+    (layers.py:1875-1890).  `_never_use_cupy` is accepted for signature
+    compatibility; there is a single device implementation."""
+    return LogZ.apply(x)
+
+
+def log_partition_flipflop(scores):
+    """[T, N, S] -> [N, 1] (layers.py:1277-1299)"""
+    return LogZ.apply(scores).unsqueeze(1)
+
+
+def global_norm_flipflop(scores):
+    """scores - logZ / T (layers.py:1302-1313)"""
+    T = scores.shape[0]
+    return scores - log_partition_flipflop(scores) / np.float32(T)

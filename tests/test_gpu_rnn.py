@@ -1,0 +1,181 @@
+"""GPU tests of the persistent LSTM / GRU kernels (csrc/rnn.cu).
+
+Two references, both plain PyTorch:
+  * `emulated`: the same recurrence with W_hh and h_{t-1} rounded to bf16 for
+    the recurrent product (what the kernel computes) -- tight tolerance;
+  * torch.nn.LSTM / nn.GRU in fp32 with bias_hh = 0 (what the reference's
+    `Lstm` / `GruMod` wrap, taiyaki/layers.py:515,633) -- tolerance of a bf16
+    recurrent product, stated below.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    from taiyaki_b200 import _lib
+    _lib.lib()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device('cuda:0')
+
+
+def q(x, emulate):
+    return x.bfloat16().float() if emulate else x
+
+
+def ref_recurrence(cell, xproj, w_hh, reverse, emulate=True):
+    """xproj [T,N,G*H] (already x W_ih^T + b_ih) -> y [T,N,H]; autograd-capable."""
+    T, N, GH = xproj.shape
+    H = w_hh.shape[1]
+    W = q(w_hh, emulate)
+    h = xproj.new_zeros(N, H)
+    c = xproj.new_zeros(N, H)
+    ys = [None] * T
+    order = range(T - 1, -1, -1) if reverse else range(T)
+    for t in order:
+        hh = torch.matmul(q(h, emulate), W.t())
+        if cell == 'lstm':
+            g = xproj[t] + hh
+            i, f, gg, o = g.chunk(4, 1)
+            i, f, gg, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(gg), torch.sigmoid(o)
+            c = f * c + i * gg
+            h = o * torch.tanh(c)
+        else:
+            xr, xz, xn = xproj[t].chunk(3, 1)
+            hr, hz, hn = hh.chunk(3, 1)
+            r, z = torch.sigmoid(xr + hr), torch.sigmoid(xz + hz)
+            n = torch.tanh(xn + r * hn)
+            h = (1 - z) * n + z * h
+        ys[t] = h
+    return torch.stack(ys, 0)
+
+
+def kernel_forward(cell, xproj, w_hh, reverse):
+    from taiyaki_b200 import _lib
+    lib = _lib.lib()
+    T, N, GH = xproj.shape
+    H = w_hh.shape[1]
+    code = 0 if cell == 'lstm' else 1
+    y = torch.empty(T, N, H, device=xproj.device)
+    reserve = torch.empty(lib.ty_rnn_reserve_bytes(code, T, N, H) // 4, device=xproj.device)
+    fn = lib.ty_lstm_forward if cell == 'lstm' else lib.ty_gru_forward
+    rc = fn(_lib.ptr(xproj), _lib.ptr(w_hh), T, N, H, int(reverse), _lib.ptr(y),
+            _lib.ptr(reserve), _lib.stream_ptr(xproj.device))
+    _lib.check(rc, 'forward')
+    return y, reserve
+
+
+def kernel_backward(cell, dy, w_hh, reverse, y, reserve):
+    from taiyaki_b200 import _lib
+    lib = _lib.lib()
+    T, N, H = dy.shape
+    G = 4 if cell == 'lstm' else 3
+    dx = torch.empty(T, N, G * H, device=dy.device)
+    if cell == 'lstm':
+        rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, int(reverse),
+                                  _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dx),
+                                  _lib.stream_ptr(dy.device))
+        dhn = None
+    else:
+        dhn = torch.empty(T, N, H, device=dy.device)
+        rc = lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, int(reverse),
+                                 _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dx), _lib.ptr(dhn),
+                                 _lib.stream_ptr(dy.device))
+    _lib.check(rc, 'backward')
+    return dx, dhn
+
+
+@pytest.mark.parametrize('cell', ['lstm', 'gru'])
+@pytest.mark.parametrize('H,N,T,reverse', [
+    (256, 8, 24, False), (256, 13, 17, True), (64, 3, 9, False), (128, 16, 11, True),
+    (192, 9, 7, False)])
+def test_forward_vs_emulated(dev, cell, H, N, T, reverse):
+    torch.manual_seed(H + N + T)
+    G = 4 if cell == 'lstm' else 3
+    xproj = torch.randn(T, N, G * H, device=dev)
+    w_hh = torch.randn(G * H, H, device=dev) / np.sqrt(H)
+    y, _ = kernel_forward(cell, xproj, w_hh, reverse)
+    ref = ref_recurrence(cell, xproj, w_hh, reverse, emulate=True)
+    torch.cuda.synchronize()
+    err = (y - ref).abs().max().item()
+    assert err < 2e-3, err       # bf16 rounding of h can flip by one ulp between the two
+    # against the un-rounded recurrence: the cost of the bf16 recurrent product
+    ref32 = ref_recurrence(cell, xproj, w_hh, reverse, emulate=False)
+    assert (y - ref32).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize('cell', ['lstm', 'gru'])
+@pytest.mark.parametrize('H,N,T,reverse', [(256, 8, 20, False), (256, 11, 13, True),
+                                           (64, 5, 8, True)])
+def test_backward_vs_autograd_of_emulated(dev, cell, H, N, T, reverse):
+    torch.manual_seed(7 + H + N)
+    G = 4 if cell == 'lstm' else 3
+    xproj = torch.randn(T, N, G * H, device=dev, requires_grad=True)
+    w_hh = torch.randn(G * H, H, device=dev) / np.sqrt(H)
+    dy = torch.randn(T, N, H, device=dev)
+    y, reserve = kernel_forward(cell, xproj.detach(), w_hh, reverse)
+    dx, dhn = kernel_backward(cell, dy, w_hh, reverse, y, reserve)
+    ref = ref_recurrence(cell, xproj, w_hh, reverse, emulate=True)
+    ref.backward(dy)
+    torch.cuda.synchronize()
+    scale = xproj.grad.abs().max().item()
+    err = (dx - xproj.grad).abs().max().item()
+    # the kernel also rounds the gate gradients to bf16 for the recurrent product
+    assert err < 3e-2 * scale, (err, scale)
+    rel = ((dx - xproj.grad).norm() / xproj.grad.norm()).item()
+    assert rel < 1e-2, rel
+
+
+@pytest.mark.parametrize('cell', ['lstm', 'gru'])
+@pytest.mark.parametrize('reverse', [False, True])
+def test_module_vs_torch_nn(dev, cell, reverse):
+    """Lstm / GruMod modules (forward + all parameter gradients) against
+    torch.nn.LSTM / nn.GRU fp32 with the same weights."""
+    from taiyaki_b200 import layers
+    torch.manual_seed(3)
+    np.random.seed(3)
+    T, N, I, H = 30, 8, 256, 256
+    mod = (layers.Lstm(I, H) if cell == 'lstm' else layers.GruMod(I, H)).to(dev)
+    nnmod = (torch.nn.LSTM(I, H) if cell == 'lstm' else torch.nn.GRU(I, H)).to(dev)
+    src = mod.lstm if cell == 'lstm' else mod.cudnn_gru
+    nnmod.load_state_dict(src.state_dict())
+    x = torch.randn(T, N, I, device=dev)
+    x1 = x.clone().requires_grad_(True)
+    x2 = x.clone().requires_grad_(True)
+    dy = torch.randn(T, N, H, device=dev)
+    y1 = layers.Reverse(mod)(x1) if reverse else mod(x1)
+    y1.backward(dy)
+    if reverse:
+        y2 = torch.flip(nnmod(torch.flip(x2, (0,)))[0], (0,))
+    else:
+        y2 = nnmod(x2)[0]
+    y2.backward(dy)
+    torch.cuda.synchronize()
+    assert (y1 - y2).abs().max().item() < 3e-2
+    for (n1, p1), (n2, p2) in zip(src.named_parameters(), nnmod.named_parameters()):
+        if 'bias_hh' in n1:
+            assert p1.grad is None
+            continue
+        rel = ((p1.grad - p2.grad).norm() / p2.grad.norm()).item()
+        assert rel < 3e-2, (n1, rel)
+    rel = ((x1.grad - x2.grad).norm() / x2.grad.norm()).item()
+    assert rel < 3e-2, rel
+
+
+def test_long_sequence_stability(dev):
+    """800 steps (BASELINE config A): outputs stay finite and track fp32."""
+    torch.manual_seed(0)
+    T, N, H = 800, 16, 256
+    xproj = torch.randn(T, N, 4 * H, device=dev)
+    w_hh = torch.randn(4 * H, H, device=dev) / np.sqrt(H)
+    y, _ = kernel_forward('lstm', xproj, w_hh, False)
+    ref = ref_recurrence('lstm', xproj, w_hh, False, emulate=False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert (y - ref).abs().max().item() < 8e-2
+    assert (y - ref).abs().mean().item() < 5e-3

@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Kernel-level timings on one GPU (CUDA events, warm-up, L2 flush between
+iterations).  Writes JSON lines to gpurun_out/microbench.jsonl.  Not the
+contract benchmark (that is bench.py); this is the tuning loop."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle  # noqa: E402  (synthetic input generators only)
+from taiyaki_b200 import _lib, ctc, layers  # noqa: E402
+
+dev = torch.device('cuda:0')
+OUT = os.path.join(ROOT, 'gpurun_out', 'microbench.jsonl')
+os.makedirs(os.path.dirname(OUT), exist_ok=True)
+_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        _flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def emit(**kw):
+    print(json.dumps(kw))
+    with open(OUT, 'a') as f:
+        f.write(json.dumps(kw) + '\n')
+
+
+def bench_crf(nblk, nbatch, ntrans, stride, tag):
+    scores = torch.tensor(oracle.synth_scores(nblk, nbatch, ntrans, seed=0), device=dev)
+    seqs, seqlen, raw = oracle.synth_seqs(nblk, nbatch, stride=stride, seed=1)
+    seqs_t, seqlen_t = torch.tensor(seqs), torch.tensor(seqlen)
+    alg_bytes = 2 * ntrans * 4 * nblk * nbatch
+    for P in ([1, 2, 4, 8] if nblk <= 2000 else [4, 8]):
+        os.environ['TY_CRF_P'] = str(P)
+        try:
+            med, mn = timeit(lambda: ctc.crf_flipflop_cost_grad(scores, seqs_t, seqlen_t, 1.0, True))
+        except Exception as e:
+            emit(what='crf_grad', tag=tag, P=P, error=str(e))
+            continue
+        emit(what='crf_grad(indices+chain+post)', tag=tag, nblk=nblk, N=nbatch, S=ntrans, P=P,
+             ms_median=med, ms_min=mn, alg_GBps=alg_bytes / med / 1e6,
+             mean_L=float(np.mean(seqlen)))
+    os.environ.pop('TY_CRF_P', None)
+    med, mn = timeit(lambda: ctc.crf_flipflop_cost_grad(scores, seqs_t, seqlen_t, 1.0, False))
+    emit(what='crf_cost_only', tag=tag, nblk=nblk, N=nbatch, ms_median=med, ms_min=mn)
+    x = scores[:, :, :40]
+    xg = x.detach().clone().requires_grad_(True)
+    med, mn = timeit(lambda: layers.flipflop_logpartition(xg))
+    emit(what='logz+posterior', tag=tag, nblk=nblk, N=nbatch, ms_median=med, ms_min=mn)
+    med, mn = timeit(lambda: layers.flipflop_logpartition(x))
+    emit(what='logz_only', tag=tag, nblk=nblk, N=nbatch, ms_median=med, ms_min=mn)
+
+
+def bench_rnn(cell, T, N, H, tag):
+    torch.manual_seed(0)
+    mod = (layers.Lstm(H, H) if cell == 'lstm' else layers.GruMod(H, H)).to(dev)
+    nnmod = (torch.nn.LSTM(H, H) if cell == 'lstm' else torch.nn.GRU(H, H)).to(dev)
+    x = torch.randn(T, N, H, device=dev, requires_grad=True)
+    dy = torch.randn(T, N, H, device=dev)
+
+    def ours_fwd():
+        with torch.no_grad():
+            mod(x)
+
+    def ours_fb():
+        y = mod(x)
+        y.backward(dy)
+
+    def cudnn_fwd():
+        with torch.no_grad():
+            nnmod(x)
+
+    def cudnn_fb():
+        y = nnmod(x)[0]
+        y.backward(dy)
+
+    for name, fn in [('ours_fwd', ours_fwd), ('ours_fwd+bwd', ours_fb),
+                     ('cudnn_fwd', cudnn_fwd), ('cudnn_fwd+bwd', cudnn_fb)]:
+        try:
+            med, mn = timeit(fn, iters=5, warmup=2)
+            emit(what='rnn_layer', cell=cell, impl=name, tag=tag, T=T, N=N, H=H, ms_median=med,
+                 ms_min=mn, us_per_step=1e3 * med / T)
+        except Exception as e:
+            emit(what='rnn_layer', cell=cell, impl=name, tag=tag, error=str(e)[:300])
+    # recurrence kernel alone (no projections)
+    lib = _lib.lib()
+    G = 4 if cell == 'lstm' else 3
+    code = 0 if cell == 'lstm' else 1
+    xproj = torch.randn(T, N, G * H, device=dev)
+    w_hh = torch.randn(G * H, H, device=dev) / np.sqrt(H)
+    y = torch.empty(T, N, H, device=dev)
+    reserve = torch.empty(lib.ty_rnn_reserve_bytes(code, T, N, H) // 4, device=dev)
+    dxp = torch.empty(T, N, G * H, device=dev)
+    dhn = torch.empty(T, N, H, device=dev)
+    st = _lib.stream_ptr(dev)
+    if cell == 'lstm':
+        f = lambda: lib.ty_lstm_forward(_lib.ptr(xproj), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), st)
+        b = lambda: lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxp), st)
+    else:
+        f = lambda: lib.ty_gru_forward(_lib.ptr(xproj), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), st)
+        b = lambda: lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxp), _lib.ptr(dhn), st)
+    for name, fn in [('kernel_fwd', f), ('kernel_bwd', b)]:
+        med, mn = timeit(fn, iters=5, warmup=2)
+        emit(what='rnn_kernel', cell=cell, impl=name, tag=tag, T=T, N=N, H=H, ms_median=med,
+             ms_min=mn, us_per_step=1e3 * med / T)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['crf', 'rnn']
+    t0 = time.time()
+    if 'crf' in which:
+        bench_crf(800, 64, 40, 5, 'A')
+        bench_crf(2000, 64, 45, 2, 'B')
+    if 'rnn' in which:
+        bench_rnn('lstm', 800, 64, 256, 'A')
+        bench_rnn('gru', 2000, 64, 256, 'B')
+    if 'sweep' in which:
+        for nblk in (1000, 2000, 4000, 8000):
+            bench_crf(nblk, 64, 40, 5, 'E%d' % nblk)
+    emit(what='done', seconds=time.time() - t0)
