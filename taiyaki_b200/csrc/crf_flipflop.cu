@@ -89,9 +89,10 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
     }
 
     auto issue_row = [&](int k) {
-        if (k < nblk && tid < S) {
+        if (k < nblk) {
             const int t = DIR == 0 ? k : nblk - 1 - k;
-            cp_async4(&rows[k % kRing][tid], lp + (size_t)t * ld + tid);
+            for (int i = tid; i < S; i += blockDim.x)      // a block may be a single warp
+                cp_async4(&rows[k % kRing][i], lp + (size_t)t * ld + i);
         }
         cp_async_commit();
     };

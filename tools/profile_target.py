@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Short workload for ncu: each hot kernel a few times at BASELINE config A
+(nblk=800, N=64, S=40, H=256).  Usage under gpurun:
+  ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 2 \
+      -o gpurun_out/prof python tools/profile_target.py [crf|logz|rnn]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle  # noqa: E402
+from taiyaki_b200 import ctc, layers  # noqa: E402
+
+dev = torch.device('cuda:0')
+which = sys.argv[1:] or ['crf', 'logz', 'rnn']
+nblk, N = 800, 64
+scores = torch.tensor(oracle.synth_scores(nblk, N, 40, seed=0), device=dev)
+seqs, seqlen, _ = oracle.synth_seqs(nblk, N, stride=5, seed=1)
+reps = int(os.environ.get('TY_PROF_REPS', '2'))
+for _ in range(reps):
+    if 'crf' in which:
+        ctc.crf_flipflop_cost_grad(scores, torch.tensor(seqs), torch.tensor(seqlen), 1.0, True)
+    if 'logz' in which:
+        layers.flipflop_logpartition(scores.detach().requires_grad_(True))
+    if 'rnn' in which:
+        torch.manual_seed(0)
+        np.random.seed(0)
+        mod = layers.Lstm(256, 256).to(dev)
+        x = torch.randn(nblk, N, 256, device=dev, requires_grad=True)
+        y = mod(x)
+        y.backward(torch.ones_like(y))
+torch.cuda.synchronize()
+print('profile target done')
