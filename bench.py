@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- signal-samples/s through the flip-flop CTC/CRF train step.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm, CPU)
+    torchrun --nproc-per-node N bench.py --gpus N ...        (N > 1, one rank per GPU)
+
+A step is one optimiser step of bin/train_flipflop.py's loop on one sub-batch
+(BASELINE.json configs[1]): mLstm_flipflop, size 256, stride 5, chunk length
+T_sig = 4000 samples (nblk = 800), 64 chunks per GPU, 4-base flip-flop (S = 40),
+synthetic r9.4.1-like reads, random-init weights:
+    zero_grad -> net -> crf_flipflop_loss + flipflop_logpartition / nblk -> backward
+    -> gradient all-reduce (N > 1) -> clipping maxima -> AdamW.
+Weak scaling: every rank processes its own 64 chunks.
+
+Legs (all in one JSON line printed by rank 0):
+  value      K steps with the batches already resident in HBM; CUDA events,
+             barrier + synchronize on both sides, max over ranks.
+  e2e        the same K steps through taiyaki_b200.training.TrainStep from
+             pinned HOST batches: H2D of signal / labels and the D2H read of
+             loss + gradient maxima are inside the timed region.
+  roofline   CRF forward-backward launches (crf_chain_kernel + crf_grad_kernel)
+             timed with CUDA events on the launching stream inside the timed
+             steps: algorithmic bytes 2*S*4 per (block, chunk) / duration,
+             against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the reference's CPU path (stock torch CPU modules + the
+             reference's own C loss, oracle/ref_train_step.py) on a bounded
+             sample, rank 0 at N = 1 only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_SIG, NCHUNK, SIZE, STRIDE, NTRANS = 4000, 64, 256, 5, 40
+METRIC = 'signal_samples_per_sec_flipflop_train_step'
+WORKLOAD = 'mLstm_flipflop size256 stride5, T_sig=4000 (nblk=800), 64 chunks/GPU, S=40'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--ref-chunks', type=int, default=4,
+                    help='chunks per step of the CPU reference sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+            'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+            'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+            'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4),
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the train step on this box's
+    host cores, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import oracle, ref_train_step
+    oracle.build()
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    r = ref_train_step.time_reference('lstm', T_SIG, args.ref_chunks, steps, warmup, STRIDE)
+    sample = ('%d chunks x T_sig=%d per step, %d timed steps, torch CPU nn.LSTM + reference C '
+              'loss (%s)' % (args.ref_chunks, T_SIG, steps,
+                             'oracle/_ref' if r['reference_c'] else 'oracle port'))
+    line = {
+        'metric': METRIC, 'value': r['samples_per_s'], 'unit': 'samples/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'impl': 'reference',
+        'config': {'workload': WORKLOAD, 'sample': sample},
+        'cpu_baseline': {'value': r['samples_per_s'], 'unit': 'samples/s', 'cores': r['threads'],
+                         'kind': 'reference' if r['reference_c'] else 'port', 'sample': sample},
+        'e2e': {'value': r['samples_per_s'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from taiyaki_b200 import _lib, ctc, helpers, signal_mapping, training, chunk_selection
+    from taiyaki_b200.alphabet import AlphabetInfo
+
+    assert torch.cuda.is_available(), 'bench.py (our arm) needs a GPU; there is no CPU path'
+    _lib.lib()
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    seed = 1 + rank                       # train_flipflop.py:266-268
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+    # ---- model, optimiser (train_flipflop.py:332-429) ----
+    alphabet_info = AlphabetInfo('ACGT', 'ACGT')
+    net = helpers.load_model(os.path.join(ROOT, 'models', 'mLstm_flipflop.py'),
+                             model_metadata={'reverse': False, 'standardize': True},
+                             stride=STRIDE, winlen=19, insize=1, size=SIZE,
+                             alphabet_info=alphabet_info).to(device)
+    if world > 1:       # all ranks start from rank 0's weights (checkpoint_00000 in the reference)
+        for p in net.parameters():
+            dist.broadcast(p.data, 0)
+    net_info = training.NETWORK_INFO(net=net, net_clone=None,
+                                     metadata=training.parse_network_metadata(net),
+                                     stride=STRIDE)
+    optimiser = torch.optim.AdamW(net.parameters(), lr=4e-3, betas=(0.9, 0.999),
+                                  weight_decay=0.01, eps=1e-6)
+    step_fn = training.TrainStep(net_info, optimiser)
+    nparam = sum(p.numel() for p in net.parameters() if p.requires_grad)
+
+    # ---- synthetic batches through the reference's batching surface ----
+    reads = signal_mapping.synthetic_reads(48, seed=7 + rank)
+    fp = chunk_selection.sample_filter_parameters(reads, 200, T_SIG, 10.0, 10.0, 0.1, STRIDE, 1.1)
+    nbatches = 4
+    host_batches = list(training.prepare_random_batches(
+        reads, T_SIG, NCHUNK, nbatches, alphabet_info, fp, net_info, None))
+    assert all(b[4] == NCHUNK for b in host_batches)
+    dev_batches = []
+    for indata, seqs, seqlens, mod_cats, nb, rej in host_batches:
+        sl_dev = seqlens.to(device)
+        ctc.hint_lengths(sl_dev, int(seqlens.max()), int(seqlens.sum()))
+        dev_batches.append((indata.to(device), seqs.to(device), sl_dev, None, nb, rej))
+    h2d = int(sum(b[0].numel() * 4 + b[1].numel() * 8 + b[2].numel() * 8
+                  for b in host_batches) / nbatches)
+
+    def run(batches, steps, read_back):
+        out = None
+        for i in range(steps):
+            out = step_fn(iter([batches[i % len(batches)]]), sharpen=1.0, read_back=read_back)
+        return out
+
+    def timed(batches, steps, read_back):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = run(batches, steps, read_back)
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), out
+
+    K, W = args.steps, max(args.warmup, 3)
+    run(dev_batches, W, False)
+    run(host_batches, 2, True)
+    assert step_fn.flat.check_views(), 'gradient views detached from the flat buffer'
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.LAUNCHES
+    _lib.PROFILE = {}
+    ms_dev, _ = timed(dev_batches, K, False)
+    launches = _lib.LAUNCHES - launches0
+    prof = _lib.PROFILE
+    _lib.PROFILE = None
+    ms_e2e, out = timed(host_batches, K, True)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    loss = out[1]
+    assert np.isfinite(loss), 'non-finite loss'
+
+    samples_per_step = T_SIG * NCHUNK * world
+    value = samples_per_step * K / (ms_dev * 1e-3)
+    e2e = samples_per_step * K / (ms_e2e * 1e-3)
+
+    # ---- roofline of the CRF forward-backward launches ----
+    peak, peak_src = measured_peak()
+    nblk = -(-T_SIG // STRIDE)
+    alg_bytes = 2 * NTRANS * 4 * nblk * NCHUNK
+    crf_ms = [a.elapsed_time(b) for a, b in prof.get('crf_fwd_bwd', [])]
+    rnn_ms = [a.elapsed_time(b) for a, b in prof.get('rnn_fwd', [])]
+    crf_avg = float(np.mean(crf_ms)) if crf_ms else float('nan')
+    achieved = alg_bytes / (crf_avg * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'crf_chain_kernel + crf_grad_kernel (CRF fwd-bwd)',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes': alg_bytes,
+                'avg_launch_ms': crf_avg, 'launches_timed': len(crf_ms),
+                'share_of_step': crf_avg / (ms_dev / K)}
+    extra = {'rnn_fwd_kernel_ms_avg': float(np.mean(rnn_ms)) if rnn_ms else None,
+             'rnn_layers': 5, 'trainable_params': nparam, 'loss': loss}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle, ref_train_step
+            oracle.build()
+            r = ref_train_step.time_reference('lstm', T_SIG, args.ref_chunks, 2, 1, STRIDE)
+            cpu_baseline = {
+                'value': r['samples_per_s'], 'unit': 'samples/s', 'cores': r['threads'],
+                'kind': 'reference' if r['reference_c'] else 'port',
+                'sample': '%d chunks x T_sig=%d, 2 timed steps after 1 warm-up; stock torch CPU '
+                          'nn.LSTM stack + the reference C loss via oracle/_ref'
+                          % (args.ref_chunks, T_SIG)}
+        except Exception as e:     # the baseline is informational; never fail the bench on it
+            cpu_baseline = {'value': None, 'error': str(e)[:200]}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': K,
+        'warmup': W, 'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16 recurrent product / tf32 projections / f32 loss',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'chunks_per_gpu': NCHUNK, 'global_chunks': NCHUNK * world,
+                   'parallelism': 'dp%d' % world,
+                   'l2': 'per-step working set (activations + reserve, >2 GB) exceeds the 126 MB L2'},
+        'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 4 * (1 + len(step_fn.flat.params)),
+                'ms_per_step': ms_e2e / K},
+        'gpu_launches': launches,
+        'clocks': sampler.summary(),
+        'roofline': roofline,
+        'cpu_baseline': cpu_baseline,
+        'detail': extra,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -113,6 +113,36 @@ def require_cuda(t, name):
             % (name, t.device))
 
 
+#: number of kernels of THIS library launched since import (bench.py reports it)
+LAUNCHES = 0
+#: when not None, a dict name -> list of (start, end) CUDA events recorded around
+#: the named launches on the launching stream (bench.py's roofline leg)
+PROFILE = None
+
+
+def count_launches(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class timed:
+    """Record CUDA events around a group of launches when PROFILE is enabled."""
+
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record(torch.cuda.current_stream(self.device))
+            PROFILE.setdefault(self.name, []).append((self.a, self.b))
+
+
 _workspaces = {}
 
 

@@ -70,7 +70,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
@@ -105,10 +105,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 1/(1+2^(-x log2 e)): two SFU ops, relative error ~2^-22
+__device__ __forceinline__ float sigmoidf_(float x) {
+    return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
+// tanh(x) = 2 sigmoid(2x) - 1: absolute error ~2e-7, saturates cleanly
 __device__ __forceinline__ float tanhf_(float x) {
-    // 1 - 2/(e^{2x}+1): absolute error ~1e-7, saturates cleanly for |x| large
-    return 1.0f - 2.0f / (__expf(2.0f * x) + 1.0f);
+    return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f);
 }
 
 struct RnnArgs {
@@ -180,7 +193,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     cluster_sync_all();
 
     float cst[2] = {0.f, 0.f};    // LSTM cell state / GRU previous h (fp32)
-    uint32_t phase[2] = {0u, 0u};
+    uint32_t phase = 0u;          // bit b = parity to wait for on full[b]
 
     auto tindex = [&](int s) { return a.reverse ? T - 1 - s : s; };
     float xp[G][2], xn[G][2];
@@ -203,10 +216,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     for (int s = 0; s < T; s++) {
         const int t = tindex(s);
         const int cur = s & 1, nxt = cur ^ 1;
-        load_x(xn, s + 1);
         if (s > 0) {
-            mbar_wait(&full[cur], phase[cur]);
-            phase[cur] ^= 1u;
+            mbar_wait(&full[cur], (phase >> cur) & 1u);
+            phase ^= 1u << cur;
         }
 
         float acc[2][4][4];
@@ -265,6 +277,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             }
             if (valid) a.y[cell * H + unit] = hnew[col];
         }
+        load_x(xn, s + 1);     // after xp was consumed: a full step to land
 
         if (s + 1 < T) {
             // own slice of h_t into the local copy of the next buffer
@@ -349,7 +362,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     }
     cluster_sync_all();
 
-    uint32_t phase[2] = {0u, 0u};
+    uint32_t phase = 0u;
     float carry[2] = {0.f, 0.f};   // LSTM: dL/dc carried back; GRU: z * dL/dh carried back
     auto tindex = [&](int sf) { return a.reverse ? T - 1 - sf : sf; };   // forward step -> time
 
@@ -386,12 +399,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
         const int sf = T - 1 - s;
         const int t = tindex(sf);
         const int cur = s & 1, nxt = cur ^ 1;
-        load_in(nxt_in, s + 1);
-
         float dh[2] = {cur_in.dy[0], cur_in.dy[1]};
         if (s > 0) {
-            mbar_wait(&full[cur], phase[cur]);
-            phase[cur] ^= 1u;
+            mbar_wait(&full[cur], (phase >> cur) & 1u);
+            phase ^= 1u << cur;
             float sx = 0.f, sy = 0.f;
 #pragma unroll
             for (int j = 0; j < kCluster; j++) {
@@ -442,6 +453,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                     ds[2 * q + col][g * U + ul] = __float2bfloat16(dg[g][col]);
         }
 
+        load_in(nxt_in, s + 1);   // after this step's inputs were consumed
         if (s + 1 < T) {
             __syncthreads();
             if (tid == 0) mbar_arrive_expect_tx(&full[nxt], kCluster * U * kNB * 4);

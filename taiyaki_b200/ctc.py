@@ -41,9 +41,21 @@ def _as_device_i64(x, device):
     return x.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
 
 
+_LENGTH_HINTS = {}
+
+
+def hint_lengths(seqlen, max_len, total):
+    """Tell the ops the (max, sum) of a DEVICE-resident seqlen tensor so they
+    need not synchronise to read it back."""
+    _LENGTH_HINTS[id(seqlen)] = (seqlen, int(max_len), int(total))
+
+
 def _max_len(seqlen):
     """Longest sequence; free when seqlen lives on the host (the reference's
     batching hands over CPU tensors, train_flipflop.py:133-135)."""
+    hint = _LENGTH_HINTS.get(id(seqlen))
+    if hint is not None and hint[0] is seqlen:
+        return hint[1], hint[2]
     if not torch.is_tensor(seqlen):
         seqlen = torch.as_tensor(np.asarray(seqlen))
     return int(seqlen.max()) if seqlen.numel() else 0, int(seqlen.sum())
@@ -76,6 +88,7 @@ def build_indices(seqs, seqlen, nbase, device, mod_cats=None, can_mods_offsets=N
         _lib.ptr(off_d), _lib.ptr(w_d), _lib.ptr(move), _lib.ptr(stay), _lib.ptr(seqlen32),
         _lib.ptr(modmove), _lib.ptr(modfact), _lib.stream_ptr(device))
     _lib.check(rc, 'ty_flipflop_indices')
+    _lib.count_launches(1)
     return move, stay, seqlen32, modmove, modfact, max_len
 
 
@@ -92,12 +105,14 @@ def _run_crf(logprob, move, stay, modmove, modfact, seqlen32, max_len, sharpfact
     ws_bytes = lib.ty_crf_flipflop_workspace_bytes(ntrans, nblk, nbatch, max_len, int(want_grad))
     ws = _lib.workspace(ws_bytes, device)
     # cost = -score / nblk / sharp, grad = -G / nblk   (ctc.pyx:66,113,145)
-    rc = lib.ty_crf_flipflop(
-        _lib.ptr(lp), ntrans, nblk, nbatch, _lib.ptr(move), _lib.ptr(stay), _lib.ptr(modmove),
-        _lib.ptr(modfact), _lib.ptr(seqlen32), max_len, float(sharpfact), nsharp,
-        -1.0 / (nblk * float(sharpfact)), _lib.ptr(cost), -1.0 / nblk, _lib.ptr(grads),
-        _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device))
+    with _lib.timed('crf_fwd_bwd' if want_grad else 'crf_fwd', device):
+        rc = lib.ty_crf_flipflop(
+            _lib.ptr(lp), ntrans, nblk, nbatch, _lib.ptr(move), _lib.ptr(stay),
+            _lib.ptr(modmove), _lib.ptr(modfact), _lib.ptr(seqlen32), max_len, float(sharpfact),
+            nsharp, -1.0 / (nblk * float(sharpfact)), _lib.ptr(cost), -1.0 / nblk,
+            _lib.ptr(grads), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device))
     _lib.check(rc, 'ty_crf_flipflop')
+    _lib.count_launches(2 if want_grad else 1)
     if CHECK_FINITE:
         assert bool(torch.isfinite(cost).all()), _FINITE_MSG.format(cost.cpu().numpy())
         if grads is not None:

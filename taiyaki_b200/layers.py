@@ -105,9 +105,11 @@ class _Recurrence(torch.autograd.Function):
         reserve = torch.empty(lib.ty_rnn_reserve_bytes(cell, T, N, H) // 4,
                               dtype=torch.float32, device=x.device)
         fn = lib.ty_lstm_forward if cell == _CELL_LSTM else lib.ty_gru_forward
-        rc = fn(_lib.ptr(xproj), _lib.ptr(w_hh_c), T, N, H, int(reverse), _lib.ptr(y),
-                _lib.ptr(reserve), _lib.stream_ptr(x.device))
+        with _lib.timed('rnn_fwd', x.device):
+            rc = fn(_lib.ptr(xproj), _lib.ptr(w_hh_c), T, N, H, int(reverse), _lib.ptr(y),
+                    _lib.ptr(reserve), _lib.stream_ptr(x.device))
         _lib.check(rc, 'ty_rnn_forward')
+        _lib.count_launches(1)
         ctx.save_for_backward(x, w_ih, w_hh_c, y, reserve)
         ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H)
         return y
@@ -131,6 +133,7 @@ class _Recurrence(torch.autograd.Function):
                                      _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
                                      _lib.ptr(dhn), stream)
         _lib.check(rc, 'ty_rnn_backward')
+        _lib.count_launches(1)
         d2 = dxproj.view(T * N, G * H)
         # h_{t-1} of every step is y shifted by one step along the loop direction
         if reverse:
@@ -505,6 +508,7 @@ class LogZ(torch.autograd.Function):
                                   _lib.ptr(grad), S, 0, _lib.ptr(ws), ws.numel(),
                                   _lib.stream_ptr(device))
         _lib.check(rc, 'ty_flipflop_logz')
+        _lib.count_launches(2 if want_grad else 1)
         if want_grad:
             ctx.save_for_backward(grad)
         return logz

@@ -1,0 +1,219 @@
+"""One optimiser step of flip-flop training -- the functions of
+bin/train_flipflop.py that sit on the hot path, kept under their own names:
+
+  prepare_random_batches   train_flipflop.py:78-142   (host batching surface)
+  calculate_loss           train_flipflop.py:145-198  (net -> CRF loss + logZ/nblk -> backward)
+  apply_clipping           train_flipflop.py:201-212
+  FlatGradients            replaces DistributedDataParallel's bucketed all-reduce
+                           (train_flipflop.py:395-397) by ONE NCCL all-reduce of
+                           a flat fp32 gradient buffer per optimiser step.
+
+Differences from the reference are confined to where the work happens: scores
+stay on the device through the loss, and the per-tensor `float(max|grad|)` host
+round trips of apply_clipping become one device reduction and one copy.
+"""
+from collections import defaultdict, namedtuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import chunk_selection, ctc, flipflopfings, layers
+
+NETWORK_METADATA = namedtuple('NETWORK_METADATA', (
+    'reverse', 'standardize', 'is_cat_mod', 'can_mods_offsets', 'can_labels', 'mod_labels'))
+NETWORK_METADATA.__new__.__defaults__ = (None, None, None)
+NETWORK_INFO = namedtuple('NETWORK_INFO', ('net', 'net_clone', 'metadata', 'stride'))
+MOD_INFO = namedtuple('MOD_INFO', ('mod_cat_weights', 'mod_factor'))
+
+
+def parse_network_metadata(network):
+    """train_flipflop.py:67-75"""
+    if layers.is_cat_mod_model(network):
+        last = network.sublayers[-1]
+        return NETWORK_METADATA(network.metadata['reverse'], network.metadata['standardize'],
+                                True, last.can_mods_offsets, last.can_labels, last.mod_labels)
+    return NETWORK_METADATA(network.metadata['reverse'], network.metadata['standardize'], False)
+
+
+def prepare_random_batches(read_data, batch_chunk_len, sub_batch_size, target_sub_batches,
+                           alphabet_info, filter_params, net_info, log,
+                           select_strands_randomly=True, first_strand_index=0, pin=True):
+    """Generator of (indata [T,N,1] pinned fp32, seqs, seqlens, mod_cats,
+    sub_batch_size, rejections) -- train_flipflop.py:78-142."""
+    total_sub_batches = 0
+    revop = np.flip if net_info.metadata.reverse else np.array
+    while total_sub_batches < target_sub_batches:
+        chunk_batch, batch_rejections = chunk_selection.sample_chunks(
+            read_data, sub_batch_size, batch_chunk_len, filter_params,
+            standardize=net_info.metadata.standardize,
+            select_strands_randomly=select_strands_randomly,
+            first_strand_index=first_strand_index)
+        first_strand_index += sum(batch_rejections.values())
+        if len(chunk_batch) < sub_batch_size and log is not None:
+            log.write(('* Warning: only {} chunks passed filters (asked for {}).\n').format(
+                len(chunk_batch), sub_batch_size))
+        if not all(chunk.seq_len > 0.0 for chunk in chunk_batch):
+            raise Exception('Error: zero length sequence')
+        stacked_current = np.vstack([revop(chunk.current) for chunk in chunk_batch]).T
+        indata = torch.tensor(stacked_current, device='cpu', dtype=torch.float32).unsqueeze(2)
+        if pin and torch.cuda.is_available():
+            indata = indata.pin_memory()
+        seqs, seqlens = [], []
+        mod_cats = [] if net_info.metadata.is_cat_mod else None
+        for chunk in chunk_batch:
+            chunk_labels = revop(chunk.sequence)
+            seqlens.append(len(chunk_labels))
+            if net_info.metadata.is_cat_mod:
+                mod_cats.append(np.ascontiguousarray(net_info.metadata.mod_labels[chunk_labels]))
+                chunk_labels = np.ascontiguousarray(net_info.metadata.can_labels[chunk_labels])
+            seqs.append(flipflopfings.flipflop_code(
+                np.ascontiguousarray(chunk_labels).astype(np.int64), alphabet_info.ncan_base))
+        seqs = torch.tensor(np.concatenate(seqs), dtype=torch.long, device='cpu')
+        seqlens = torch.tensor(seqlens, dtype=torch.long, device='cpu')
+        if net_info.metadata.is_cat_mod:
+            mod_cats = torch.tensor(np.concatenate(mod_cats), dtype=torch.long, device='cpu')
+        total_sub_batches += 1
+        yield indata, seqs, seqlens, mod_cats, len(chunk_batch), batch_rejections
+
+
+def flipflop_loss(outputs, seqs, seqlens, sharpen, mod_cats=None, can_mods_offsets=None,
+                  mod_cat_weights=None):
+    """Per-chunk loss vector: CRF cost + logZ / nblk (train_flipflop.py:163-176)."""
+    nblk = float(outputs.shape[0])
+    ntrans = outputs.shape[2]
+    if mod_cats is not None:
+        lossvector = ctc.cat_mod_flipflop_loss(outputs, seqs, seqlens, mod_cats,
+                                               can_mods_offsets, mod_cat_weights, sharpen)
+        ntrans -= int(can_mods_offsets[-1])
+    else:
+        lossvector = ctc.crf_flipflop_loss(outputs, seqs, seqlens, sharpen)
+    return lossvector + layers.flipflop_logpartition(outputs[:, :, :ntrans]) / nblk
+
+
+def calculate_loss(net_info, batch_gen, sharpen, mod_cat_weights=None, mod_factor=None,
+                   calc_grads=False, device=None):
+    """train_flipflop.py:145-198.  Returns (chunk_count, mean loss as a DEVICE
+    tensor, samples, bases, rejection dict); the caller decides when to read
+    the loss back (one host sync per optimiser step instead of one per
+    sub-batch)."""
+    can_mods_offsets = net_info.metadata.can_mods_offsets
+    total_chunk_count = total_samples = total_bases = n_subbatches = 0
+    total_fval = None
+    rejection_dict = defaultdict(int)
+    device = device if device is not None else next(net_info.net.parameters()).device
+    for (indata, seqs, seqlens, mod_cats, sub_batch_size, batch_rejections) in batch_gen:
+        n_subbatches += 1
+        for k, v in batch_rejections.items():
+            rejection_dict[k] += v
+        total_chunk_count += sub_batch_size
+        with torch.set_grad_enabled(calc_grads):
+            outputs = net_info.net(indata.to(device, non_blocking=True))
+            if net_info.metadata.is_cat_mod:
+                lossvector = flipflop_loss(outputs, seqs, seqlens, sharpen, mod_cats,
+                                           can_mods_offsets, mod_cat_weights * mod_factor)
+            else:
+                lossvector = flipflop_loss(outputs, seqs, seqlens, sharpen)
+            loss = lossvector.mean()
+        if calc_grads:
+            loss.backward()
+        total_fval = loss.detach() if total_fval is None else total_fval + loss.detach()
+        total_samples += int(indata.nelement())
+        total_bases += ctc._max_len(seqlens)[1]     # host value (or a registered hint)
+    if calc_grads and n_subbatches > 1:
+        for p in net_info.net.parameters():
+            if p.grad is not None:
+                p.grad /= n_subbatches
+    return (total_chunk_count, total_fval / n_subbatches, total_samples, total_bases,
+            rejection_dict)
+
+
+class FlatGradients:
+    """All trainable gradients as views of one flat fp32 buffer.
+
+    `zero()` clears it, `all_reduce()` averages it across ranks with a single
+    collective (NCCL over NVLink on GPUs, gloo in the CPU tests).  Data
+    parallelism is the reference's only strategy (train_flipflop.py:255-268,
+    :395-397): chunks are independent and only the weight gradient is shared.
+    """
+
+    def __init__(self, parameters, process_group=None):
+        self.params = [p for p in parameters if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+
+    def zero(self):
+        self.flat.zero_()
+
+    def check_views(self):
+        """Autograd accumulates in place, so the views must still alias `flat`."""
+        base = self.flat.data_ptr()
+        return all(p.grad is not None and
+                   base <= p.grad.data_ptr() < base + self.flat.numel() * 4
+                   for p in self.params)
+
+    def all_reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
+
+    def grad_maxs(self):
+        """max|grad| per parameter tensor as ONE device tensor."""
+        return torch.stack(torch._foreach_norm([p.grad for p in self.params], float('inf')))
+
+
+def apply_clipping(net_info, grad_max_threshs, flat=None):
+    """Clip each parameter tensor by value at its threshold
+    (train_flipflop.py:201-212).  Returns the per-tensor maxima as a device
+    tensor (read back together with the loss)."""
+    parameters = flat.params if flat is not None else \
+        [p for p in net_info.net.parameters() if p.requires_grad]
+    grad_maxs = torch.stack(torch._foreach_norm([p.grad for p in parameters], float('inf')))
+    if grad_max_threshs is not None:
+        thr = torch.as_tensor(np.asarray(grad_max_threshs, dtype=np.float32),
+                              device=grad_maxs.device)
+        for p, t in zip(parameters, thr):
+            # clamp to [-t, t] is a no-op where max|grad| <= t
+            torch.minimum(torch.maximum(p.grad, -t, out=p.grad), t, out=p.grad)
+    return grad_maxs
+
+
+class TrainStep:
+    """zero_grad -> calculate_loss(calc_grads) -> all-reduce -> clipping ->
+    AdamW step (train_flipflop.py:570-578) as one callable."""
+
+    def __init__(self, net_info, optimiser, rolling_mads=None, lr_scheduler=None,
+                 mod_info=None):
+        self.net_info = net_info
+        self.optimiser = optimiser
+        self.rolling_mads = rolling_mads
+        self.lr_scheduler = lr_scheduler
+        self.mod_info = mod_info
+        self.flat = FlatGradients(net_info.net.parameters())
+        self.grad_max_threshs = None
+
+    def __call__(self, batch_gen, sharpen=1.0, mod_factor=1.0, read_back=True):
+        self.flat.zero()
+        mcw = None if self.mod_info is None else self.mod_info.mod_cat_weights
+        res = calculate_loss(self.net_info, batch_gen, sharpen, mcw, mod_factor,
+                             calc_grads=True)
+        self.flat.all_reduce()
+        grad_maxs = apply_clipping(self.net_info, self.grad_max_threshs, self.flat)
+        self.optimiser.step()
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+        loss_dev = res[1]
+        if not read_back:
+            return res, None, grad_maxs
+        # one device->host copy per optimiser step: loss and gradient maxima together
+        host = torch.cat([loss_dev.reshape(1), grad_maxs]).cpu().numpy()
+        if self.rolling_mads is not None:
+            self.grad_max_threshs = self.rolling_mads.update(host[1:])
+        return res, float(host[0]), host[1:]

@@ -1,0 +1,175 @@
+"""CPU tests of the host-side surface: batching (chunk_selection /
+signal_mapping / prepare_random_batches), flip-flop coding, the flat-gradient
+all-reduce over gloo with world_size 2, the CLI parser, and bench.py's
+reference arm plumbing."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_flipflopfings_mirror_matches_golden(kat):
+    from taiyaki_b200 import flipflopfings as fff
+    np.testing.assert_array_equal(fff.flipflop_code(kat['code_in0']), kat['code_out0'])
+    c = fff.flipflop_code(kat['code_in1'])
+    np.testing.assert_array_equal(c, kat['code_out1'])
+    np.testing.assert_array_equal(fff.move_indices(c), kat['code_move1'])
+    np.testing.assert_array_equal(fff.stay_indices(c), kat['code_stay1'])
+    assert fff.nstate_flipflop(4) == 40 and fff.nbase_flipflop(40) == 4
+    with pytest.raises(AssertionError):
+        fff.nbase_flipflop(45)
+
+
+def test_synthetic_reads_and_chunk_sampling():
+    from taiyaki_b200 import chunk_selection, signal_mapping
+    np.random.seed(0)
+    reads = signal_mapping.synthetic_reads(6, seed=3)
+    r = reads[0]
+    assert r.Ref_to_signal[0] == 0 and r.Ref_to_signal[-1] == len(r.Dacs)
+    assert np.all(np.diff(r.Ref_to_signal) >= 1)
+    fp = chunk_selection.sample_filter_parameters(reads, 40, 2000, 3.0, 10.0, 0.5, 5, 1.1)
+    assert 8.0 < fp.median_meandwell < 10.0
+    chunks, rej = chunk_selection.sample_chunks(reads, 12, 2000, fp)
+    assert len(chunks) == 12 and rej['pass'] == 12
+    for c in chunks:
+        assert c.sig_len == 2000 and 150 < c.seq_len < 300
+        assert abs(float(np.mean(c.current))) < 0.5
+    # too-short reads are rejected with the reference's reason string
+    short = reads[0].get_chunk_with_sample_length(10 ** 7)
+    assert short.reject_reason == 'tooshort' and not short.accepted
+    # the path-buffer filter (signal_mapping.py:699-703)
+    tight = fp._replace(path_buffer=100.0)
+    ch = reads[0].get_chunk_with_sample_length(2000)
+    ch.apply_filters(tight)
+    assert ch.reject_reason == 'pathbuffer'
+
+
+def test_prepare_random_batches_layout():
+    from taiyaki_b200 import chunk_selection, flipflopfings, signal_mapping, training
+    from taiyaki_b200.alphabet import AlphabetInfo
+    np.random.seed(1)
+    reads = signal_mapping.synthetic_reads(5, seed=4)
+    fp = chunk_selection.sample_filter_parameters(reads, 30, 1000, 3.0, 10.0, 0.5, 5, 1.1)
+    md = training.NETWORK_METADATA(False, True, False)
+    net_info = training.NETWORK_INFO(net=None, net_clone=None, metadata=md, stride=5)
+    gen = training.prepare_random_batches(reads, 1000, 7, 2, AlphabetInfo('ACGT', 'ACGT'), fp,
+                                          net_info, None, pin=False)
+    batches = list(gen)
+    assert len(batches) == 2
+    indata, seqs, seqlens, mod_cats, n, rej = batches[0]
+    assert indata.shape == (1000, 7, 1) and indata.dtype == torch.float32
+    assert seqs.dtype == torch.long and int(seqlens.sum()) == len(seqs) and mod_cats is None
+    s0 = seqs[:int(seqlens[0])].numpy()
+    assert s0.max() < 8
+    # flip-flop coded: no two equal consecutive codes
+    assert np.all(s0[1:] != s0[:-1])
+    assert flipflopfings.stay_indices(s0).max() < 40
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    from taiyaki_b200.training import FlatGradients
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+    net[2].bias.requires_grad = False            # a frozen parameter, like bias_hh
+    flat = FlatGradients(net.parameters())
+    torch.manual_seed(100 + rank)                # different data per rank
+    x = torch.randn(6, 5)
+    flat.zero()
+    net(x).pow(2).mean().backward()
+    assert flat.check_views()
+    local = flat.flat.clone()
+    flat.all_reduce()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    want = sum(gathered) / world
+    ok = torch.allclose(flat.flat, want, atol=1e-7)
+    maxs = flat.grad_maxs()
+    ok = ok and maxs.numel() == 3 and net[2].bias.grad is None
+    ok = ok and torch.allclose(maxs[0], net[0].weight.grad.abs().max())
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    mgr = ctx.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out[0] and out[1]
+
+
+def test_rolling_mad_and_med_mad():
+    from taiyaki_b200 import maths
+    rm = maths.RollingMAD(2, n_mads=1.0, window=5)
+    for i in range(4):
+        assert rm.update([1.0 + i, 10.0]) is None
+    thr = rm.update([5.0, 10.0])
+    assert thr.shape == (2,) and abs(thr[1] - 10.0) < 1e-6 and thr[0] > 3.0
+    med, mad = maths.med_mad(np.array([1.0, 2.0, 3.0, 4.0, 100.0]))
+    assert med == 3.0 and abs(mad - 1.4826) < 1e-6
+
+
+def test_train_cli_parser_defaults_match_reference():
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    import importlib
+    tf = importlib.import_module('train_flipflop')
+    a = tf.get_train_flipflop_parser().parse_args(['models/mLstm_flipflop.py', 'synthetic:10'])
+    # bin/_bin_argparse.py:9-208
+    assert (a.size, a.stride, a.winlen) == (384, 5, 19)
+    assert (a.chunk_len_min, a.chunk_len_max, a.min_sub_batch_size) == (3000, 8000, 128)
+    assert a.lr_max == 4e-3 and a.lr_min == 1e-4 and a.niteration == 150000
+    assert tuple(a.sharpen) == (1.0, 1.0, 25000) and a.gradient_clip_num_mads == 0
+    assert a.weight_decay == 0.01 and a.eps == 1e-6 and a.warmup_batches == 200
+
+
+def test_model_definition_files_build():
+    from taiyaki_b200 import helpers, layers
+    from taiyaki_b200.alphabet import AlphabetInfo
+    np.random.seed(0)
+    net = helpers.load_model(os.path.join(ROOT, 'models', 'mLstm_flipflop.py'), size=64,
+                             stride=5, winlen=19, insize=1,
+                             alphabet_info=AlphabetInfo('ACGT', 'ACGT'))
+    assert isinstance(net, layers.Serial) and len(net.sublayers) == 9
+    assert isinstance(net.sublayers[3], layers.Reverse)
+    names = [n for n, _ in net.named_parameters()]
+    assert 'sublayers.3.layer.lstm.weight_hh_l0' in names
+    cm = helpers.load_model(os.path.join(ROOT, 'models', 'mGru_cat_mod_flipflop.py'), size=64,
+                            stride=2, winlen=19, insize=1,
+                            alphabet_info=AlphabetInfo('ACGTZ', 'ACGTC', ['5mC']))
+    last = cm.sublayers[-1]
+    assert layers.is_cat_mod_model(cm) and last.size == 42   # linear outputs; forward emits 45
+    np.testing.assert_array_equal(last.can_mods_offsets, [0, 1, 3, 4, 5])
+    # full-size parameter count of the reference's mLstm_flipflop
+    big = helpers.load_model(os.path.join(ROOT, 'models', 'mLstm_flipflop.py'), size=256,
+                             stride=5, winlen=19, insize=1,
+                             alphabet_info=AlphabetInfo('ACGT', 'ACGT'))
+    assert sum(p.numel() for p in big.parameters()) == 2720400
+    assert sum(p.numel() for p in big.parameters() if p.requires_grad) == 2715280
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '1', '--ref-chunks', '1'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] in ('reference', 'port')
+    assert line['e2e']['h2d_bytes_per_step'] == 0
