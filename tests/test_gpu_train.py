@@ -1,0 +1,120 @@
+"""GPU tests of the assembled train step and the entry point."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    from taiyaki_b200 import _lib
+    _lib.lib()
+    return torch.device('cuda:0')
+
+
+def build(dev, model, size, alphabet):
+    from taiyaki_b200 import helpers, training
+    net = helpers.load_model(os.path.join(ROOT, 'models', model),
+                             model_metadata={'reverse': False, 'standardize': True},
+                             size=size, stride=5 if 'Lstm' in model else 2, winlen=19, insize=1,
+                             alphabet_info=alphabet).to(dev)
+    md = training.parse_network_metadata(net)
+    return training.NETWORK_INFO(net=net, net_clone=None, metadata=md,
+                                 stride=5 if 'Lstm' in model else 2)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
+
+
+@pytest.mark.parametrize('model,alpha', [('mLstm_flipflop.py', 'ACGT'), ('mGru_flipflop.py', 'ACGT'),
+                                         ('mGru_cat_mod_flipflop.py', 'ACGTZ')])
+def test_train_steps_reduce_loss(dev, model, alpha):
+    from taiyaki_b200 import chunk_selection, signal_mapping, training
+    from taiyaki_b200.alphabet import AlphabetInfo
+    np.random.seed(0)
+    torch.manual_seed(0)
+    ai = AlphabetInfo('ACGTZ', 'ACGTC', ['5mC']) if alpha == 'ACGTZ' else AlphabetInfo('ACGT', 'ACGT')
+    net_info = build(dev, model, 64, ai)
+    reads = signal_mapping.synthetic_reads(8, seed=2, mod_fraction=0.5 if alpha == 'ACGTZ' else 0.0)
+    fp = chunk_selection.sample_filter_parameters(reads, 50, 1000, 10.0, 10.0, 0.1,
+                                                  net_info.stride, 1.1)
+    opt = torch.optim.AdamW(net_info.net.parameters(), lr=2e-3, eps=1e-6)
+    mod_info = training.MOD_INFO(np.ones(ai.nbase, dtype=np.float32), None)
+    step = training.TrainStep(net_info, opt, mod_info=mod_info)
+    batches = list(training.prepare_random_batches(reads, 1000, 12, 1, ai, fp, net_info, None))
+    losses = []
+    for _ in range(25):
+        _, loss, gmax = step(iter(batches), sharpen=1.0, mod_factor=1.0)
+        assert np.isfinite(loss) and np.all(np.isfinite(gmax))
+        losses.append(loss)
+    assert step.flat.check_views()
+    assert losses[-1] < losses[0] - 0.05, losses[::6]
+
+
+def test_loss_and_grads_match_cpu_reference_network(dev, oracle):
+    """Whole step (network + loss) against the CPU reference restatement
+    (oracle/ref_train_step.py: stock torch modules + reference C loss) with the
+    same weights: loss within the tolerance of a bf16 recurrent product."""
+    from oracle import ref_train_step as ref
+    from taiyaki_b200 import training
+    from taiyaki_b200.alphabet import AlphabetInfo
+    np.random.seed(1)
+    torch.manual_seed(1)
+    net_info = build(dev, 'mLstm_flipflop.py', 64, AlphabetInfo('ACGT', 'ACGT'))
+    cpu = ref.ref_network('lstm', 64)
+    ours = net_info.net
+    # copy weights: conv x3, lstm x5, linear
+    for i in range(3):
+        cpu[i].conv.load_state_dict(ours.sublayers[i].conv.state_dict())
+    for i in range(3, 8):
+        layer = ours.sublayers[i].layer if hasattr(ours.sublayers[i], 'layer') else ours.sublayers[i]
+        cpu[i].rnn.load_state_dict({k: v.cpu() for k, v in layer.lstm.state_dict().items()})
+    cpu[8].linear.load_state_dict(ours.sublayers[8].linear.state_dict())
+    T_sig, N = 600, 6
+    x = torch.randn(T_sig, N, 1)
+    seqs, seqlen, _ = oracle.synth_seqs(T_sig // 5, N, stride=5, seed=5)
+    seqs, seqlen = torch.tensor(seqs), torch.tensor(seqlen)
+    out_cpu = cpu(x)
+    lv_cpu = ref.RefFlipFlopCRF.apply(out_cpu, seqs, seqlen, 1.0) + \
+        ref.log_partition_flipflop(out_cpu).squeeze(1) / out_cpu.shape[0]
+    lv_cpu.mean().backward()
+    out = ours(x.to(dev))
+    lv = training.flipflop_loss(out, seqs, seqlen, 1.0)
+    lv.mean().backward()
+    torch.cuda.synchronize()
+    assert (out.cpu() - out_cpu).abs().max().item() < 0.15     # scores span [-5, 5]
+    np.testing.assert_allclose(lv.detach().cpu().numpy(), lv_cpu.detach().numpy(), rtol=3e-2,
+                               atol=3e-2)
+    g1 = ours.sublayers[8].linear.weight.grad.cpu()
+    g2 = cpu[8].linear.weight.grad
+    assert ((g1 - g2).norm() / g2.norm()).item() < 5e-2
+    g1 = ours.sublayers[3].layer.lstm.weight_ih_l0.grad.cpu()
+    g2 = cpu[3].rnn.weight_ih_l0.grad
+    assert ((g1 - g2).norm() / g2.norm()).item() < 0.1
+
+
+def test_train_flipflop_entry_point(dev, tmp_path):
+    out = tmp_path / 'training'
+    cmd = [sys.executable, os.path.join(ROOT, 'bin', 'train_flipflop.py'), '--size', '64',
+           '--niteration', '60', '--warmup_batches', '10', '--chunk_len_min', '500',
+           '--chunk_len_max', '1000', '--min_sub_batch_size', '16', '--save_every', '50',
+           '--reporting_sub_batches', '2', '--seed', '1', '--quiet', '--overwrite',
+           '--outdir', str(out), os.path.join(ROOT, 'models', 'mGru_flipflop.py'), 'synthetic:12']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    batch = (out / 'batch.log').read_text().strip().splitlines()
+    assert len(batch) == 61                       # header + one line per iteration
+    first, last = float(batch[1].split('\t')[1]), float(batch[-1].split('\t')[1])
+    assert np.isfinite(last) and last < first
+    assert (out / 'model_final.checkpoint').exists()
+    assert (out / 'model_checkpoint_00001.checkpoint').exists()
+    assert 'ksample/s' in (out / 'model.log').read_text()
