@@ -4,27 +4,38 @@
 // modified-base term).
 //
 // Structure (DESIGN.md "CRF kernels"):
-//   crf_chain_kernel   one CTA per (chunk, direction).  The sequence positions
-//                      of the chunk are striped over the threads, P contiguous
-//                      positions per thread held in registers; the time loop is
-//                      the only sequential dimension.  Per step: gather the two
-//                      transition scores of each position from the 40(45)-float
-//                      row staged in shared memory by a cp.async ring, take the
-//                      neighbour's alpha by warp shuffle (one shared-memory word
-//                      per warp boundary), log-add-exp, one __syncthreads.
-//                      The normaliser is a two-step-stale block max so no
-//                      reduction sits on the dependency chain; any finite
-//                      per-(t,chunk) scalar is a valid normaliser because the
-//                      shifts are summed into the score (c_crf_flipflop.c:73-77,
-//                      :124).  alpha_t / beta_{t+1} rows are spilled to the HBM
-//                      workspace for the posterior kernel.
-//   crf_grad_kernel    one CTA per (block, chunk) row: softmax over the 2L-1
-//                      joint stay/move scores (c_crf_flipflop.c:372-413) and a
-//                      shared-memory histogram into the ntrans bins, written
-//                      once with the operator's scale folded in.
+//   crf_chain_kernel   one CTA per (chunk, direction) + one "binning" CTA per
+//                      chunk in the same launch.
+//       chains: the sequence positions of the chunk are striped over the
+//         threads, P consecutive positions per thread in registers; time is the
+//         only sequential dimension and the kernel is bound by the per-step
+//         dependency latency, so the step is written for minimum instruction
+//         count: the DP runs in the log2 domain (bare ex2/lg2 SFU ops); a few
+//         "transformer" threads turn the raw score row (cp.async ring) into
+//         w*sharp*log2(e) - c one step ahead, so a position costs 2 LDS gathers
+//         and 8 arithmetic instructions; masked positions point at a -1e30 pad
+//         slot instead of being selected away; the normaliser c is the block
+//         max of the vector two steps earlier (any finite per-(t,chunk) scalar
+//         is valid: the shifts are summed into the score, c_crf_flipflop.c:73-77,
+//         :124) so no reduction sits on the dependency chain.  alpha_t /
+//         beta_{t+1} rows and their accumulated offsets go to the HBM workspace.
+//       binning: a counting sort of the chunk's stay / move entries by
+//         transition index (CSR), once per call, so the posterior kernel needs
+//         no atomics.
+//   crf_post_kernel    posterior of c_crf_flipflop.c:372-413 /
+//                      c_cat_mod_flipflop.c:419-468.  One thread per (block,
+//                      transition bin): it sums 2^(alpha+beta+w - Z_t) over the
+//                      bin's entries from shared-memory copies of the alpha /
+//                      beta rows, where Z_t is the analytic normaliser (total
+//                      score minus the accumulated offsets); the 40 canonical
+//                      bins are then renormalised to sum to one exactly like
+//                      the reference's softmax, so Z_t only has to be close.
 #include "common.cuh"
 
 namespace ty {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 struct CrfArgs {
     const float *logprob;
@@ -33,166 +44,236 @@ struct CrfArgs {
     const float *modmovefact;
     const int32_t *seqlen;
     float sharp;
-    int nsharp;
+    int nsharp;        // columns < nsharp are multiplied by sharp
+    int ncan;          // columns < ncan are stay / move transitions (carry the shift); the rest are cat-mod
     float score_scale;
     float *score_out;
     float grad_scale;
     float *grad_out;
     // workspace
-    int *seqoff;     // [nbatch] prefix sums of seqlen
-    float *fb;       // [nbatch][2] forward / backward log-scores
-    float *fwd_ws;   // [nbatch][nblk][Ls] alpha_t
-    float *bwd_ws;   // [nbatch][nblk][Ls] beta_{t+1}
+    int *seqoff;       // [nbatch] prefix sums of seqlen
+    float *fb;         // [nbatch][2] forward / backward log2-scores
+    float *coff;       // [2][nbatch][nblk] accumulated log2 offsets of the stored rows
+    float *fwd_ws;     // [nbatch][nblk][Ls] alpha_t         (log2 domain, normalised)
+    float *bwd_ws;     // [nbatch][nblk][Ls] beta_{t+1}
+    // entries sorted by transition bin, per chunk; word = pos | move << 13 | bin << 14 | mm << 20
+    int *ent_n;        // [nbatch][2] entries in each list
+    uint32_t *ent_w;   // [nbatch][2 * Ls]  stays + moves, keyed by their own transition
+    float *ent_mf;     // [nbatch][2 * Ls]  MOD: factor of a move entry (0 for stays)
+    uint32_t *ent2_w;  // [nbatch][Ls]      MOD: moves keyed by their mod transition (bin = mod, mm = move)
+    float *ent2_mf;    // [nbatch][Ls]
     int Ls;
     int want_grad;
+    int nchain;        // CTAs that run chains; the rest sort
 };
 
-constexpr int kRing = 8;      // cp.async ring slots for score rows
+constexpr int kRing = 8;      // cp.async ring slots for raw score rows
 constexpr int kDepth = 6;     // rows in flight
-constexpr int kRowPad = 64;   // floats per ring slot (ntrans <= 64)
+constexpr int kRowPad = 64;   // floats per row slot (ntrans <= 63); slot 63 = -1e30 pad
+constexpr int kPadSlot = 63;
 
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// log2(2^x + 2^y)
+__device__ __forceinline__ float logaddexp2(float x, float y) {
+    return fmaxf(x, y) + lg2f(1.0f + ex2f(-fabsf(x - y)));
+}
+
+// One chain.  Warp-specialised: warps 0..ncw-1 run the DP; the LAST warp is the
+// "transformer": it owns the cp.async ring, turns raw score rows into
+// w*sharp*log2(e) - c one step ahead, and keeps the offset bookkeeping, so the
+// DP warps execute nothing but the recurrence.
 template <int P, bool MOD, int DIR>
 __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, const int L,
-                                               const int off, float (*rows)[kRowPad],
-                                               float (*bnd)[32], float (*wmaxbuf)[32]) {
+                                               const int off) {
+    __shared__ __align__(16) float raw[kRing][kRowPad];
+    __shared__ __align__(16) float tr[2][kRowPad];
+    __shared__ __align__(16) float bnd[2][32];
+    __shared__ __align__(16) float wmaxs[2][32];
+    __shared__ float s_end;
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarp = blockDim.x >> 5;
-    const int nwarp4 = (nwarp + 3) & ~3;
+    const int ncw = (blockDim.x >> 5) - 1;          // DP warps
+    const bool is_tx = warp == ncw;
     const int S = a.ntrans;
     const int nblk = a.nblk;
     const size_t ld = (size_t)a.nbatch * S;
-    const float *lp = a.logprob + (size_t)b * S;
     const int p0 = tid * P;
 
-    // Per-position transition indices live in registers for the whole chain.
+    // ---- DP state: byte offsets into a transformed row (pad slot when invalid) ----
     int st[P], mv[P], mm[P];
     float mf[P];
     float al[P];
 #pragma unroll
     for (int i = 0; i < P; i++) {
         const int p = p0 + i;
-        st[i] = 0; mv[i] = 0; mm[i] = 0; mf[i] = 0.f;
-        if (p < L) st[i] = a.stayidx[off + p];
-        // DIR 0 (forward): move INTO p from p-1.  DIR 1: move OUT of p to p+1.
-        const int q = DIR == 0 ? p - 1 : p;
-        if (q >= 0 && q < L - 1) {
-            mv[i] = a.moveidx[off - b + q];
-            if (MOD) {
-                mm[i] = a.modmoveidx[off - b + q];
-                mf[i] = a.modmovefact[off - b + q];
+        st[i] = kPadSlot * 4; mv[i] = kPadSlot * 4; mm[i] = 0; mf[i] = 0.f;
+        al[i] = kNegLarge;
+        if (!is_tx) {
+            if (p < L) st[i] = a.stayidx[off + p] * 4;
+            // DIR 0 (forward): move INTO p from p-1.  DIR 1: move OUT of p to p+1.
+            const int q = DIR == 0 ? p - 1 : p;
+            if (p < L && q >= 0 && q < L - 1) {
+                mv[i] = a.moveidx[off - b + q] * 4;
+                if (MOD) {
+                    mm[i] = a.modmoveidx[off - b + q] * 4;
+                    mf[i] = a.modmovefact[off - b + q];
+                }
             }
+            // c_crf_flipflop.c:113-116 / :220-224 point priors
+            if (p == (DIR == 0 ? 0 : L - 1)) al[i] = 0.f;
         }
-        // positions without a move see a neighbour pinned at -1e30, so the
-        // log-add-exp below returns the stay term unchanged (no branch needed)
-        // c_crf_flipflop.c:113-116 / :220-224 point priors
-        al[i] = (p == (DIR == 0 ? 0 : L - 1)) ? 0.f : kNegLarge;
     }
 
-    auto issue_row = [&](int k) {
+    // ---- transformer state ----
+    const bool l0 = lane < S, l1 = lane + 32 < S;
+    const float sc0 = (lane < a.nsharp ? a.sharp : 1.0f) * kLog2e;
+    const float sc1 = (lane + 32 < a.nsharp ? a.sharp : 1.0f) * kLog2e;
+    const bool can0 = lane < a.ncan, can1 = lane + 32 < a.ncan;
+    const long long tstep = DIR == 0 ? (long long)ld : -(long long)ld;
+    // raw row k lives at src(k) = lp + t(k)*ld ; t(k) = k or nblk-1-k
+    const float *src = a.logprob + (size_t)b * S + (size_t)(DIR == 0 ? 0 : nblk - 1) * ld + lane;
+    auto issue_row = [&](int k) {       // src points at row k
         if (k < nblk) {
-            const int t = DIR == 0 ? k : nblk - 1 - k;
-            for (int i = tid; i < S; i += blockDim.x)      // a block may be a single warp
-                cp_async4(&rows[k % kRing][i], lp + (size_t)t * ld + i);
+            if (l0) cp_async4(&raw[k & (kRing - 1)][lane], src);
+            if (l1) cp_async4(&raw[k & (kRing - 1)][lane + 32], src + 32);
         }
         cp_async_commit();
+        src += tstep;
     };
+    auto transform_row = [&](int k, int par, float c) {
+        if (l0) {
+            const float w = raw[k & (kRing - 1)][lane];
+            tr[par][lane] = can0 ? fmaf(w, sc0, -c) : w * sc0;
+        }
+        if (l1) {
+            const float w = raw[k & (kRing - 1)][lane + 32];
+            tr[par][lane + 32] = can1 ? fmaf(w, sc1, -c) : w * sc1;
+        }
+    };
+    float coff_run = 0.f;             // accumulated offset of the vector in registers
+    float c_cur = 0.f, c_prev = 0.f;  // shifts inside the current / previous row
+    float part = 0.f;                 // lane-striped partial sums of the shifts
+    float *coff = nullptr;
+    if (is_tx) {
 #pragma unroll
-    for (int k = 0; k < kDepth; k++) issue_row(k);
-
-    if (tid < 32) {
-        wmaxbuf[0][tid] = tid < nwarp ? 0.f : -3.0e38f;
-        wmaxbuf[1][tid] = tid < nwarp ? 0.f : -3.0e38f;
-    }
-    // boundary words of the initial vector, read by iteration 0
-    if (DIR == 0) {
-        if (lane == 31) bnd[1][warp] = al[P - 1];
+        for (int k = 0; k < kDepth; k++) issue_row(k);
+        wmaxs[0][lane] = lane < ncw ? 0.f : -3.0e38f;
+        wmaxs[1][lane] = lane < ncw ? 0.f : -3.0e38f;
+        if (lane == 0) { tr[0][kPadSlot] = kNegLarge; tr[1][kPadSlot] = kNegLarge; }
+        cp_async_wait<kDepth - 1>();      // own copies of row 0 have landed
+        transform_row(0, 0, 0.f);
+        if (a.want_grad)
+            coff = a.coff + ((size_t)DIR * a.nbatch + b) * nblk + (DIR == 0 ? 0 : nblk - 1);
     } else {
-        if (lane == 0) bnd[1][warp] = al[0];
+        // boundary words of the initial vector, read by step 0
+        if (DIR == 0) {
+            if (lane == 31) bnd[1][warp] = al[P - 1];
+        } else {
+            if (lane == 0) bnd[1][warp] = al[0];
+        }
     }
-    float pend_max = 0.f;     // max of the vector currently in registers (per warp)
-    double csum = 0.0;
-    cp_async_wait<kDepth - 1>();
+    float pend_max = 0.f;             // warp max of the vector in registers
     __syncthreads();
 
-    float *ws = (DIR == 0 ? a.fwd_ws : a.bwd_ws);
-    if (a.want_grad) ws += ((size_t)b * nblk) * a.Ls + p0;
+    float *dst = nullptr;             // spill row of the current step
+    const long long dstep = DIR == 0 ? (long long)a.Ls : -(long long)a.Ls;
+    if (a.want_grad && !is_tx)
+        dst = (DIR == 0 ? a.fwd_ws : a.bwd_ws) +
+              ((size_t)b * nblk + (DIR == 0 ? 0 : nblk - 1)) * a.Ls + p0;
 
-    for (int k = 0; k < nblk; k++) {
-        const int t = DIR == 0 ? k : nblk - 1 - k;
-        issue_row(k + kDepth);
-
-        // normaliser: max of the vector two steps ago (see header comment)
-        float c = -3.0e38f;
-        {
-            const float4 *wm4 = reinterpret_cast<const float4 *>(wmaxbuf[(k + 1) & 1]);
-            for (int w = 0; w < nwarp4 / 4; w++) {
-                const float4 v = wm4[w];
-                c = fmaxf(c, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    // One time step; PAR = k & 1 is a compile-time constant (loop unrolled by 2)
+    // so the row / boundary buffers are addressed with immediates.
+    auto step = [&](const int k, auto par_c) {
+        constexpr int PAR = decltype(par_c)::value;
+        if (is_tx) {
+            issue_row(k + kDepth);
+            // Shift of the next row.  The freshest block max visible without a
+            // reduction on the chain is that of the vector two steps ago,
+            // m_{k-1}; two shifts (rows k-1, k) were applied since, so the shift
+            // that re-centres is m_{k-1} - c_{k-1} - c_k.  (Subtracting the stale
+            // max alone is an unstable recurrence.)
+            const float c_next = warp_max(wmaxs[PAR ^ 1][lane]) - c_cur - c_prev;
+            if (a.want_grad) {
+                if (lane == 0) *coff = coff_run;
+                coff += DIR == 0 ? 1 : -1;
             }
-        }
-        if (lane == 0) wmaxbuf[k & 1][warp] = pend_max;
-
-        // spill alpha_t (DIR 0) / beta_{t+1} (DIR 1) for the posterior kernel
-        if (a.want_grad) {
-            float *dst = ws + (size_t)t * a.Ls;
-            if (P % 4 == 0) {
+            if (lane == (k & 31)) part += c_cur;
+            coff_run += c_cur;
+            c_prev = c_cur;
+            c_cur = c_next;
+            cp_async_wait<kDepth - 1>();          // own copies of row k+1 have landed
+            if (k + 1 < nblk) transform_row(k + 1, PAR ^ 1, c_next);
+        } else {
+            if (lane == 0) wmaxs[PAR][warp] = pend_max;
+            // spill alpha_t (DIR 0) / beta_{t+1} (DIR 1) for the posterior kernel
+            if (a.want_grad) {
+                if (P % 4 == 0) {
 #pragma unroll
-                for (int i = 0; i < P; i += 4)
-                    if (p0 + i < L)
-                        __stcs(reinterpret_cast<float4 *>(dst + i),
-                               make_float4(al[i], al[i + 1], al[i + 2], al[i + 3]));
+                    for (int i = 0; i < P; i += 4)
+                        if (p0 + i < L)
+                            __stcs(reinterpret_cast<float4 *>(dst + i),
+                                   make_float4(al[i], al[i + 1], al[i + 2], al[i + 3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < P; i++)
+                        if (p0 + i < L) __stcs(dst + i, al[i]);
+                }
+                dst += dstep;
+            }
+            // neighbour value across the thread boundary
+            float nb;
+            if (DIR == 0) {
+                nb = __shfl_up_sync(kFullMask, al[P - 1], 1);
+                if (lane == 0) nb = warp > 0 ? bnd[PAR ^ 1][warp - 1] : kNegLarge;
             } else {
-#pragma unroll
-                for (int i = 0; i < P; i++)
-                    if (p0 + i < L) __stcs(dst + i, al[i]);
+                nb = __shfl_down_sync(kFullMask, al[0], 1);
+                if (lane == 31) nb = warp + 1 < ncw ? bnd[PAR ^ 1][warp + 1] : kNegLarge;
             }
-        }
-
-        const float *row = rows[k % kRing];
-        // neighbour value across the thread boundary
-        float nb;
-        if (DIR == 0) {
-            nb = __shfl_up_sync(kFullMask, al[P - 1], 1);
-            if (lane == 0) nb = warp > 0 ? bnd[(k + 1) & 1][warp - 1] : kNegLarge;
-        } else {
-            nb = __shfl_down_sync(kFullMask, al[0], 1);
-            if (lane == 31) nb = warp + 1 < nwarp ? bnd[(k + 1) & 1][warp + 1] : kNegLarge;
-        }
-
-        float nw[P];
-        float tmax = -3.0e38f;
+            const char *row = reinterpret_cast<const char *>(tr[PAR]);
+            float nw[P];
+            float tmax = -3.0e38f;
 #pragma unroll
-        for (int i = 0; i < P; i++) {
-            const float stay = al[i] + a.sharp * row[st[i]];
-            float other;
-            if (DIR == 0) other = (i == 0) ? nb : al[i - 1];
-            else other = (i == P - 1) ? nb : al[i + 1];
-            float wm = a.sharp * row[mv[i]];
-            if (MOD) wm = fmaf(row[mm[i]], mf[i], wm);
-            float v = logaddexp(stay, other + wm) - c;
-            if (p0 + i >= L) v = kNegLarge;
-            nw[i] = v;
-            tmax = fmaxf(tmax, v);
-        }
+            for (int i = 0; i < P; i++) {
+                const float stay = al[i] + *reinterpret_cast<const float *>(row + st[i]);
+                float other;
+                if (DIR == 0) other = (i == 0) ? nb : al[i - 1];
+                else other = (i == P - 1) ? nb : al[i + 1];
+                float move = other + *reinterpret_cast<const float *>(row + mv[i]);
+                if (MOD) move = fmaf(*reinterpret_cast<const float *>(row + mm[i]), mf[i], move);
+                nw[i] = logaddexp2(stay, move);
+                tmax = fmaxf(tmax, nw[i]);
+            }
 #pragma unroll
-        for (int i = 0; i < P; i++) al[i] = nw[i];
-
-        if (DIR == 0) {
-            if (lane == 31) bnd[k & 1][warp] = al[P - 1];
-        } else {
-            if (lane == 0) bnd[k & 1][warp] = al[0];
+            for (int i = 0; i < P; i++) al[i] = nw[i];
+            if (DIR == 0) {
+                if (lane == 31) bnd[PAR][warp] = al[P - 1];
+            } else {
+                if (lane == 0) bnd[PAR][warp] = al[0];
+            }
+            pend_max = warp_max(tmax);
         }
-        pend_max = warp_max(tmax);
-        if (tid == 0) csum += (double)c;
-
-        cp_async_wait<kDepth - 1>();
         __syncthreads();
+    };
+
+    int k = 0;
+    for (; k + 1 < nblk; k += 2) {
+        step(k, std::integral_constant<int, 0>{});
+        step(k + 1, std::integral_constant<int, 1>{});
     }
+    if (k < nblk) step(k, std::integral_constant<int, 0>{});
 
     // c_crf_flipflop.c:131-132 / :234: final position (forward) or first (backward)
     const int pend = DIR == 0 ? L - 1 : 0;
-    __shared__ float s_end;
-    if (pend >= p0 && pend < p0 + P) {
+    if (!is_tx && pend >= p0 && pend < p0 + P) {
         float v = 0.f;
 #pragma unroll
         for (int i = 0; i < P; i++)
@@ -200,20 +281,129 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
         s_end = v;
     }
     __syncthreads();
-    if (tid == 0) {
-        const float score = (float)(csum + (double)s_end);
-        if (a.want_grad) a.fb[2 * b + DIR] = score;
-        else a.score_out[b] = a.score_scale * score;
+    if (is_tx) {
+        double tot = (double)part;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
+        if (lane == 0) {
+            const float score2 = (float)(tot + (double)s_end);       // log2 units
+            if (a.want_grad) a.fb[2 * b + DIR] = score2;
+            else a.score_out[b] = a.score_scale * kLn2 * score2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Counting sort of one chunk's entries by transition index, once per call, so
+// the posterior kernel can sum bins without atomics on every entry.  List 1:
+// stays (position p, key stay[p]) and moves (position p, key move[p], p < L-1).
+// Cat-mod list 2: the moves again, keyed by their mod transition.  Order inside
+// a bin is by position, so the sums are deterministic.
+// Entry word: pos | is_move << 13 | key << 14 | other << 20   (pos < 8192)
+template <bool MOD>
+__device__ void crf_sort_chunk(const CrfArgs &a, const int b) {
+    __shared__ int cnt[4][kRowPad];
+    __shared__ int cnt2[4][kRowPad];
+    __shared__ int s_off;
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        int s = 0;
+        for (int i = tid; i < b; i += 32) s += a.seqlen[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+        if (tid == 0) s_off = s;
+    }
+    __syncthreads();
+    const int off = s_off;
+    const int L = a.seqlen[b];
+    const int nthr = blockDim.x;
+    if (L <= 0) {
+        if (tid == 0) { a.ent_n[2 * b] = 0; a.ent_n[2 * b + 1] = 0; }
+        return;
+    }
+    const int32_t *st = a.stayidx + off;
+    const int32_t *mv = a.moveidx + (off - b);
+    const int32_t *mm = MOD ? a.modmoveidx + (off - b) : nullptr;
+    const float *mf = MOD ? a.modmovefact + (off - b) : nullptr;
+    const int chunk = (L + 3) / 4;
+    // work item = (bin, quarter of the positions); any block size
+    for (int item = tid; item < 4 * kRowPad; item += nthr) {
+        const int bin = item & 63, part = item >> 6;
+        const int lo = part * chunk, hi = min(L, lo + chunk);
+        int c = 0, c2 = 0;
+        for (int p = lo; p < hi; p++) {
+            c += st[p] == bin;
+            if (p < L - 1) {
+                c += mv[p] == bin;
+                if (MOD) c2 += mm[p] == bin;
+            }
+        }
+        cnt[part][bin] = c;
+        if (MOD) cnt2[part][bin] = c2;
+    }
+    __syncthreads();
+    // exclusive scan over (bin, part) in bin-major order by warp 0
+    if (tid < 32) {
+        for (int list = 0; list < (MOD ? 2 : 1); list++) {
+            int (*cn)[kRowPad] = list == 0 ? cnt : cnt2;
+            int run = 0;
+            for (int base = 0; base < kRowPad; base += 32) {
+                const int bb = base + tid;
+                const int n0 = cn[0][bb], n1 = cn[1][bb], n2 = cn[2][bb], n3 = cn[3][bb];
+                const int tot = n0 + n1 + n2 + n3;
+                int inc = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(kFullMask, inc, o);
+                    if (tid >= o) inc += v;
+                }
+                const int excl = run + inc - tot;
+                cn[0][bb] = excl; cn[1][bb] = excl + n0; cn[2][bb] = excl + n0 + n1;
+                cn[3][bb] = excl + n0 + n1 + n2;
+                run += __shfl_sync(kFullMask, inc, 31);
+            }
+            if (tid == 0) a.ent_n[2 * b + list] = run;
+        }
+        if (!MOD && tid == 0) a.ent_n[2 * b + 1] = 0;
+    }
+    __syncthreads();
+    const size_t eb = (size_t)b * 2 * a.Ls;
+    const size_t eb2 = (size_t)b * a.Ls;
+    for (int item = tid; item < 4 * kRowPad; item += nthr) {
+        const int bin = item & 63, part = item >> 6;
+        const int lo = part * chunk, hi = min(L, lo + chunk);
+        int w = cnt[part][bin], w2 = MOD ? cnt2[part][bin] : 0;
+        for (int p = lo; p < hi; p++) {
+            if (st[p] == bin) {
+                a.ent_w[eb + w] = (uint32_t)p | ((uint32_t)bin << 14);
+                if (MOD) a.ent_mf[eb + w] = 0.f;
+                w++;
+            }
+            if (p < L - 1) {
+                if (mv[p] == bin) {
+                    a.ent_w[eb + w] = (uint32_t)p | (1u << 13) | ((uint32_t)bin << 14) |
+                                      (MOD ? (uint32_t)mm[p] << 20 : 0u);
+                    if (MOD) a.ent_mf[eb + w] = mf[p];
+                    w++;
+                }
+                if (MOD && mm[p] == bin) {
+                    a.ent2_w[eb2 + w2] = (uint32_t)p | (1u << 13) | ((uint32_t)bin << 14) |
+                                         ((uint32_t)mv[p] << 20);
+                    a.ent2_mf[eb2 + w2] = mf[p];
+                    w2++;
+                }
+            }
+        }
     }
 }
 
 template <int P, bool MOD>
-__global__ void __launch_bounds__(P <= 4 ? 1024 : 512) crf_chain_kernel(const CrfArgs a) {
-    __shared__ __align__(16) float rows[kRing][kRowPad];
-    __shared__ __align__(16) float bnd[2][32];
-    __shared__ __align__(16) float wmaxbuf[2][32];
+__global__ void __launch_bounds__(P <= 4 ? 1024 : 544) crf_chain_kernel(const CrfArgs a) {
+    if ((int)blockIdx.x >= a.nchain) {        // sorting CTAs (want_grad only)
+        crf_sort_chunk<MOD>(a, blockIdx.x - a.nchain);
+        return;
+    }
     __shared__ int s_off;
-
     const int b = a.want_grad ? (blockIdx.x >> 1) : blockIdx.x;
     const int dir = a.want_grad ? (blockIdx.x & 1) : 0;
 
@@ -236,96 +426,143 @@ __global__ void __launch_bounds__(P <= 4 ? 1024 : 512) crf_chain_kernel(const Cr
         }
         return;
     }
-    if (dir == 0) crf_chain_body<P, MOD, 0>(a, b, L, off, rows, bnd, wmaxbuf);
-    else crf_chain_body<P, MOD, 1>(a, b, L, off, rows, bnd, wmaxbuf);
+    if (dir == 0) crf_chain_body<P, MOD, 0>(a, b, L, off);
+    else crf_chain_body<P, MOD, 1>(a, b, L, off);
 }
 
 // ---------------------------------------------------------------------------
-constexpr int kGradThreads = 128;
-
-__device__ __forceinline__ void online_update(float &m, float &s, float u) {
-    if (u > m) {
-        s = s * __expf(m - u) + 1.0f;
-        m = u;
-    } else {
-        s += __expf(u - m);
-    }
-}
+// Posterior.  grid = (row tiles, chunks); one WARP per row (block, chunk).
+// The row's alpha_t / beta_{t+1} vectors and the chunk's sorted entry words are
+// staged in shared memory; each lane walks a contiguous slice of the sorted
+// entries, accumulating 2^(alpha + beta + w - Z_t) per run of equal bin and
+// flushing a run with one shared-memory add, so adds are rare and collide only
+// at slice boundaries.  Z_t is the analytic normaliser (total score minus the
+// accumulated offsets of the two rows); the canonical bins are then
+// renormalised to sum to one exactly like the reference's softmax
+// (c_crf_flipflop.c:401), so Z_t only has to be close.
+constexpr int kPostWarps = 8;
 
 template <bool MOD>
-__global__ void __launch_bounds__(kGradThreads) crf_grad_kernel(const CrfArgs a) {
-    __shared__ float row[kRowPad];
-    __shared__ float bins[kRowPad];
-    __shared__ float red_m[kGradThreads / 32], red_s[kGradThreads / 32];
+__global__ void __launch_bounds__(kPostWarps * 32) crf_post_kernel(const CrfArgs a) {
+    extern __shared__ __align__(16) float dyn[];   // al[R][Ls], be[R][Ls+4], words[2Ls] (+ MOD extras)
+    __shared__ float q[kPostWarps][kRowPad];       // w2 - Z_t (canonical), w2 (mod)
+    __shared__ float bins[kPostWarps][kRowPad];
 
-    const int tid = threadIdx.x;
-    const int t = blockIdx.x / a.nbatch;
-    const int b = blockIdx.x - t * a.nbatch;
-    const int S = a.ntrans;
+    const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * kPostWarps;
+    const int S = a.ntrans, Ls = a.Ls;
     const int L = a.seqlen[b];
-    const size_t rowoff = ((size_t)t * a.nbatch + b) * S;
+    const int nrow = min(kPostWarps, a.nblk - t0);
+    const int t = t0 + r;
 
     if (L <= 0) {
-        if (tid < S) a.grad_out[rowoff + tid] = 0.f;
-        if (t == 0 && tid == 0) a.score_out[b] = 0.f;
+        if (r < nrow)
+            for (int s = lane; s < S; s += 32)
+                a.grad_out[((size_t)t * a.nbatch + b) * S + s] = 0.f;
+        if (t0 == 0 && tid == 0) a.score_out[b] = 0.f;
         return;
     }
-    if (tid < S) {
-        const float w = a.logprob[rowoff + tid];
-        row[tid] = tid < a.nsharp ? a.sharp * w : w;
-        bins[tid] = 0.f;
-    }
-    if (t == 0 && tid == 0)   // score = 0.5 (F + B), c_crf_flipflop.c:482-491
-        a.score_out[b] = a.score_scale * 0.5f * (a.fb[2 * b] + a.fb[2 * b + 1]);
-    __syncthreads();
+    // total log2 score = mean of forward and backward (c_crf_flipflop.c:482-491)
+    const float score2 = 0.5f * (a.fb[2 * b] + a.fb[2 * b + 1]);
+    if (t0 == 0 && tid == 0) a.score_out[b] = a.score_scale * kLn2 * score2;
 
-    const int off = a.seqoff[b];
-    const float *al = a.fwd_ws + ((size_t)b * a.nblk + t) * a.Ls;
-    const float *be = a.bwd_ws + ((size_t)b * a.nblk + t) * a.Ls;
-    const int32_t *st = a.stayidx + off;
-    const int32_t *mv = a.moveidx + (off - b);
-    const int32_t *mm = MOD ? a.modmoveidx + (off - b) : nullptr;
-    const float *mf = MOD ? a.modmovefact + (off - b) : nullptr;
+    const int bes = Ls + 4;
+    float *al = dyn;
+    float *be = al + (size_t)kPostWarps * Ls;
+    uint32_t *words = reinterpret_cast<uint32_t *>(be + (size_t)kPostWarps * bes);
+    float *wmf = reinterpret_cast<float *>(words + 2 * Ls);        // MOD only
+    uint32_t *words2 = reinterpret_cast<uint32_t *>(wmf + 2 * Ls); // MOD only
+    float *wmf2 = reinterpret_cast<float *>(words2 + Ls);          // MOD only
+    const int n1 = a.ent_n[2 * b], n2 = MOD ? a.ent_n[2 * b + 1] : 0;
 
-    float m = -3.0e38f, s = 0.f;
-    for (int p = tid; p < L; p += kGradThreads) {
-        const float av = al[p];
-        online_update(m, s, av + be[p] + row[st[p]]);
-        if (p < L - 1) {
-            float wm = row[mv[p]];
-            if (MOD) wm = fmaf(row[mm[p]], mf[p], wm);
-            online_update(m, s, av + be[p + 1] + wm);
+    // ---- stage: each warp its own row (float4, coalesced), all warps the entry lists ----
+    if (r < nrow) {
+        const size_t g = ((size_t)b * a.nblk + t) * Ls;
+        const float4 *fa = reinterpret_cast<const float4 *>(a.fwd_ws + g);
+        const float4 *fbp = reinterpret_cast<const float4 *>(a.bwd_ws + g);
+        float4 *sa = reinterpret_cast<float4 *>(al + (size_t)r * Ls);
+        float4 *sb = reinterpret_cast<float4 *>(be + (size_t)r * bes);
+        for (int i = lane; i < (L + 3) / 4; i += 32) {
+            sa[i] = __ldcs(fa + i);
+            sb[i] = __ldcs(fbp + i);
+        }
+        for (int s = lane; s < kRowPad; s += 32) {
+            float v = 0.f;
+            if (s < S) {
+                const float w = a.logprob[((size_t)t * a.nbatch + b) * S + s];
+                // Z_t = score - offset(alpha_t) - offset(beta_{t+1})
+                const float z = score2 - a.coff[(size_t)b * a.nblk + t] -
+                                a.coff[((size_t)a.nbatch + b) * a.nblk + t];
+                const float sc = s < a.nsharp ? a.sharp * kLog2e : kLog2e;
+                v = s < a.ncan ? fmaf(w, sc, -z) : w * sc;
+            }
+            q[r][s] = v;
+            bins[r][s] = 0.f;
         }
     }
-    // block combine of (max, sum)
-    const float wm_ = warp_max(m);
-    s = warp_sum(s * __expf(m - wm_));
-    if ((tid & 31) == 0) { red_m[tid >> 5] = wm_; red_s[tid >> 5] = s; }
-    __syncthreads();
-    float M = red_m[0];
-#pragma unroll
-    for (int w = 1; w < kGradThreads / 32; w++) M = fmaxf(M, red_m[w]);
-    float Z = 0.f;
-#pragma unroll
-    for (int w = 0; w < kGradThreads / 32; w++) Z += red_s[w] * __expf(red_m[w] - M);
-    const float invZ = 1.0f / Z;
-
-    for (int p = tid; p < L; p += kGradThreads) {
-        const float av = al[p];
-        const int si = st[p];
-        atomicAdd(&bins[si], __expf(av + be[p] + row[si] - M) * invZ);
-        if (p < L - 1) {
-            const int mi = mv[p];
-            float wm = row[mi];
-            int mmi = 0; float f = 0.f;
-            if (MOD) { mmi = mm[p]; f = mf[p]; wm = fmaf(row[mmi], f, wm); }
-            const float pm = __expf(av + be[p + 1] + wm - M) * invZ;
-            atomicAdd(&bins[mi], pm);
-            if (MOD) atomicAdd(&bins[mmi], pm * f);   // c_cat_mod_flipflop.c:465-466
+    {
+        const uint32_t *gw = a.ent_w + (size_t)b * 2 * Ls;
+        for (int i = tid; i < n1; i += kPostWarps * 32) words[i] = gw[i];
+        if (MOD) {
+            const float *gf = a.ent_mf + (size_t)b * 2 * Ls;
+            const uint32_t *gw2 = a.ent2_w + (size_t)b * Ls;
+            const float *gf2 = a.ent2_mf + (size_t)b * Ls;
+            for (int i = tid; i < n1; i += kPostWarps * 32) wmf[i] = gf[i];
+            for (int i = tid; i < n2; i += kPostWarps * 32) { words2[i] = gw2[i]; wmf2[i] = gf2[i]; }
         }
     }
     __syncthreads();
-    if (tid < S) a.grad_out[rowoff + tid] = a.grad_scale * bins[tid];
+    if (r >= nrow) return;
+
+    const float *ar = al + (size_t)r * Ls;
+    const float *br = be + (size_t)r * bes;
+    const float *qr = q[r];
+    float *binr = bins[r];
+    {
+        // contiguous slice of the sorted entries for this lane
+        const int per = (n1 + 31) / 32;
+        const int lo = min(n1, lane * per), hi = min(n1, lo + per);
+        float acc = 0.f;
+        int cur = -1;
+        for (int j = lo; j < hi; j++) {
+            const uint32_t w = words[j];
+            const int pa = w & 0x1fff, mvf = (w >> 13) & 1, bin = (w >> 14) & 63;
+            if (bin != cur) {
+                if (cur >= 0) atomicAdd(&binr[cur], acc);
+                cur = bin; acc = 0.f;
+            }
+            float x = ar[pa] + br[pa + mvf] + qr[bin];
+            if (MOD) x = fmaf(qr[(w >> 20) & 63], wmf[j], x);   // 0 * w for stays
+            acc += ex2f(x);
+        }
+        if (cur >= 0) atomicAdd(&binr[cur], acc);
+    }
+    if (MOD) {
+        const int per = (n2 + 31) / 32;
+        const int lo = min(n2, lane * per), hi = min(n2, lo + per);
+        float acc = 0.f;
+        int cur = -1;
+        for (int j = lo; j < hi; j++) {
+            const uint32_t w = words2[j];
+            const int pa = w & 0x1fff, bin = (w >> 14) & 63, mvb = (w >> 20) & 63;
+            const float f = wmf2[j];
+            if (bin != cur) {
+                if (cur >= 0) atomicAdd(&binr[cur], acc);
+                cur = bin; acc = 0.f;
+            }
+            const float x = fmaf(qr[bin], f, ar[pa] + br[pa + 1] + qr[mvb]);
+            acc = fmaf(ex2f(x), f, acc);              // c_cat_mod_flipflop.c:465-466
+        }
+        if (cur >= 0) atomicAdd(&binr[cur], acc);
+    }
+    __syncwarp();
+    // normalise the canonical bins to sum to one and write the row once
+    float part = 0.f;
+    for (int s = lane; s < a.ncan; s += 32) part += binr[s];
+    const float scale = a.grad_scale / warp_sum(part);
+    for (int s = lane; s < S; s += 32)
+        a.grad_out[((size_t)t * a.nbatch + b) * S + s] = scale * binr[s];
 }
 
 // ---------------------------------------------------------------------------
@@ -380,7 +617,7 @@ __global__ void indices_kernel(const int64_t *seqs, const int64_t *seqlen, int n
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct CrfWsLayout {
-    size_t seqoff, fb, fwd, bwd, total;
+    size_t seqoff, fb, coff, fwd, bwd, ent_n, ent_w, ent_mf, ent2_w, ent2_mf, total;
     int Ls;
 };
 
@@ -388,11 +625,20 @@ static CrfWsLayout crf_layout(int nblk, int nbatch, int max_seqlen, int want_gra
     CrfWsLayout w{};
     w.Ls = (int)align_up((size_t)(max_seqlen > 0 ? max_seqlen : 1), 4);
     size_t o = 0;
-    w.seqoff = o; o += align_up((size_t)nbatch * sizeof(int), 256);
-    w.fb = o; o += align_up((size_t)nbatch * 2 * sizeof(float), 256);
-    const size_t mat = want_grad ? align_up((size_t)nbatch * nblk * w.Ls * sizeof(float), 256) : 0;
-    w.fwd = o; o += mat;
-    w.bwd = o; o += mat;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    w.seqoff = take((size_t)nbatch * sizeof(int));
+    w.fb = take((size_t)nbatch * 2 * sizeof(float));
+    if (want_grad) {
+        const size_t ne = (size_t)nbatch * 2 * w.Ls;
+        w.coff = take((size_t)2 * nbatch * nblk * sizeof(float));
+        w.fwd = take((size_t)nbatch * nblk * w.Ls * sizeof(float));
+        w.bwd = take((size_t)nbatch * nblk * w.Ls * sizeof(float));
+        w.ent_n = take((size_t)nbatch * 2 * sizeof(int));
+        w.ent_w = take(ne * sizeof(uint32_t));
+        w.ent_mf = take(ne * sizeof(float));
+        w.ent2_w = take(ne / 2 * sizeof(uint32_t));
+        w.ent2_mf = take(ne / 2 * sizeof(float));
+    }
     w.total = o;
     return w;
 }
@@ -402,7 +648,8 @@ static void launch_chain(const CrfArgs &a, int max_seqlen, cudaStream_t s) {
     int threads = (max_seqlen + P - 1) / P;
     threads = (threads + 31) / 32 * 32;
     if (threads < 32) threads = 32;
-    const int grid = a.want_grad ? 2 * a.nbatch : a.nbatch;
+    threads += 32;       // the transformer warp
+    const int grid = a.nchain + (a.want_grad ? a.nbatch : 0);
     crf_chain_kernel<P, MOD><<<grid, threads, 0, s>>>(a);
 }
 
@@ -424,11 +671,11 @@ int ty::crf_pick_p(int max_seqlen) {
     const char *e = getenv("TY_CRF_P");   // tuning override, read per call
     const int forced = e ? atoi(e) : 0;
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) {
-        const int cap = forced >= 8 ? 512 : 1024;
+        const int cap = forced >= 8 ? 512 : 992;
         if ((max_seqlen + forced - 1) / forced <= cap) return forced;
     }
-    if (max_seqlen <= 4096) return 4;
-    if (max_seqlen <= 8192) return 16;
+    if (max_seqlen <= 3968) return 4;
+    if (max_seqlen <= 8191) return 16;
     return 0;
 }
 
@@ -443,8 +690,10 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
         set_error("ty_crf_flipflop: null pointer");
         return TY_EINVAL;
     }
-    if (ntrans <= 0 || ntrans > kRowPad || nblk <= 0 || nbatch <= 0 || max_seqlen < 0) {
-        set_error("ty_crf_flipflop: bad shape ntrans=%d nblk=%d nbatch=%d", ntrans, nblk, nbatch);
+    if (ntrans <= 0 || ntrans >= kRowPad || nblk <= 0 || nbatch <= 0 || max_seqlen < 0 ||
+        nsharp < 0 || nsharp > ntrans) {
+        set_error("ty_crf_flipflop: bad shape ntrans=%d nblk=%d nbatch=%d nsharp=%d", ntrans,
+                  nblk, nbatch, nsharp);
         return TY_EINVAL;
     }
     if ((modmoveidx == nullptr) != (modmovefact == nullptr)) {
@@ -459,7 +708,7 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
     }
     const int P = crf_pick_p(max_seqlen > 0 ? max_seqlen : 1);
     if (P == 0) {
-        set_error("ty_crf_flipflop: max_seqlen %d > 8192 unsupported", max_seqlen);
+        set_error("ty_crf_flipflop: max_seqlen %d > 8191 unsupported", max_seqlen);
         return TY_EINVAL;
     }
     char *base = static_cast<char *>(workspace);
@@ -468,14 +717,27 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
     a.moveidx = moveidx; a.stayidx = stayidx; a.modmoveidx = modmoveidx;
     a.modmovefact = modmovefact; a.seqlen = seqlen;
     a.sharp = sharp; a.nsharp = nsharp;
+    a.ncan = ntrans;
+    if (modmoveidx) {   // cat-mod columns follow the 2*nb*(nb+1) flip-flop block (ctc.pyx:262-264)
+        int nb = 1;
+        while (2 * (nb + 1) * (nb + 2) <= ntrans) nb++;
+        a.ncan = 2 * nb * (nb + 1);
+    }
     a.score_scale = score_scale; a.score_out = score_out;
     a.grad_scale = grad_scale; a.grad_out = grad_out;
     a.seqoff = reinterpret_cast<int *>(base + w.seqoff);
     a.fb = reinterpret_cast<float *>(base + w.fb);
+    a.coff = reinterpret_cast<float *>(base + w.coff);
     a.fwd_ws = reinterpret_cast<float *>(base + w.fwd);
     a.bwd_ws = reinterpret_cast<float *>(base + w.bwd);
+    a.ent_n = reinterpret_cast<int *>(base + w.ent_n);
+    a.ent_w = reinterpret_cast<uint32_t *>(base + w.ent_w);
+    a.ent_mf = reinterpret_cast<float *>(base + w.ent_mf);
+    a.ent2_w = reinterpret_cast<uint32_t *>(base + w.ent2_w);
+    a.ent2_mf = reinterpret_cast<float *>(base + w.ent2_mf);
     a.Ls = w.Ls;
     a.want_grad = want_grad;
+    a.nchain = want_grad ? 2 * nbatch : nbatch;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool mod = modmoveidx != nullptr;
 #define TY_CHAIN(PP)                                           \
@@ -490,10 +752,25 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
     int rc = check_launch("crf_chain_kernel");
     if (rc) return rc;
     if (want_grad) {
-        const int grid = nblk * nbatch;
-        if (mod) crf_grad_kernel<true><<<grid, kGradThreads, 0, s>>>(a);
-        else crf_grad_kernel<false><<<grid, kGradThreads, 0, s>>>(a);
-        rc = check_launch("crf_grad_kernel");
+        // one warp per row; alpha/beta rows + the chunk's entry lists in shared memory
+        size_t smem = (size_t)kPostWarps * (2 * (size_t)w.Ls + 4) * sizeof(float) +
+                      2 * (size_t)w.Ls * sizeof(uint32_t);
+        if (mod) smem += 2 * (size_t)w.Ls * sizeof(float) + (size_t)w.Ls * 8;
+        if (smem > 200 * 1024) {
+            set_error("ty_crf_flipflop: max_seqlen %d needs %zu bytes of shared memory", max_seqlen, smem);
+            return TY_EINVAL;
+        }
+        const dim3 grid((nblk + kPostWarps - 1) / kPostWarps, nbatch);
+        if (mod) {
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(crf_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+            crf_post_kernel<true><<<grid, kPostWarps * 32, smem, s>>>(a);
+        } else {
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(crf_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+            crf_post_kernel<false><<<grid, kPostWarps * 32, smem, s>>>(a);
+        }
+        rc = check_launch("crf_post_kernel");
     }
     return rc;
 }

@@ -140,11 +140,26 @@ template <> struct Cell<kLstm> { static constexpr int G = 4, NS = 5; };   // i f
 template <> struct Cell<kGru> { static constexpr int G = 3, NS = 4; };    // r z n | W_hn h
 
 // ---------------------------------------------------------------------------
+// `reserve` layout (what forward keeps for BPTT), both cells:
+//     gates [T][N][H][4] fp32   LSTM: i f g o      GRU: r z n (W_hn h)
+//     cstate [T][N][H]   fp32   LSTM: c_t          GRU: unused
+// One thread owns all gates of a (unit, chunk) cell, so the gates of a cell
+// are one 16-byte store / load.
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+        "r"(v), "r"(rbar)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // Forward.  H multiple of 64, H <= 256.  Threads: 32 * H/64 (warp w owns 8 units).
 template <int CELL, int H>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     rnn_forward_kernel(const RnnArgs a) {
-    constexpr int G = Cell<CELL>::G, NS = Cell<CELL>::NS;
+    constexpr int G = Cell<CELL>::G;
     constexpr int U = H / kCluster;     // units per CTA
     constexpr int KT = H / 16;          // k tiles
     constexpr int HS = H + 8;           // padded row (bf16) -> conflict-free ldmatrix
@@ -161,6 +176,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     const int T = a.T, N = a.N;
     const int b0 = group * kNB + 2 * q;            // chunk of accumulator column 0
     const bool v0 = b0 < N, v1 = b0 + 1 < N;
+    float *const gates_out = a.reserve;
+    float *const cstate_out = a.reserve + (size_t)T * N * H * 4;
 
     // --- W_hh slice -> A fragments (registers, whole sequence) ---
     uint32_t A[2][KT][4];
@@ -196,26 +213,45 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     uint32_t phase = 0u;          // bit b = parity to wait for on full[b]
 
     auto tindex = [&](int s) { return a.reverse ? T - 1 - s : s; };
-    float xp[G][2], xn[G][2];
+    auto xaddr = [&](int s) { return a.xproj + ((size_t)tindex(s) * N + b0) * (G * H) + unit; };
     auto load_x = [&](float (&dst)[G][2], int s) {
         if (s < T) {
-            const size_t base = ((size_t)tindex(s) * N + b0) * (G * H) + unit;
+            const float *base = xaddr(s);
 #pragma unroll
             for (int g = 0; g < G; g++) {
-                dst[g][0] = v0 ? __ldg(a.xproj + base + (size_t)g * H) : 0.f;
-                dst[g][1] = v1 ? __ldg(a.xproj + base + (size_t)(G * H) + (size_t)g * H) : 0.f;
+                dst[g][0] = v0 ? __ldg(base + (size_t)g * H) : 0.f;
+                dst[g][1] = v1 ? __ldg(base + (size_t)(G * H) + (size_t)g * H) : 0.f;
             }
         }
     };
-    load_x(xp, 0);
+    auto prefetch_x = [&](int s) {     // pull a later step's projection rows into L2
+        if (s < T) {
+            const float *base = xaddr(s);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (v0) prefetch_l2(base + (size_t)g * H);
+                if (v1) prefetch_l2(base + (size_t)(G * H) + (size_t)g * H);
+            }
+        }
+    };
 
     const uint32_t hs_base = smem_u32(&hs[0][0][0]);
+    const uint32_t bar_base = smem_u32(&full[0]);
     // ldmatrix source row for this lane: matrix (lane>>3) -> k offset 8*(lane>>3), row lane&7
     const uint32_t ld_off = (uint32_t)(((lane & 7) * HS + 8 * (lane >> 3)) * 2);
+    // destination of this thread's packed pair of h values (see the exchange below)
+    const bool even = (r & 1) == 0;
+    const uint32_t send_off =
+        (uint32_t)((((even ? 2 * q : 2 * q + 1) * HS) + (even ? unit : unit - 1)) * 2);
 
-    for (int s = 0; s < T; s++) {
+    // One time step.  `xp` holds this step's projection (loaded a step ago),
+    // `xn` receives the next step's, issued only after `xp` has been consumed.
+    auto step = [&](const int s, float (&xp)[G][2], float (&xn)[G][2]) {
         const int t = tindex(s);
         const int cur = s & 1, nxt = cur ^ 1;
+        prefetch_x(s + 3);
+        if (tid == 0 && s + 1 < T)      // arm the barrier that collects h_t (phase of step s+1)
+            mbar_arrive_expect_tx(&full[nxt], kCluster * kNB * U * 2);
         if (s > 0) {
             mbar_wait(&full[cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
@@ -250,8 +286,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 #pragma unroll
         for (int col = 0; col < 2; col++) {
             const bool valid = col == 0 ? v0 : v1;
-            const size_t cell = (size_t)t * N + b0 + col;
-            float *res = a.reserve + (cell * NS) * H + unit;
+            const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
+            float4 sv;
             if (CELL == kLstm) {
                 const float gi = sigmoidf_(pre[0][col] + xp[0][col]);
                 const float gf = sigmoidf_(pre[0][2 + col] + xp[1][col]);
@@ -260,48 +296,51 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 const float c = gf * cst[col] + gi * gg;
                 cst[col] = c;
                 hnew[col] = go * tanhf_(c);
-                if (valid) {
-                    res[0] = gi; res[H] = gf; res[2 * H] = gg; res[3 * H] = go; res[4 * H] = c;
-                }
+                sv = make_float4(gi, gf, gg, go);
+                if (valid) __stcs(cstate_out + cell, c);
             } else {
-                const float hr = pre[0][col], hz = pre[0][2 + col], hn = pre[1][col];
-                const float gr = sigmoidf_(hr + xp[0][col]);
-                const float gz = sigmoidf_(hz + xp[1][col]);
+                const float hn = pre[1][col];
+                const float gr = sigmoidf_(pre[0][col] + xp[0][col]);
+                const float gz = sigmoidf_(pre[0][2 + col] + xp[1][col]);
                 const float gn = tanhf_(xp[2][col] + gr * hn);
                 const float h = (1.0f - gz) * gn + gz * cst[col];
                 cst[col] = h;
                 hnew[col] = h;
-                if (valid) {
-                    res[0] = gr; res[H] = gz; res[2 * H] = gn; res[3 * H] = hn;
-                }
+                sv = make_float4(gr, gz, gn, hn);
             }
-            if (valid) a.y[cell * H + unit] = hnew[col];
+            if (valid) {
+                __stcs(reinterpret_cast<float4 *>(gates_out) + cell, sv);
+                a.y[cell] = hnew[col];
+            }
         }
-        load_x(xn, s + 1);     // after xp was consumed: a full step to land
+        load_x(xn, s + 1);     // xp is dead from here on
 
         if (s + 1 < T) {
-            // own slice of h_t into the local copy of the next buffer
-            hs[nxt][2 * q][unit] = __float2bfloat16(hnew[0]);
-            hs[nxt][2 * q + 1][unit] = __float2bfloat16(hnew[1]);
-            __syncthreads();
-            if (tid == 0) mbar_arrive_expect_tx(&full[nxt], (kCluster - 1) * kNB * U * 2);
-            // ... and into the 7 peers: 16-byte pieces, completion on the peer's mbarrier
-            constexpr int PPR = U / 8;                 // pieces per row
-            constexpr int PIECES = kNB * PPR;
-            const uint32_t bar_local = smem_u32(&full[nxt]);
-            for (int idx = tid; idx < (kCluster - 1) * PIECES; idx += NTHR) {
-                const int pi = idx / PIECES;
-                const uint32_t peer = pi + (pi >= (int)rank);
-                const int piece = idx - pi * PIECES;
-                const int n = piece / PPR, w8 = piece - n * PPR;
-                const __nv_bfloat16 *src = &hs[nxt][n][rank * U + 8 * w8];
-                const uint4 v = *reinterpret_cast<const uint4 *>(src);
-                st_async_v4(mapa(smem_u32(src), peer), v, mapa(bar_local, peer));
-            }
-        }
+            // Exchange h_t: lanes r and r^1 swap one value so that each thread
+            // owns two consecutive units of one chunk (a 4-byte bf16 pair), then
+            // stores it straight from registers into all 8 CTAs of the cluster
+            // (its own included); the receivers' mbarriers count the bytes.
+            const float give = even ? hnew[1] : hnew[0];
+            const float got = __shfl_xor_sync(kFullMask, give, 4);
+            const uint32_t pair = even ? pack_bf16(hnew[0], got) : pack_bf16(got, hnew[1]);
+            const uint32_t dst = hs_base + (uint32_t)(nxt * kNB * HS * 2) + send_off;
+            const uint32_t bar = bar_base + (uint32_t)(nxt * 8);
 #pragma unroll
-        for (int g = 0; g < G; g++) { xp[g][0] = xn[g][0]; xp[g][1] = xn[g][1]; }
+            for (uint32_t peer = 0; peer < kCluster; peer++)
+                st_async_b32(mapa(dst, peer), pair, mapa(bar, peer));
+        }
+    };
+
+    float xa[G][2], xb[G][2];
+    load_x(xa, 0);
+    prefetch_x(1);
+    prefetch_x(2);
+    int s = 0;
+    for (; s + 1 < T; s += 2) {
+        step(s, xa, xb);
+        step(s + 1, xb, xa);
     }
+    if (s < T) step(s, xa, xb);
     cluster_sync_all();
 }
 
@@ -312,7 +351,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 template <int CELL, int H>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     rnn_backward_kernel(const RnnArgs a) {
-    constexpr int G = Cell<CELL>::G, NS = Cell<CELL>::NS;
+    constexpr int G = Cell<CELL>::G;
     constexpr int U = H / kCluster;
     constexpr int KL = (G * U + 15) / 16 * 16;   // local gate rows, padded
     constexpr int KT = KL / 16;
@@ -333,6 +372,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     const int T = a.T, N = a.N;
     const int b0 = group * kNB + 2 * q;
     const bool v0 = b0 < N, v1 = b0 + 1 < N;
+    const float4 *const gates_in = reinterpret_cast<const float4 *>(a.reserve);
+    const float *const cstate_in = a.reserve + (size_t)T * N * H * 4;
 
     // --- W_hh^T slice -> A fragments: A[m = hidden unit][k = local gate row] ---
     // local gate row kl = g*U + u  <->  W_hh row g*H + rank*U + u
@@ -366,9 +407,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     float carry[2] = {0.f, 0.f};   // LSTM: dL/dc carried back; GRU: z * dL/dh carried back
     auto tindex = [&](int sf) { return a.reverse ? T - 1 - sf : sf; };   // forward step -> time
 
-    // per-step inputs, prefetched one step ahead
-    struct In { float sv[NS][2]; float dy[2]; float prev[2]; };
-    In cur_in, nxt_in;
+    // per-step inputs: saved gates, c_t, incoming gradient, c_{t-1} / h_{t-1}
+    struct In { float4 gt[2]; float c[2]; float dy[2]; float prev[2]; };
     auto load_in = [&](In &d, int s) {
         if (s >= T) return;
         const int sf = T - 1 - s;                 // forward step being differentiated
@@ -376,30 +416,46 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 #pragma unroll
         for (int col = 0; col < 2; col++) {
             const bool valid = col == 0 ? v0 : v1;
-            const size_t cell = (size_t)t * N + b0 + col;
-#pragma unroll
-            for (int k = 0; k < NS; k++)
-                d.sv[k][col] = valid ? __ldg(a.reserve + (cell * NS + k) * H + unit) : 0.f;
-            d.dy[col] = valid ? __ldg(a.dy + cell * H + unit) : 0.f;
+            const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
+            d.gt[col] = valid ? __ldcs(gates_in + cell) : make_float4(0.f, 0.f, 0.f, 0.f);
+            d.c[col] = (valid && CELL == kLstm) ? __ldcs(cstate_in + cell) : 0.f;
+            d.dy[col] = valid ? __ldcs(a.dy + cell) : 0.f;
             float pv = 0.f;
             if (valid && sf > 0) {
-                const size_t pcell = (size_t)tindex(sf - 1) * N + b0 + col;
-                pv = CELL == kLstm ? __ldg(a.reserve + (pcell * NS + 4) * H + unit)   // c_{t-1}
-                                   : __ldg(a.y + pcell * H + unit);                   // h_{t-1}
+                const size_t pcell = ((size_t)tindex(sf - 1) * N + b0 + col) * H + unit;
+                pv = CELL == kLstm ? __ldg(cstate_in + pcell)      // c_{t-1}
+                                   : __ldg(a.y + pcell);           // h_{t-1}
             }
             d.prev[col] = pv;
         }
     };
-    load_in(cur_in, 0);
+    auto prefetch_in = [&](int s) {
+        if (s >= T) return;
+        const int t = tindex(T - 1 - s);
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            if (col == 0 ? v0 : v1) {
+                const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
+                prefetch_l2(gates_in + cell);
+                prefetch_l2(a.dy + cell);
+                if (CELL == kLstm) prefetch_l2(cstate_in + cell);
+            }
+        }
+    };
 
     const uint32_t ds_base = smem_u32(&ds[0][0]);
     const uint32_t ld_off = (uint32_t)(((lane & 7) * DS + 8 * (lane >> 3)) * 2);
+    const uint32_t rs_base = smem_u32(&rs[0][0][0][0]);
+    const uint32_t bar_base = smem_u32(&full[0]);
 
-    for (int s = 0; s < T; s++) {
+    auto step = [&](const int s, In &in, In &nxt_in) {
         const int sf = T - 1 - s;
         const int t = tindex(sf);
         const int cur = s & 1, nxt = cur ^ 1;
-        float dh[2] = {cur_in.dy[0], cur_in.dy[1]};
+        prefetch_in(s + 3);
+        if (tid == 0 && s + 1 < T) mbar_arrive_expect_tx(&full[nxt], kCluster * U * kNB * 4);
+
+        float dh[2] = {in.dy[0], in.dy[1]};
         if (s > 0) {
             mbar_wait(&full[cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
@@ -412,51 +468,51 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             dh[0] += sx; dh[1] += sy;
         }
 
-        float dg[G][2];
 #pragma unroll
         for (int col = 0; col < 2; col++) {
             const bool valid = col == 0 ? v0 : v1;
-            const size_t cell = (size_t)t * N + b0 + col;
+            const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
+            const size_t xrow = ((size_t)t * N + b0 + col) * (G * H) + unit;
+            float dg[G];
             if (CELL == kLstm) {
-                const float gi = cur_in.sv[0][col], gf = cur_in.sv[1][col], gg = cur_in.sv[2][col],
-                            go = cur_in.sv[3][col], c = cur_in.sv[4][col];
-                const float tc = tanhf_(c);
+                const float gi = in.gt[col].x, gf = in.gt[col].y, gg = in.gt[col].z,
+                            go = in.gt[col].w;
+                const float tc = tanhf_(in.c[col]);
                 const float d = dh[col];
                 const float dc = carry[col] + d * go * (1.0f - tc * tc);
-                dg[3][col] = d * tc * go * (1.0f - go);
-                dg[0][col] = dc * gg * gi * (1.0f - gi);
-                dg[2][col] = dc * gi * (1.0f - gg * gg);
-                dg[1][col] = dc * cur_in.prev[col] * gf * (1.0f - gf);
+                dg[3] = d * tc * go * (1.0f - go);
+                dg[0] = dc * gg * gi * (1.0f - gi);
+                dg[2] = dc * gi * (1.0f - gg * gg);
+                dg[1] = dc * in.prev[col] * gf * (1.0f - gf);
                 carry[col] = dc * gf;
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    ds[2 * q + col][g * U + ul] = __float2bfloat16(dg[g]);
             } else {
-                const float gr = cur_in.sv[0][col], gz = cur_in.sv[1][col], gn = cur_in.sv[2][col],
-                            hn = cur_in.sv[3][col];
+                const float gr = in.gt[col].x, gz = in.gt[col].y, gn = in.gt[col].z,
+                            hn = in.gt[col].w;
                 const float d = dh[col] + carry[col];
                 const float dn = d * (1.0f - gz) * (1.0f - gn * gn);      // d n_pre
-                dg[1][col] = d * (cur_in.prev[col] - gn) * gz * (1.0f - gz);
-                dg[0][col] = dn * hn * gr * (1.0f - gr);
-                dg[2][col] = dn;                                          // x-side n gradient
+                dg[1] = d * (in.prev[col] - gn) * gz * (1.0f - gz);
+                dg[0] = dn * hn * gr * (1.0f - gr);
+                dg[2] = dn;                                               // x-side n gradient
                 carry[col] = d * gz;
                 const float dhn = dn * gr;                                // hidden-side n gradient
-                if (valid) a.dhn[cell * H + unit] = dhn;
+                if (valid) __stcs(a.dhn + cell, dhn);
                 // the recurrent product uses the hidden-side gradient for gate n
+                ds[2 * q + col][0 * U + ul] = __float2bfloat16(dg[0]);
+                ds[2 * q + col][1 * U + ul] = __float2bfloat16(dg[1]);
                 ds[2 * q + col][2 * U + ul] = __float2bfloat16(dhn);
             }
             if (valid) {
 #pragma unroll
-                for (int g = 0; g < G; g++)
-                    a.dxproj[cell * (G * H) + (size_t)g * H + unit] = dg[g][col];
+                for (int g = 0; g < G; g++) __stcs(a.dxproj + xrow + (size_t)g * H, dg[g]);
             }
-#pragma unroll
-            for (int g = 0; g < G; g++)
-                if (!(CELL == kGru && g == 2))
-                    ds[2 * q + col][g * U + ul] = __float2bfloat16(dg[g][col]);
         }
+        load_in(nxt_in, s + 1);   // `in` is dead from here on
 
-        load_in(nxt_in, s + 1);   // after this step's inputs were consumed
         if (s + 1 < T) {
             __syncthreads();
-            if (tid == 0) mbar_arrive_expect_tx(&full[nxt], kCluster * U * kNB * 4);
             float acc[MT][2][4];
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)
@@ -481,8 +537,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 for (int mt = 0; mt < MT; mt++) mma_bf16(acc[mt][0], A[mt][KT - 1], bf[0], bf[1]);
             }
             // reduce-scatter: rows of this warp's tiles belong to the CTA owning those units
-            const uint32_t rs_nxt = smem_u32(&rs[nxt][rank][0][0]);
-            const uint32_t bar_local = smem_u32(&full[nxt]);
+            const uint32_t rs_nxt = rs_base + (uint32_t)(((nxt * kCluster + rank) * U * kNB) * 4);
+            const uint32_t bar = bar_base + (uint32_t)(nxt * 8);
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
@@ -493,12 +549,26 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                     const float x = acc[mt][0][2 * half] + acc[mt][1][2 * half];
                     const float y = acc[mt][0][2 * half + 1] + acc[mt][1][2 * half + 1];
                     const uint32_t local = rs_nxt + (uint32_t)((hl * kNB + 2 * q) * 4);
-                    st_async_v2(mapa(local, dest), x, y, mapa(bar_local, dest));
+                    st_async_v2(mapa(local, dest), x, y, mapa(bar, dest));
                 }
             }
+            // ds is rewritten by the next step's gate gradients: every warp of
+            // this CTA must be past its ldmatrix reads first.  The next wait on
+            // `full` implies it (the barrier needs this CTA's own partials too),
+            // except for the pad rows, which are never rewritten.
         }
-        cur_in = nxt_in;
+    };
+
+    In ia, ib;
+    load_in(ia, 0);
+    prefetch_in(1);
+    prefetch_in(2);
+    int s = 0;
+    for (; s + 1 < T; s += 2) {
+        step(s, ia, ib);
+        step(s + 1, ib, ia);
     }
+    if (s < T) step(s, ia, ib);
     cluster_sync_all();
 }
 
@@ -535,8 +605,8 @@ static int check_shape(int T, int N, int H, const void *p0, const void *p1, cons
 using namespace ty;
 
 extern "C" size_t ty_rnn_reserve_bytes(int cell, int T, int N, int H) {
-    const int ns = cell == kLstm ? Cell<kLstm>::NS : Cell<kGru>::NS;
-    return (size_t)T * N * ns * H * sizeof(float);
+    (void)cell;
+    return (size_t)T * N * 5 * H * sizeof(float);
 }
 
 extern "C" int ty_lstm_forward(const float *xproj, const float *w_hh, int T, int N, int H,

@@ -50,7 +50,7 @@ def test_workspace_queries_need_no_gpu(libpath):
     assert lib.ty_crf_flipflop_workspace_bytes(40, 800, 64, 440, 0) < 4096
     assert lib.ty_flipflop_logz_workspace_bytes(4, 800, 64) >= 2 * 800 * 64 * 8 * 4
     assert lib.ty_rnn_reserve_bytes(0, 10, 4, 256) == 10 * 4 * 5 * 256 * 4
-    assert lib.ty_rnn_reserve_bytes(1, 10, 4, 256) == 10 * 4 * 4 * 256 * 4
+    assert lib.ty_rnn_reserve_bytes(1, 10, 4, 256) == 10 * 4 * 5 * 256 * 4
 
 
 def test_ops_refuse_cpu_tensors(libpath):
