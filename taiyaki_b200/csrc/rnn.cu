@@ -133,6 +133,7 @@ struct RnnArgs {
     const float *dy;       // bwd: [T][N][H]
     float *dxproj;         // bwd: [T][N][G*H]
     float *dhn;            // bwd GRU: [T][N][H] gradient of the hidden-side n pre-activation
+    unsigned zero;         // always 0; opaque to the compiler (see `late`)
 };
 
 template <int CELL> struct Cell;
@@ -150,6 +151,23 @@ __device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
         "r"(v), "r"(rbar)
         : "memory");
+}
+// Loads that must stay where they are written: `volatile` asm is ordered with
+// the other volatile asm (st.async, mbarrier), so placing these after the
+// exchange keeps them BELOW the consumers of the current step's inputs.  Hoisted
+// above them (as the compiler does with plain __ldg) they share a scoreboard
+// slot with the older loads and the consumers end up waiting for the new ones.
+__device__ __forceinline__ float ld_nc_pinned(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_nc_pinned4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -214,13 +232,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 
     auto tindex = [&](int s) { return a.reverse ? T - 1 - s : s; };
     auto xaddr = [&](int s) { return a.xproj + ((size_t)tindex(s) * N + b0) * (G * H) + unit; };
-    auto load_x = [&](float (&dst)[G][2], int s) {
+    // `late` is a value produced at the very end of the step; (late & a.zero) is 0
+    // but neither nvcc nor ptxas can know, so the loads cannot be scheduled above
+    // the consumers of the current step's inputs (where they would share a
+    // scoreboard slot with the older loads and stall those consumers).
+    auto load_x = [&](float (&dst)[G][2], int s, uint32_t late) {
         if (s < T) {
-            const float *base = xaddr(s);
+            const float *base = xaddr(s) + (late & a.zero);
 #pragma unroll
             for (int g = 0; g < G; g++) {
-                dst[g][0] = v0 ? __ldg(base + (size_t)g * H) : 0.f;
-                dst[g][1] = v1 ? __ldg(base + (size_t)(G * H) + (size_t)g * H) : 0.f;
+                dst[g][0] = v0 ? ld_nc_pinned(base + (size_t)g * H) : 0.f;
+                dst[g][1] = v1 ? ld_nc_pinned(base + (size_t)(G * H) + (size_t)g * H) : 0.f;
             }
         }
     };
@@ -283,6 +305,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 pre[m][e] = (acc[m][0][e] + acc[m][1][e]) + (acc[m][2][e] + acc[m][3][e]);
 
         float hnew[2];
+        uint32_t late_tok = 0;
 #pragma unroll
         for (int col = 0; col < 2; col++) {
             const bool valid = col == 0 ? v0 : v1;
@@ -312,9 +335,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 __stcs(reinterpret_cast<float4 *>(gates_out) + cell, sv);
                 a.y[cell] = hnew[col];
             }
+            late_tok ^= __float_as_uint(hnew[col]);
         }
-        load_x(xn, s + 1);     // xp is dead from here on
-
         if (s + 1 < T) {
             // Exchange h_t: lanes r and r^1 swap one value so that each thread
             // owns two consecutive units of one chunk (a 4-byte bf16 pair), then
@@ -329,10 +351,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             for (uint32_t peer = 0; peer < kCluster; peer++)
                 st_async_b32(mapa(dst, peer), pair, mapa(bar, peer));
         }
+        load_x(xn, s + 1, late_tok);
     };
 
     float xa[G][2], xb[G][2];
-    load_x(xa, 0);
+    load_x(xa, 0, 0u);
     prefetch_x(1);
     prefetch_x(2);
     int s = 0;
@@ -409,22 +432,23 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 
     // per-step inputs: saved gates, c_t, incoming gradient, c_{t-1} / h_{t-1}
     struct In { float4 gt[2]; float c[2]; float dy[2]; float prev[2]; };
-    auto load_in = [&](In &d, int s) {
+    auto load_in = [&](In &d, int s, uint32_t late) {
         if (s >= T) return;
         const int sf = T - 1 - s;                 // forward step being differentiated
         const int t = tindex(sf);
+        const size_t lz = late & a.zero;          // 0, opaque: see rnn_forward_kernel
 #pragma unroll
         for (int col = 0; col < 2; col++) {
             const bool valid = col == 0 ? v0 : v1;
-            const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
-            d.gt[col] = valid ? __ldcs(gates_in + cell) : make_float4(0.f, 0.f, 0.f, 0.f);
-            d.c[col] = (valid && CELL == kLstm) ? __ldcs(cstate_in + cell) : 0.f;
-            d.dy[col] = valid ? __ldcs(a.dy + cell) : 0.f;
+            const size_t cell = ((size_t)t * N + b0 + col) * H + unit + lz;
+            d.gt[col] = valid ? ld_nc_pinned4(gates_in + cell) : make_float4(0.f, 0.f, 0.f, 0.f);
+            d.c[col] = (valid && CELL == kLstm) ? ld_nc_pinned(cstate_in + cell) : 0.f;
+            d.dy[col] = valid ? ld_nc_pinned(a.dy + cell) : 0.f;
             float pv = 0.f;
             if (valid && sf > 0) {
-                const size_t pcell = ((size_t)tindex(sf - 1) * N + b0 + col) * H + unit;
-                pv = CELL == kLstm ? __ldg(cstate_in + pcell)      // c_{t-1}
-                                   : __ldg(a.y + pcell);           // h_{t-1}
+                const size_t pcell = ((size_t)tindex(sf - 1) * N + b0 + col) * H + unit + lz;
+                pv = CELL == kLstm ? ld_nc_pinned(cstate_in + pcell)      // c_{t-1}
+                                   : ld_nc_pinned(a.y + pcell);           // h_{t-1}
             }
             d.prev[col] = pv;
         }
@@ -456,6 +480,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
         if (tid == 0 && s + 1 < T) mbar_arrive_expect_tx(&full[nxt], kCluster * U * kNB * 4);
 
         float dh[2] = {in.dy[0], in.dy[1]};
+        uint32_t late_tok = 0;
         if (s > 0) {
             mbar_wait(&full[cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
@@ -508,9 +533,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 #pragma unroll
                 for (int g = 0; g < G; g++) __stcs(a.dxproj + xrow + (size_t)g * H, dg[g]);
             }
+            late_tok ^= __float_as_uint(dg[0]) ^ __float_as_uint(carry[col]);
         }
-        load_in(nxt_in, s + 1);   // `in` is dead from here on
-
         if (s + 1 < T) {
             __syncthreads();
             float acc[MT][2][4];
@@ -557,10 +581,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             // `full` implies it (the barrier needs this CTA's own partials too),
             // except for the pad rows, which are never rewritten.
         }
+        load_in(nxt_in, s + 1, late_tok);
     };
 
     In ia, ib;
-    load_in(ia, 0);
+    load_in(ia, 0, 0u);
     prefetch_in(1);
     prefetch_in(2);
     int s = 0;
