@@ -128,6 +128,11 @@ int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatch,
  * xproj: [T][N][G*H] = x W_ih^T + b_ih computed by the caller (one large
  * GEMM); w_hh: [G*H][H] fp32; reverse != 0 iterates t downward
  * (layers.py:117-153 without the two flips).  G = 4 (LSTM) or 3 (GRU).
+ * Backward writes dxproj [T][N][G*H] (gradient of xproj), for the GRU also
+ * dhn [T][N][H] (gradient of the hidden-side n pre-activation W_hn h, which
+ * differs from the x-side one by the reset gate), and ADDS the bias gradient
+ * (sum of dxproj over time and chunks) into dbias [G*H] when it is not NULL.
+ * Weight and input gradients are dense GEMMs the caller does over all steps.
  */
 size_t ty_rnn_reserve_bytes(int cell, int T, int N, int H);
 
@@ -135,12 +140,12 @@ int ty_lstm_forward(const float *xproj, const float *w_hh, int T, int N, int H,
                     int reverse, float *y, void *reserve, void *stream);
 int ty_lstm_backward(const float *dy, const float *w_hh, int T, int N, int H,
                      int reverse, const float *y, const void *reserve,
-                     float *dxproj, void *stream);
+                     float *dxproj, float *dbias, void *stream);
 int ty_gru_forward(const float *xproj, const float *w_hh, int T, int N, int H,
                    int reverse, float *y, void *reserve, void *stream);
 int ty_gru_backward(const float *dy, const float *w_hh, int T, int N, int H,
                     int reverse, const float *y, const void *reserve,
-                    float *dxproj, float *dhproj, void *stream);
+                    float *dxproj, float *dhn, float *dbias, void *stream);
 
 #ifdef __cplusplus
 }

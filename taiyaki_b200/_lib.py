@@ -38,11 +38,11 @@ _SIGNATURES = {
     'ty_lstm_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p]),
     'ty_lstm_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                 c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     'ty_gru_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                c_void_p, c_void_p]),
     'ty_gru_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 # host-pointer drop-ins carrying the reference's own names (libctc.pxd:3-25)
 HOST_ABI = ['crf_flipflop_grad', 'crf_flipflop_cost', 'cat_mod_flipflop_grad',

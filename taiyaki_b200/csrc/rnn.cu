@@ -134,6 +134,7 @@ struct RnnArgs {
     float *dxproj;         // bwd: [T][N][G*H]
     float *dhn;            // bwd GRU: [T][N][H] gradient of the hidden-side n pre-activation
     unsigned zero;         // always 0; opaque to the compiler (see `late`)
+    float *dbias;          // bwd: [G*H] += sum over time and chunks of dxproj (may be null)
 };
 
 template <int CELL> struct Cell;
@@ -428,6 +429,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 
     uint32_t phase = 0u;
     float carry[2] = {0.f, 0.f};   // LSTM: dL/dc carried back; GRU: z * dL/dh carried back
+    float dbacc[G];                // bias gradient of this thread's unit: sum over time and its chunks
+#pragma unroll
+    for (int g = 0; g < G; g++) dbacc[g] = 0.f;
     auto tindex = [&](int sf) { return a.reverse ? T - 1 - sf : sf; };   // forward step -> time
 
     // per-step inputs: saved gates, c_t, incoming gradient, c_{t-1} / h_{t-1}
@@ -531,7 +535,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             }
             if (valid) {
 #pragma unroll
-                for (int g = 0; g < G; g++) __stcs(a.dxproj + xrow + (size_t)g * H, dg[g]);
+                for (int g = 0; g < G; g++) {
+                    __stcs(a.dxproj + xrow + (size_t)g * H, dg[g]);
+                    dbacc[g] += dg[g];
+                }
             }
             late_tok ^= __float_as_uint(dg[0]) ^ __float_as_uint(carry[col]);
         }
@@ -581,7 +588,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             // `full` implies it (the barrier needs this CTA's own partials too),
             // except for the pad rows, which are never rewritten.
         }
-        load_in(nxt_in, s + 1, late_tok);
+        load_in(nxt_in, s + 1, late_tok);   // after this step's inputs were consumed (see forward)
     };
 
     In ia, ib;
@@ -594,6 +601,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
         step(s + 1, ib, ia);
     }
     if (s < T) step(s, ia, ib);
+    if (a.dbias) {
+#pragma unroll
+        for (int g = 0; g < G; g++) atomicAdd(a.dbias + (size_t)g * H + unit, dbacc[g]);
+    }
     cluster_sync_all();
 }
 
@@ -646,14 +657,14 @@ extern "C" int ty_lstm_forward(const float *xproj, const float *w_hh, int T, int
 
 extern "C" int ty_lstm_backward(const float *dy, const float *w_hh, int T, int N, int H,
                                 int reverse, const float *y, const void *reserve, float *dxproj,
-                                void *stream) {
+                                float *dbias, void *stream) {
     if (int rc = check_shape(T, N, H, dy, w_hh, dxproj)) return rc;
     if (!reserve) { set_error("ty_lstm_backward: reserve is null"); return TY_EINVAL; }
     RnnArgs a{};
     a.dy = dy; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse;
     a.y = const_cast<float *>(y);
     a.reserve = const_cast<float *>(static_cast<const float *>(reserve));
-    a.dxproj = dxproj;
+    a.dxproj = dxproj; a.dbias = dbias;
     return launch_rnn<kLstm>(true, a, H, static_cast<cudaStream_t>(stream));
 }
 
@@ -669,13 +680,13 @@ extern "C" int ty_gru_forward(const float *xproj, const float *w_hh, int T, int 
 
 extern "C" int ty_gru_backward(const float *dy, const float *w_hh, int T, int N, int H,
                                int reverse, const float *y, const void *reserve, float *dxproj,
-                               float *dhn, void *stream) {
+                               float *dhn, float *dbias, void *stream) {
     if (int rc = check_shape(T, N, H, dy, w_hh, dxproj)) return rc;
     if (!reserve || !y || !dhn) { set_error("ty_gru_backward: null pointer"); return TY_EINVAL; }
     RnnArgs a{};
     a.dy = dy; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse;
     a.y = const_cast<float *>(y);
     a.reserve = const_cast<float *>(static_cast<const float *>(reserve));
-    a.dxproj = dxproj; a.dhn = dhn;
+    a.dxproj = dxproj; a.dhn = dhn; a.dbias = dbias;
     return launch_rnn<kGru>(true, a, H, static_cast<cudaStream_t>(stream));
 }

@@ -123,15 +123,18 @@ class _Recurrence(torch.autograd.Function):
         dy = dy.contiguous().float()
         dxproj = torch.empty(T, N, G * H, dtype=torch.float32, device=x.device)
         stream = _lib.stream_ptr(x.device)
+        # the bias gradient (sum of dxproj over time and chunks) comes out of the kernel
+        db = torch.zeros(G * H, dtype=torch.float32, device=x.device) if has_bias else None
         if cell == _CELL_LSTM:
             rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
-                                      _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj), stream)
+                                      _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
+                                      _lib.ptr(db), stream)
             dhn = None
         else:
             dhn = torch.empty(T, N, H, dtype=torch.float32, device=x.device)
             rc = lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
                                      _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
-                                     _lib.ptr(dhn), stream)
+                                     _lib.ptr(dhn), _lib.ptr(db), stream)
         _lib.check(rc, 'ty_rnn_backward')
         _lib.count_launches(1)
         d2 = dxproj.view(T * N, G * H)
@@ -152,7 +155,6 @@ class _Recurrence(torch.autograd.Function):
                 dw_hh = torch.cat([
                     d_cur[:, :, :2 * H].reshape(-1, 2 * H).t() @ hp2,
                     dhn_cur.reshape(-1, H).t() @ hp2], 0)
-        db = d2.sum(0) if has_bias else None
         return dx, dw_ih, dw_hh, db, None, None
 
 

@@ -78,14 +78,14 @@ def kernel_backward(cell, dy, w_hh, reverse, y, reserve):
     dx = torch.empty(T, N, G * H, device=dy.device)
     if cell == 'lstm':
         rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, int(reverse),
-                                  _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dx),
+                                  _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dx), None,
                                   _lib.stream_ptr(dy.device))
         dhn = None
     else:
         dhn = torch.empty(T, N, H, device=dy.device)
         rc = lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, int(reverse),
                                  _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dx), _lib.ptr(dhn),
-                                 _lib.stream_ptr(dy.device))
+                                 None, _lib.stream_ptr(dy.device))
     _lib.check(rc, 'backward')
     return dx, dhn
 
