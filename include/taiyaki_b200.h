@@ -125,8 +125,9 @@ int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatch,
 /* ----------------------------------------------------------------------
  * Recurrent layers (time-major [T][N][H], PyTorch gate order, b_hh == 0).
  * See taiyaki_b200/csrc/rnn.cu for the data layout of `reserve`.
- * xproj: [T][N][G*H] = x W_ih^T + b_ih computed by the caller (one large
- * GEMM); w_hh: [G*H][H] fp32; reverse != 0 iterates t downward
+ * xproj: [T][N][G*H] = x W_ih^T computed by the caller (one large GEMM);
+ * bias: [G*H] input bias b_ih added inside the kernel (NULL if already in
+ * xproj); w_hh: [G*H][H] fp32; reverse != 0 iterates t downward
  * (layers.py:117-153 without the two flips).  G = 4 (LSTM) or 3 (GRU).
  * Backward writes dxproj [T][N][G*H] (gradient of xproj), for the GRU also
  * dhn [T][N][H] (gradient of the hidden-side n pre-activation W_hn h, which
@@ -136,13 +137,15 @@ int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatch,
  */
 size_t ty_rnn_reserve_bytes(int cell, int T, int N, int H);
 
-int ty_lstm_forward(const float *xproj, const float *w_hh, int T, int N, int H,
-                    int reverse, float *y, void *reserve, void *stream);
+int ty_lstm_forward(const float *xproj, const float *bias, const float *w_hh,
+                    int T, int N, int H, int reverse, float *y, void *reserve,
+                    void *stream);
 int ty_lstm_backward(const float *dy, const float *w_hh, int T, int N, int H,
                      int reverse, const float *y, const void *reserve,
                      float *dxproj, float *dbias, void *stream);
-int ty_gru_forward(const float *xproj, const float *w_hh, int T, int N, int H,
-                   int reverse, float *y, void *reserve, void *stream);
+int ty_gru_forward(const float *xproj, const float *bias, const float *w_hh,
+                   int T, int N, int H, int reverse, float *y, void *reserve,
+                   void *stream);
 int ty_gru_backward(const float *dy, const float *w_hh, int T, int N, int H,
                     int reverse, const float *y, const void *reserve,
                     float *dxproj, float *dhn, float *dbias, void *stream);

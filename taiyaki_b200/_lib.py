@@ -35,12 +35,12 @@ _SIGNATURES = {
     'ty_flipflop_logz': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                  c_float, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     'ty_rnn_reserve_bytes': (c_size_t, [c_int] * 4),
-    'ty_lstm_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                c_void_p, c_void_p]),
+    'ty_lstm_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p]),
     'ty_lstm_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
-    'ty_gru_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                               c_void_p, c_void_p]),
+    'ty_gru_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p]),
     'ty_gru_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -135,6 +135,7 @@ struct RnnArgs {
     float *dhn;            // bwd GRU: [T][N][H] gradient of the hidden-side n pre-activation
     unsigned zero;         // always 0; opaque to the compiler (see `late`)
     float *dbias;          // bwd: [G*H] += sum over time and chunks of dxproj (may be null)
+    const float *bias;     // fwd: [G*H] added to xproj (may be null)
 };
 
 template <int CELL> struct Cell;
@@ -230,6 +231,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 
     float cst[2] = {0.f, 0.f};    // LSTM cell state / GRU previous h (fp32)
     uint32_t phase = 0u;          // bit b = parity to wait for on full[b]
+    // input bias of this thread's unit; it seeds the accumulators, so adding it is free
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.bias) {
+#pragma unroll
+        for (int g = 0; g < G; g++) bias[g] = a.bias[(size_t)g * H + unit];
+    }
 
     auto tindex = [&](int s) { return a.reverse ? T - 1 - s : s; };
     auto xaddr = [&](int s) { return a.xproj + ((size_t)tindex(s) * N + b0) * (G * H) + unit; };
@@ -287,6 +294,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             for (int c = 0; c < 4; c++)
 #pragma unroll
                 for (int e = 0; e < 4; e++) acc[m][c][e] = 0.f;
+        // element e of tile m: gate 2m + (e >> 1), column e & 1.  (For the GRU the
+        // n-gate bias belongs to the x side: it is added below, not to W_hn h.)
+        acc[0][0][0] = bias[0]; acc[0][0][1] = bias[0];
+        acc[0][0][2] = bias[1]; acc[0][0][3] = bias[1];
+        if (CELL == kLstm) {
+            acc[1][0][0] = bias[2]; acc[1][0][1] = bias[2];
+            acc[1][0][2] = bias[3]; acc[1][0][3] = bias[3];
+        }
 
         const uint32_t hcur = hs_base + (uint32_t)(cur * kNB * HS * 2) + ld_off;
 #pragma unroll
@@ -326,7 +341,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 const float hn = pre[1][col];
                 const float gr = sigmoidf_(pre[0][col] + xp[0][col]);
                 const float gz = sigmoidf_(pre[0][2 + col] + xp[1][col]);
-                const float gn = tanhf_(xp[2][col] + gr * hn);
+                const float gn = tanhf_(xp[2][col] + bias[2] + gr * hn);
                 const float h = (1.0f - gz) * gn + gz * cst[col];
                 cst[col] = h;
                 hnew[col] = h;
@@ -645,12 +660,13 @@ extern "C" size_t ty_rnn_reserve_bytes(int cell, int T, int N, int H) {
     return (size_t)T * N * 5 * H * sizeof(float);
 }
 
-extern "C" int ty_lstm_forward(const float *xproj, const float *w_hh, int T, int N, int H,
-                               int reverse, float *y, void *reserve, void *stream) {
+extern "C" int ty_lstm_forward(const float *xproj, const float *bias, const float *w_hh, int T,
+                               int N, int H, int reverse, float *y, void *reserve,
+                               void *stream) {
     if (int rc = check_shape(T, N, H, xproj, w_hh, y)) return rc;
     if (!reserve) { set_error("ty_lstm_forward: reserve is null"); return TY_EINVAL; }
     RnnArgs a{};
-    a.xproj = xproj; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse; a.y = y;
+    a.xproj = xproj; a.bias = bias; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse; a.y = y;
     a.reserve = static_cast<float *>(reserve);
     return launch_rnn<kLstm>(false, a, H, static_cast<cudaStream_t>(stream));
 }
@@ -668,12 +684,13 @@ extern "C" int ty_lstm_backward(const float *dy, const float *w_hh, int T, int N
     return launch_rnn<kLstm>(true, a, H, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int ty_gru_forward(const float *xproj, const float *w_hh, int T, int N, int H,
-                              int reverse, float *y, void *reserve, void *stream) {
+extern "C" int ty_gru_forward(const float *xproj, const float *bias, const float *w_hh, int T,
+                              int N, int H, int reverse, float *y, void *reserve,
+                              void *stream) {
     if (int rc = check_shape(T, N, H, xproj, w_hh, y)) return rc;
     if (!reserve) { set_error("ty_gru_forward: reserve is null"); return TY_EINVAL; }
     RnnArgs a{};
-    a.xproj = xproj; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse; a.y = y;
+    a.xproj = xproj; a.bias = bias; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse; a.y = y;
     a.reserve = static_cast<float *>(reserve);
     return launch_rnn<kGru>(false, a, H, static_cast<cudaStream_t>(stream));
 }

@@ -63,11 +63,14 @@ def _reshape(x, shape):
     return x.reshape(shape)
 
 
-class _tf32_matmul:
-    """The dense input/weight-gradient projections run on the tensor cores with
-    TF32 operands and fp32 accumulation (what cuDNN does for the reference on
-    Ampere and later: torch.backends.cudnn.allow_tf32 defaults to True)."""
+#: Operand type of the dense projection GEMMs around the recurrence
+#: (x W_ih^T, and the weight / input gradients): 'bf16' (tensor cores, fp32
+#: accumulate and fp32 result -- north_star's "dense bf16 contractions") or
+#: 'tf32' (what cuDNN does for the reference on Ampere and later).
+PROJECTION_DTYPE = 'bf16'
 
+
+class _tf32_matmul:
     def __enter__(self):
         self.prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -76,14 +79,28 @@ class _tf32_matmul:
         torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
+def _mm(a, b):
+    """a @ b with fp32 result; bf16 operands go to the tensor cores with fp32
+    accumulation, fp32 operands use TF32."""
+    if a.dtype == torch.bfloat16:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    with _tf32_matmul():
+        return torch.mm(a, b)
+
+
+def _operand(t):
+    return t.to(torch.bfloat16) if PROJECTION_DTYPE == 'bf16' else t
+
+
 # ---------------------------------------------------------------------------
 # recurrence
 class _Recurrence(torch.autograd.Function):
     """y = RNN(x) with the sequential part in csrc/rnn.cu.
 
-    forward:  xproj = x W_ih^T + b_ih (one GEMM) -> ty_{lstm,gru}_forward
-    backward: ty_{lstm,gru}_backward gives d xproj (and the hidden-side n-gate
-              gradient for the GRU); weight / input gradients are dense GEMMs.
+    forward:  xproj = x W_ih^T (one GEMM) -> ty_{lstm,gru}_forward (adds b_ih)
+    backward: ty_{lstm,gru}_backward gives d xproj, the bias gradient (and the
+              hidden-side n-gate gradient for the GRU); weight / input
+              gradients are dense GEMMs over all time steps.
     """
 
     @staticmethod
@@ -95,66 +112,67 @@ class _Recurrence(torch.autograd.Function):
         H = w_hh.shape[1]
         x = x.contiguous().float()
         w_hh_c = w_hh.detach().contiguous().float()
-        x2 = x.view(T * N, I)
-        with _tf32_matmul():
-            if b_ih is not None:
-                xproj = torch.addmm(b_ih.detach(), x2, w_ih.detach().t())
-            else:
-                xproj = x2 @ w_ih.detach().t()
+        xo = _operand(x.view(T * N, I))
+        wo = _operand(w_ih.detach())
+        xproj = _mm(xo, wo.t())
+        bias = b_ih.detach().contiguous().float() if b_ih is not None else None
         y = torch.empty(T, N, H, dtype=torch.float32, device=x.device)
         reserve = torch.empty(lib.ty_rnn_reserve_bytes(cell, T, N, H) // 4,
                               dtype=torch.float32, device=x.device)
         fn = lib.ty_lstm_forward if cell == _CELL_LSTM else lib.ty_gru_forward
         with _lib.timed('rnn_fwd', x.device):
-            rc = fn(_lib.ptr(xproj), _lib.ptr(w_hh_c), T, N, H, int(reverse), _lib.ptr(y),
-                    _lib.ptr(reserve), _lib.stream_ptr(x.device))
+            rc = fn(_lib.ptr(xproj), _lib.ptr(bias), _lib.ptr(w_hh_c), T, N, H, int(reverse),
+                    _lib.ptr(y), _lib.ptr(reserve), _lib.stream_ptr(x.device))
         _lib.check(rc, 'ty_rnn_forward')
         _lib.count_launches(1)
-        ctx.save_for_backward(x, w_ih, w_hh_c, y, reserve)
-        ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H)
+        ctx.save_for_backward(xo, wo, w_hh_c, y, reserve)
+        ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H, I)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.lib()
-        x, w_ih, w_hh_c, y, reserve = ctx.saved_tensors
-        cell, reverse, has_bias, G, H = ctx.cfg
-        T, N, I = x.shape
+        xo, wo, w_hh_c, y, reserve = ctx.saved_tensors
+        cell, reverse, has_bias, G, H, I = ctx.cfg
+        T, N, _ = y.shape
+        dev = y.device
         dy = dy.contiguous().float()
-        dxproj = torch.empty(T, N, G * H, dtype=torch.float32, device=x.device)
-        stream = _lib.stream_ptr(x.device)
+        dxproj = torch.empty(T, N, G * H, dtype=torch.float32, device=dev)
+        stream = _lib.stream_ptr(dev)
         # the bias gradient (sum of dxproj over time and chunks) comes out of the kernel
-        db = torch.zeros(G * H, dtype=torch.float32, device=x.device) if has_bias else None
-        if cell == _CELL_LSTM:
-            rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
-                                      _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
-                                      _lib.ptr(db), stream)
-            dhn = None
-        else:
-            dhn = torch.empty(T, N, H, dtype=torch.float32, device=x.device)
-            rc = lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
-                                     _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
-                                     _lib.ptr(dhn), _lib.ptr(db), stream)
+        db = torch.zeros(G * H, dtype=torch.float32, device=dev) if has_bias else None
+        with _lib.timed('rnn_bwd', dev):
+            if cell == _CELL_LSTM:
+                rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
+                                          _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
+                                          _lib.ptr(db), stream)
+                dhn = None
+            else:
+                dhn = torch.empty(T, N, H, dtype=torch.float32, device=dev)
+                rc = lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
+                                         _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
+                                         _lib.ptr(dhn), _lib.ptr(db), stream)
         _lib.check(rc, 'ty_rnn_backward')
         _lib.count_launches(1)
-        d2 = dxproj.view(T * N, G * H)
+        do = _operand(dxproj)                      # [T, N, G*H]
+        yo = _operand(y)
+        d2 = do.view(T * N, G * H)
         # h_{t-1} of every step is y shifted by one step along the loop direction
         if reverse:
-            d_cur, h_prev = dxproj[:-1], y[1:]
-            dhn_cur = dhn[:-1] if dhn is not None else None
+            d_cur, h_prev = do[:-1], yo[1:]
         else:
-            d_cur, h_prev = dxproj[1:], y[:-1]
-            dhn_cur = dhn[1:] if dhn is not None else None
+            d_cur, h_prev = do[1:], yo[:-1]
         hp2 = h_prev.reshape(-1, H)
-        with _tf32_matmul():
-            dx = (d2 @ w_ih).view(T, N, I) if ctx.needs_input_grad[0] else None
-            dw_ih = d2.t() @ x.view(T * N, I)
-            if cell == _CELL_LSTM:
-                dw_hh = d_cur.reshape(-1, G * H).t() @ hp2
-            else:
-                dw_hh = torch.cat([
-                    d_cur[:, :, :2 * H].reshape(-1, 2 * H).t() @ hp2,
-                    dhn_cur.reshape(-1, H).t() @ hp2], 0)
+        dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
+        dw_ih = _mm(d2.t(), xo)
+        if cell == _CELL_LSTM:
+            dw_hh = _mm(d_cur.reshape(-1, G * H).t(), hp2)
+        else:
+            dhn_o = _operand(dhn)
+            dhn_cur = dhn_o[:-1] if reverse else dhn_o[1:]
+            dw_hh = torch.cat([
+                _mm(d_cur[:, :, :2 * H].reshape(-1, 2 * H).t(), hp2),
+                _mm(dhn_cur.reshape(-1, H).t(), hp2)], 0)
         return dx, dw_ih, dw_hh, db, None, None
 
 

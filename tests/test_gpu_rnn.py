@@ -64,7 +64,7 @@ def kernel_forward(cell, xproj, w_hh, reverse):
     y = torch.empty(T, N, H, device=xproj.device)
     reserve = torch.empty(lib.ty_rnn_reserve_bytes(code, T, N, H) // 4, device=xproj.device)
     fn = lib.ty_lstm_forward if cell == 'lstm' else lib.ty_gru_forward
-    rc = fn(_lib.ptr(xproj), _lib.ptr(w_hh), T, N, H, int(reverse), _lib.ptr(y),
+    rc = fn(_lib.ptr(xproj), None, _lib.ptr(w_hh), T, N, H, int(reverse), _lib.ptr(y),
             _lib.ptr(reserve), _lib.stream_ptr(xproj.device))
     _lib.check(rc, 'forward')
     return y, reserve

@@ -145,10 +145,10 @@ def bench_rnn(cell, T, N, H, tag):
     dhn = torch.empty(T, N, H, device=dev)
     st = _lib.stream_ptr(dev)
     if cell == 'lstm':
-        f = lambda: lib.ty_lstm_forward(_lib.ptr(xproj), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), st)
+        f = lambda: lib.ty_lstm_forward(_lib.ptr(xproj), None, _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), st)
         b = lambda: lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxp), None, st)
     else:
-        f = lambda: lib.ty_gru_forward(_lib.ptr(xproj), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), st)
+        f = lambda: lib.ty_gru_forward(_lib.ptr(xproj), None, _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), st)
         b = lambda: lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxp), _lib.ptr(dhn), None, st)
     for name, fn in [('kernel_fwd', f), ('kernel_bwd', b)]:
         med, mn = timeit(fn, iters=5, warmup=2)
