@@ -271,7 +271,7 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'bf16 recurrent product / tf32 projections / f32 loss',
+        'vs_baseline': None, 'dtype': 'bf16 tensor-core products (fp32 accumulate) / f32 state, gates and loss',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'chunks_per_gpu': NCHUNK, 'global_chunks': NCHUNK * world,
                    'parallelism': 'dp%d' % world,

@@ -319,6 +319,50 @@ class Serial(nn.Module):
                             ('sublayers', [layer.json() for layer in self.sublayers])])
 
 
+class _ConvTimeMajor(torch.autograd.Function):
+    """1D convolution of a time-major [T, N, C] tensor as window-gather + one
+    dense GEMM, producing time-major [T_out, N, C_out] directly (no TBF<->BFT
+    permutes, layers.py:816-831).  Backward: weight gradient and column
+    gradient are GEMMs, the column gradient is scattered back with `fold`.
+    Same arithmetic as nn.Conv1d on the zero-padded signal."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding):
+        T, N, C = x.shape
+        Cout, _, k = weight.shape
+        xp = torch.nn.functional.pad(x, (0, 0, 0, 0, padding[0], padding[1]))
+        Tp = xp.shape[0]
+        Tout = (Tp - k) // stride + 1
+        cols = xp.unfold(0, k, stride).reshape(Tout * N, C * k)     # [T_out*N, C*k]
+        wide = C * k >= 64
+        co = _operand(cols) if wide else cols
+        wo = weight.detach().reshape(Cout, C * k)
+        wo = _operand(wo) if wide else wo
+        out = _mm(co, wo.t())
+        if bias is not None:
+            out += bias.detach()
+        ctx.save_for_backward(co, wo)
+        ctx.cfg = (T, N, C, Cout, k, stride, padding, Tp, Tout, wide, bias is not None)
+        return out.view(Tout, N, Cout)
+
+    @staticmethod
+    def backward(ctx, dout):
+        co, wo = ctx.saved_tensors
+        T, N, C, Cout, k, stride, padding, Tp, Tout, wide, has_bias = ctx.cfg
+        d2 = dout.reshape(Tout * N, Cout)
+        db = d2.sum(0) if has_bias else None
+        do = _operand(d2) if wide else d2
+        dw = _mm(do.t(), co).view(Cout, C, k)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcols = _mm(do, wo)                                     # [T_out*N, C*k]
+            dcols = dcols.view(Tout, N, C * k).permute(1, 2, 0)     # [N, C*k, T_out]
+            dxp = torch.nn.functional.fold(dcols, output_size=(1, Tp), kernel_size=(1, k),
+                                           stride=(1, stride))      # [N, C, 1, Tp]
+            dx = dxp[:, :, 0, padding[0]:padding[0] + T].permute(2, 0, 1)
+        return dx, dw, db, None, None
+
+
 class Convolution(nn.Module):
     """1D convolution over time for [T, N, F] tensors (layers.py:744-850)."""
 
@@ -347,6 +391,10 @@ class Convolution(nn.Module):
             init_(self.conv.bias, truncated_normal(list(self.conv.bias.shape), sd=0.5))
 
     def forward(self, x):
+        if x.is_cuda:
+            out = _ConvTimeMajor.apply(x, self.conv.weight, self.conv.bias, self.stride,
+                                       self.padding)
+            return self.activation(out)
         x = x.permute(1, 2, 0)
         out = self.activation(self.conv(self.pad(x)))
         return out.permute(2, 0, 1)

@@ -118,3 +118,29 @@ def test_train_flipflop_entry_point(dev, tmp_path):
     assert (out / 'model_final.checkpoint').exists()
     assert (out / 'model_checkpoint_00001.checkpoint').exists()
     assert 'ksample/s' in (out / 'model.log').read_text()
+
+
+@pytest.mark.parametrize('C,Cout,k,stride', [(1, 4, 5, 1), (4, 16, 5, 1), (16, 256, 19, 5),
+                                             (1, 256, 19, 2)])
+def test_convolution_matches_conv1d(dev, C, Cout, k, stride):
+    """layers.Convolution (window gather + GEMM, time-major) against nn.Conv1d on the
+    zero-padded signal (taiyaki/layers.py:791-831); wide layers use bf16 operands."""
+    from taiyaki_b200 import layers
+    from taiyaki_b200.activation import linear
+    torch.manual_seed(0)
+    np.random.seed(0)
+    conv = layers.Convolution(C, Cout, k, stride=stride, fun=linear).to(dev)
+    x1 = torch.randn(403, 5, C, device=dev, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    y1 = conv(x1)
+    y2 = conv.conv(conv.pad(x2.permute(1, 2, 0))).permute(2, 0, 1)
+    assert y1.shape == y2.shape == (-(-403 // stride), 5, Cout)
+    g = torch.randn_like(y2)
+    y1.backward(g)
+    gw1 = conv.conv.weight.grad.clone()
+    conv.zero_grad()
+    y2.backward(g)
+    tol = 2e-2 if C * k >= 64 else 1e-3
+    assert (y1 - y2).abs().max().item() < tol * max(1.0, y2.abs().max().item())
+    assert ((x1.grad - x2.grad).norm() / x2.grad.norm()).item() < tol
+    assert ((gw1 - conv.conv.weight.grad).norm() / conv.conv.weight.grad.norm()).item() < tol
