@@ -236,16 +236,23 @@ def main():
     peak, peak_src = measured_peak()
     nblk = -(-T_SIG // STRIDE)
     alg_bytes = 2 * NTRANS * 4 * nblk * NCHUNK
-    crf_ms = [a.elapsed_time(b) for a, b in prof.get('crf_fwd_bwd', [])]
+    key = 'loss_fwd_bwd' if 'loss_fwd_bwd' in prof else 'crf_fwd_bwd'
+    crf_ms = [a.elapsed_time(b) for a, b in prof.get(key, [])]
     rnn_ms = [a.elapsed_time(b) for a, b in prof.get('rnn_fwd', [])]
+    rnnb_ms = [a.elapsed_time(b) for a, b in prof.get('rnn_bwd', [])]
     crf_avg = float(np.mean(crf_ms)) if crf_ms else float('nan')
     achieved = alg_bytes / (crf_avg * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'crf_chain_kernel + crf_grad_kernel (CRF fwd-bwd)',
+    kname = ('ty_flipflop_train_loss: crf_chain_kernel || logz_chain_kernel, crf_post_kernel, '
+             'logz_post_kernel (fused CRF loss + logZ/nblk, fwd-bwd)' if key == 'loss_fwd_bwd'
+             else 'crf_chain_kernel + crf_post_kernel (CRF fwd-bwd)')
+    roofline = {'bound': 'hbm', 'kernel': kname,
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes': alg_bytes,
                 'avg_launch_ms': crf_avg, 'launches_timed': len(crf_ms),
-                'share_of_step': crf_avg / (ms_dev / K)}
+                'share_of_step': crf_avg / (ms_dev / K),
+                'note': 'latency-bound sequential DP (nblk dependent steps); see DESIGN.md 4.1'}
     extra = {'rnn_fwd_kernel_ms_avg': float(np.mean(rnn_ms)) if rnn_ms else None,
+             'rnn_bwd_kernel_ms_avg': float(np.mean(rnnb_ms)) if rnnb_ms else None,
              'rnn_layers': 5, 'trainable_params': nparam, 'loss': loss}
 
     if rank != 0:

@@ -122,6 +122,30 @@ int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatch,
                      int accumulate, void *workspace, size_t workspace_bytes,
                      void *stream);
 
+/* The same in two phases (bit 0: lattice chains, bit 1: posterior), so the
+ * chains can be overlapped with other work. */
+int ty_flipflop_logz_phase(const float *scores, int ld, int nblk, int nbatch,
+                           int nbase, float logz_scale, float *logz_out,
+                           float grad_scale, float *grad_out, int ld_grad,
+                           int accumulate, void *workspace, size_t workspace_bytes,
+                           int phases, void *stream);
+
+/* The whole training loss of bin/train_flipflop.py:163-182 in one call:
+ *   cost_out[b] = CRF cost (= -score / nblk / sharp), logz_out[b] = logZ_b / nblk,
+ *   grad_out    = d (cost_b + logZ_b / nblk) / d scores   [nblk][nbatch][ntrans]
+ * The two families of chains run concurrently (side stream inside the library);
+ * ncan = number of stay/move transition columns (40), the remaining
+ * ntrans - ncan columns are the cat-mod stream (modmoveidx != NULL). */
+size_t ty_flipflop_train_loss_workspace_bytes(int ntrans, int nblk, int nbatch,
+                                              int max_seqlen, int want_grad);
+int ty_flipflop_train_loss(const float *scores, int ntrans, int nblk, int nbatch,
+                           const int32_t *moveidx, const int32_t *stayidx,
+                           const int32_t *modmoveidx, const float *modmovefact,
+                           const int32_t *seqlen, int max_seqlen, float sharp,
+                           int ncan, float *cost_out, float *logz_out,
+                           float *grad_out, void *workspace, size_t workspace_bytes,
+                           void *stream);
+
 /* ----------------------------------------------------------------------
  * Recurrent layers (time-major [T][N][H], PyTorch gate order, b_hh == 0).
  * See taiyaki_b200/csrc/rnn.cu for the data layout of `reserve`.
@@ -149,6 +173,20 @@ int ty_gru_forward(const float *xproj, const float *bias, const float *w_hh,
 int ty_gru_backward(const float *dy, const float *w_hh, int T, int N, int H,
                     int reverse, const float *y, const void *reserve,
                     float *dxproj, float *dhn, float *dbias, void *stream);
+
+/* Extended forms used by the Python layer (cell: 0 = LSTM, 1 = GRU).
+ * y_bf16 (may be NULL): additionally write y as bf16 [T][N][H], the operand of
+ * the next layer's projection GEMM and of this layer's weight-gradient GEMM.
+ * grads_bf16 != 0: dxproj / dhn point to bf16 buffers (same shapes); they are
+ * only ever GEMM operands, and the bias gradient is accumulated in fp32 before
+ * rounding. */
+int ty_rnn_forward_ex(int cell, const float *xproj, const float *bias,
+                      const float *w_hh, int T, int N, int H, int reverse,
+                      float *y, void *y_bf16, void *reserve, void *stream);
+int ty_rnn_backward_ex(int cell, const float *dy, const float *w_hh, int T, int N,
+                       int H, int reverse, const float *y, const void *reserve,
+                       void *dxproj, void *dhn, int grads_bf16, float *dbias,
+                       void *stream);
 
 #ifdef __cplusplus
 }

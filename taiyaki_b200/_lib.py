@@ -34,7 +34,19 @@ _SIGNATURES = {
     'ty_flipflop_logz_workspace_bytes': (c_size_t, [c_int] * 3),
     'ty_flipflop_logz': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                  c_float, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'ty_flipflop_logz_phase': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                       c_float, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int,
+                                       c_void_p]),
+    'ty_flipflop_train_loss_workspace_bytes': (c_size_t, [c_int] * 5),
+    'ty_flipflop_train_loss': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int, c_float, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ty_rnn_reserve_bytes': (c_size_t, [c_int] * 4),
+    'ty_rnn_forward_ex': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ty_rnn_backward_ex': (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                   c_void_p]),
     'ty_lstm_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
     'ty_lstm_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,

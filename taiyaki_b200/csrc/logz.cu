@@ -38,6 +38,21 @@ struct LogzArgs {
 
 constexpr int kU = 8;                      // prefetch distance (steps)
 constexpr float kFlopInit = -50000.0f;     // layers.py:1289 (LARGE_LOG_VAL)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// The chains run in the log2 domain (scores scaled by log2 e when loaded) so a
+// step is bare ex2 / lg2 SFU operations; the stored lattice vectors are log2.
+__device__ __forceinline__ float ex2f_(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f_(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ float max8(float v) {   // max over aligned groups of 8 lanes
     v = fmaxf(v, __shfl_xor_sync(kFullMask, v, 1));
@@ -65,6 +80,8 @@ __global__ void __launch_bounds__(128) logz_chain_kernel(const LogzArgs a) {
             const int k = k0 + u;
             if (k < nblk) {
                 const int t = dir == 0 ? k : nblk - 1 - k;
+                // raw scores: they are scaled by log2(e) where they are consumed, so the
+                // loaded registers are not touched until then (keeps the prefetch distance)
                 r1[u] = __ldg(w + (size_t)t * ldt + lane);
                 r2[u] = __ldg(w + (size_t)t * ldt + 32 + from);
             } else {
@@ -83,7 +100,7 @@ __global__ void __launch_bounds__(128) logz_chain_kernel(const LogzArgs a) {
             load(n1, n2, k0 + kU);
             float m[kU];
 #pragma unroll
-            for (int u = 0; u < kU; u++) m[u] = warp_max(fmaxf(c1[u], c2[u]));
+            for (int u = 0; u < kU; u++) m[u] = kLog2e * warp_max(fmaxf(c1[u], c2[u]));
 #pragma unroll
             for (int u = 0; u < kU; u++) {
                 const int k = k0 + u;
@@ -91,8 +108,8 @@ __global__ void __launch_bounds__(128) logz_chain_kernel(const LogzArgs a) {
                     if (a.want_grad && lane < 8)
                         a.fwdz[((size_t)k * a.nbatch + b) * 8 + lane] = phi;
                     const float base = phi - m[u];
-                    float e1 = __expf(base + c1[u]);
-                    float e2 = __expf(base + c2[u]);
+                    float e1 = ex2f_(fmaf(kLog2e, c1[u], base));
+                    float e2 = ex2f_(fmaf(kLog2e, c2[u], base));
                     e1 += __shfl_xor_sync(kFullMask, e1, 1);
                     e2 += __shfl_xor_sync(kFullMask, e2, 4);
                     e1 += __shfl_xor_sync(kFullMask, e1, 2);
@@ -100,7 +117,7 @@ __global__ void __launch_bounds__(128) logz_chain_kernel(const LogzArgs a) {
                     // lane needs the new value of state `from`
                     const float g1 = __shfl_sync(kFullMask, e1, (lane & 3) << 3);
                     const float g2 = __shfl_sync(kFullMask, e2, lane & 3);
-                    const float raw = __logf(from < 4 ? g1 : g2);
+                    const float raw = lg2f_(from < 4 ? g1 : g2);
                     phi = raw - c;
                     if (lane == 0) acc += (double)m[u] + (double)c;
                     c = max8(raw) - c;
@@ -110,22 +127,22 @@ __global__ void __launch_bounds__(128) logz_chain_kernel(const LogzArgs a) {
             for (int u = 0; u < kU; u++) { c1[u] = n1[u]; c2[u] = n2[u]; }
         }
         // free end: logZ = offsets + logsumexp over the 8 states
-        float e = __expf(phi - c);
+        float e = ex2f_(phi - c);
         e += __shfl_xor_sync(kFullMask, e, 1);
         e += __shfl_xor_sync(kFullMask, e, 2);
         e += __shfl_xor_sync(kFullMask, e, 4);
         if (lane == 0)
-            a.logz_out[b] = a.logz_scale * (float)(acc + (double)c + (double)__logf(e));
+            a.logz_out[b] = a.logz_scale * kLn2 * (float)(acc + (double)c + (double)lg2f_(e));
     } else {
         // psi: lane holds pa = psi[to] and pb = psi[4 + (from & 3)]
-        const float init = -logf(8.0f);   // cupy_extensions/flipflop.py:166
+        const float init = -3.0f;         // -log2(8): cupy_extensions/flipflop.py:166
         float pa = init, pb = init;
         float c = init;
         for (int k0 = 0; k0 < nblk; k0 += kU) {
             load(n1, n2, k0 + kU);
             float m[kU];
 #pragma unroll
-            for (int u = 0; u < kU; u++) m[u] = warp_max(fmaxf(c1[u], c2[u]));
+            for (int u = 0; u < kU; u++) m[u] = kLog2e * warp_max(fmaxf(c1[u], c2[u]));
 #pragma unroll
             for (int u = 0; u < kU; u++) {
                 const int k = k0 + u;
@@ -138,11 +155,11 @@ __global__ void __launch_bounds__(128) logz_chain_kernel(const LogzArgs a) {
                         if (lane < 4)
                             a.bwdz[((size_t)t * a.nbatch + b) * 8 + 4 + lane] = pb;
                     }
-                    float e1 = __expf(pa + c1[u] - m[u]);
-                    const float e2 = __expf(pb + c2[u] - m[u]);
+                    float e1 = ex2f_(fmaf(kLog2e, c1[u], pa - m[u]));
+                    const float e2 = ex2f_(fmaf(kLog2e, c2[u], pb - m[u]));
                     e1 += __shfl_xor_sync(kFullMask, e1, 8);
                     e1 += __shfl_xor_sync(kFullMask, e1, 16);
-                    const float raw = __logf(e1 + e2);      // new psi[from]
+                    const float raw = lg2f_(e1 + e2);       // new psi[from]
                     const float ga = __shfl_sync(kFullMask, raw, to);
                     const float gb = __shfl_sync(kFullMask, raw, 4 + (lane & 3));
                     pa = ga - c;
@@ -166,11 +183,11 @@ __global__ void __launch_bounds__(256) logz_post_kernel(const LogzArgs a) {
     const float *p = a.bwdz + rowi * 8;
     const int from = lane & 7, to = lane >> 3;
     const float phi = f[from];
-    const float x1 = phi + w[lane] + p[to];
-    const float x2 = lane < 8 ? phi + w[32 + lane] + p[4 + (lane & 3)] : -3.0e38f;
+    const float x1 = fmaf(kLog2e, w[lane], phi + p[to]);
+    const float x2 = lane < 8 ? fmaf(kLog2e, w[32 + lane], phi + p[4 + (lane & 3)]) : -3.0e38f;
     const float M = warp_max(fmaxf(x1, x2));
-    const float e1 = __expf(x1 - M);
-    const float e2 = lane < 8 ? __expf(x2 - M) : 0.f;
+    const float e1 = ex2f_(x1 - M);
+    const float e2 = lane < 8 ? ex2f_(x2 - M) : 0.f;
     const float Z = warp_sum(e1 + e2);
     const float sc = a.grad_scale / Z;
     float *g = a.grad_out + rowi * a.ld_grad;
@@ -194,10 +211,13 @@ extern "C" size_t ty_flipflop_logz_workspace_bytes(int nbase, int nblk, int nbat
     return 2 * align_up((size_t)nblk * nbatch * 8 * sizeof(float), 256);
 }
 
-extern "C" int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatch, int nbase,
-                                float logz_scale, float *logz_out, float grad_scale,
-                                float *grad_out, int ld_grad, int accumulate, void *workspace,
-                                size_t workspace_bytes, void *stream) {
+// phases: bit 0 = lattice chains (logZ and, with grad_out, the stored vectors),
+//         bit 1 = posterior (gradient) from the stored vectors
+extern "C" int ty_flipflop_logz_phase(const float *scores, int ld, int nblk, int nbatch,
+                                      int nbase, float logz_scale, float *logz_out,
+                                      float grad_scale, float *grad_out, int ld_grad,
+                                      int accumulate, void *workspace, size_t workspace_bytes,
+                                      int phases, void *stream) {
     if (!scores || !logz_out || nblk <= 0 || nbatch <= 0) {
         set_error("ty_flipflop_logz: bad argument");
         return TY_EINVAL;
@@ -229,10 +249,22 @@ extern "C" int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatc
     // one chain (warp) per CTA spreads the latency-bound chains over the SMs
     const int warps_per_cta = nchain <= 148 * 4 ? 1 : 4;
     const int grid = (nchain + warps_per_cta - 1) / warps_per_cta;
-    logz_chain_kernel<<<grid, 32 * warps_per_cta, 0, s>>>(a);
-    int rc = check_launch("logz_chain_kernel");
-    if (rc || !want_grad) return rc;
+    int rc = TY_OK;
+    if (phases & 1) {
+        logz_chain_kernel<<<grid, 32 * warps_per_cta, 0, s>>>(a);
+        rc = check_launch("logz_chain_kernel");
+    }
+    if (rc || !want_grad || !(phases & 2)) return rc;
     const size_t nrow = (size_t)nblk * nbatch;
     logz_post_kernel<<<(unsigned)((nrow + 7) / 8), 256, 0, s>>>(a);
     return check_launch("logz_post_kernel");
+}
+
+extern "C" int ty_flipflop_logz(const float *scores, int ld, int nblk, int nbatch, int nbase,
+                                float logz_scale, float *logz_out, float grad_scale,
+                                float *grad_out, int ld_grad, int accumulate, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    return ty_flipflop_logz_phase(scores, ld, nblk, nbatch, nbase, logz_scale, logz_out,
+                                  grad_scale, grad_out, ld_grad, accumulate, workspace,
+                                  workspace_bytes, 3, stream);
 }

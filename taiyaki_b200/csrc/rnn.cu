@@ -136,6 +136,8 @@ struct RnnArgs {
     unsigned zero;         // always 0; opaque to the compiler (see `late`)
     float *dbias;          // bwd: [G*H] += sum over time and chunks of dxproj (may be null)
     const float *bias;     // fwd: [G*H] added to xproj (may be null)
+    __nv_bfloat16 *y16;    // fwd: optional bf16 copy of y (operand of the next GEMMs)
+    __nv_bfloat16 *dxproj16, *dhn16;   // bwd: write the gradients as bf16 instead of fp32
 };
 
 template <int CELL> struct Cell;
@@ -366,6 +368,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 #pragma unroll
             for (uint32_t peer = 0; peer < kCluster; peer++)
                 st_async_b32(mapa(dst, peer), pair, mapa(bar, peer));
+            // the same bf16 pair (units u, u+1 of one chunk) is the GEMM-operand copy of y
+            if (a.y16 && (even ? v0 : v1))
+                *reinterpret_cast<uint32_t *>(
+                    a.y16 + ((size_t)t * N + b0 + (even ? 0 : 1)) * H + (even ? unit : unit - 1)) = pair;
+        } else if (a.y16) {          // last step: no exchange, write the copy directly
+            if (v0) a.y16[((size_t)t * N + b0) * H + unit] = __float2bfloat16(hnew[0]);
+            if (v1) a.y16[((size_t)t * N + b0 + 1) * H + unit] = __float2bfloat16(hnew[1]);
         }
         load_x(xn, s + 1, late_tok);
     };
@@ -542,7 +551,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 dg[2] = dn;                                               // x-side n gradient
                 carry[col] = d * gz;
                 const float dhn = dn * gr;                                // hidden-side n gradient
-                if (valid) __stcs(a.dhn + cell, dhn);
+                if (valid) {
+                    if (a.dhn16) a.dhn16[cell] = __float2bfloat16(dhn);
+                    else __stcs(a.dhn + cell, dhn);
+                }
                 // the recurrent product uses the hidden-side gradient for gate n
                 ds[2 * q + col][0 * U + ul] = __float2bfloat16(dg[0]);
                 ds[2 * q + col][1 * U + ul] = __float2bfloat16(dg[1]);
@@ -551,7 +563,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             if (valid) {
 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    __stcs(a.dxproj + xrow + (size_t)g * H, dg[g]);
+                    if (a.dxproj16) a.dxproj16[xrow + (size_t)g * H] = __float2bfloat16(dg[g]);
+                    else __stcs(a.dxproj + xrow + (size_t)g * H, dg[g]);
                     dbacc[g] += dg[g];
                 }
             }
@@ -658,6 +671,45 @@ using namespace ty;
 extern "C" size_t ty_rnn_reserve_bytes(int cell, int T, int N, int H) {
     (void)cell;
     return (size_t)T * N * 5 * H * sizeof(float);
+}
+
+// bf16 side outputs: see include/taiyaki_b200.h (ty_rnn_forward_ex / ty_rnn_backward_ex)
+extern "C" int ty_rnn_forward_ex(int cell, const float *xproj, const float *bias,
+                                 const float *w_hh, int T, int N, int H, int reverse, float *y,
+                                 void *y_bf16, void *reserve, void *stream) {
+    if (int rc = check_shape(T, N, H, xproj, w_hh, y)) return rc;
+    if (!reserve) { set_error("ty_rnn_forward_ex: reserve is null"); return TY_EINVAL; }
+    RnnArgs a{};
+    a.xproj = xproj; a.bias = bias; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse; a.y = y;
+    a.y16 = static_cast<__nv_bfloat16 *>(y_bf16);
+    a.reserve = static_cast<float *>(reserve);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return cell == kLstm ? launch_rnn<kLstm>(false, a, H, s) : launch_rnn<kGru>(false, a, H, s);
+}
+
+extern "C" int ty_rnn_backward_ex(int cell, const float *dy, const float *w_hh, int T, int N,
+                                  int H, int reverse, const float *y, const void *reserve,
+                                  void *dxproj, void *dhn, int grads_bf16, float *dbias,
+                                  void *stream) {
+    if (int rc = check_shape(T, N, H, dy, w_hh, dxproj)) return rc;
+    if (!reserve || (cell == kGru && (!y || !dhn))) {
+        set_error("ty_rnn_backward_ex: null pointer");
+        return TY_EINVAL;
+    }
+    RnnArgs a{};
+    a.dy = dy; a.w_hh = w_hh; a.T = T; a.N = N; a.reverse = reverse;
+    a.y = const_cast<float *>(y);
+    a.reserve = const_cast<float *>(static_cast<const float *>(reserve));
+    if (grads_bf16) {
+        a.dxproj16 = static_cast<__nv_bfloat16 *>(dxproj);
+        a.dhn16 = static_cast<__nv_bfloat16 *>(dhn);
+    } else {
+        a.dxproj = static_cast<float *>(dxproj);
+        a.dhn = static_cast<float *>(dhn);
+    }
+    a.dbias = dbias;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return cell == kLstm ? launch_rnn<kLstm>(true, a, H, s) : launch_rnn<kGru>(true, a, H, s);
 }
 
 extern "C" int ty_lstm_forward(const float *xproj, const float *bias, const float *w_hh, int T,

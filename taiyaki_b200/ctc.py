@@ -181,3 +181,56 @@ def crf_flipflop_cost_grad(logprob, seqs, seqlen, sharpfact=1.0, want_grad=True)
     move, stay, seqlen32, _, _, max_len = build_indices(seqs, seqlen, nbase, logprob.device)
     return _run_crf(logprob, move, stay, None, None, seqlen32, max_len, sharpfact, ntrans,
                     want_grad)
+
+
+class FlipFlopTrainLoss(torch.autograd.Function):
+    """cost + logZ / nblk of bin/train_flipflop.py:163-182 as one operator
+    (ty_flipflop_train_loss): the label-constrained and the partition-function
+    chains run concurrently and the combined gradient is written once.
+    Numerically the sum of `crf_flipflop_loss` (or `cat_mod_flipflop_loss`) and
+    `layers.flipflop_logpartition(outputs[:, :, :40]) / nblk`."""
+
+    @staticmethod
+    def forward(ctx, logprob, seqs, seqlen, sharpfact, mod_cats, can_mods_offsets,
+                mod_cat_weights):
+        _lib.require_cuda(logprob, 'logprob')
+        lib = _lib.lib()
+        device = logprob.device
+        lp = logprob.detach()
+        if lp.dtype != torch.float32 or not lp.is_contiguous():
+            lp = lp.float().contiguous()
+        nblk, nbatch, ntrans = lp.shape
+        ncan = ntrans if mod_cats is None else ntrans - int(can_mods_offsets[-1])
+        nbase = flipflopfings.nbase_flipflop(ncan)
+        move, stay, seqlen32, modmove, modfact, max_len = build_indices(
+            seqs, seqlen, nbase, device, mod_cats, can_mods_offsets, mod_cat_weights)
+        want_grad = logprob.requires_grad
+        cost = torch.empty(nbatch, dtype=torch.float32, device=device)
+        logz = torch.empty(nbatch, dtype=torch.float32, device=device)
+        grads = torch.empty_like(lp) if want_grad else None
+        ws_bytes = lib.ty_flipflop_train_loss_workspace_bytes(ntrans, nblk, nbatch, max_len,
+                                                              int(want_grad))
+        ws = _lib.workspace(ws_bytes, device)
+        with _lib.timed('loss_fwd_bwd' if want_grad else 'loss_fwd', device):
+            rc = lib.ty_flipflop_train_loss(
+                _lib.ptr(lp), ntrans, nblk, nbatch, _lib.ptr(move), _lib.ptr(stay),
+                _lib.ptr(modmove), _lib.ptr(modfact), _lib.ptr(seqlen32), max_len,
+                float(sharpfact), ncan, _lib.ptr(cost), _lib.ptr(logz), _lib.ptr(grads),
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device))
+        _lib.check(rc, 'ty_flipflop_train_loss')
+        _lib.count_launches(4 if want_grad else 2)
+        if want_grad:
+            ctx.save_for_backward(grads)
+        return cost + logz
+
+    @staticmethod
+    def backward(ctx, output_grads):
+        grads, = ctx.saved_tensors
+        return (grads * output_grads.unsqueeze(1), None, None, None, None, None, None)
+
+
+def flipflop_train_loss(logprob, seqs, seqlen, sharpfact, mod_cats=None, can_mods_offsets=None,
+                        mod_cat_weights=None):
+    """Per-chunk training loss vector [N] = CRF cost + logZ / nblk."""
+    return FlipFlopTrainLoss.apply(logprob, seqs, seqlen, sharpfact, mod_cats, can_mods_offsets,
+                                   mod_cat_weights)

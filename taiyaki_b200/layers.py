@@ -104,58 +104,62 @@ class _Recurrence(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, cell, reverse):
+    def forward(ctx, x, w_ih, w_hh, b_ih, cell, reverse, x16):
         _lib.require_cuda(x, 'x')
         lib = _lib.lib()
         T, N, I = x.shape
         G = 4 if cell == _CELL_LSTM else 3
         H = w_hh.shape[1]
-        x = x.contiguous().float()
+        use16 = PROJECTION_DTYPE == 'bf16'
         w_hh_c = w_hh.detach().contiguous().float()
-        xo = _operand(x.view(T * N, I))
+        if use16 and x16 is not None:
+            xo = x16.view(T * N, I)            # bf16 copy written by the producing layer
+        else:
+            xo = _operand(x.contiguous().float().view(T * N, I))
         wo = _operand(w_ih.detach())
         xproj = _mm(xo, wo.t())
         bias = b_ih.detach().contiguous().float() if b_ih is not None else None
-        y = torch.empty(T, N, H, dtype=torch.float32, device=x.device)
+        dev = x.device
+        y = torch.empty(T, N, H, dtype=torch.float32, device=dev)
+        y16 = torch.empty(T, N, H, dtype=torch.bfloat16, device=dev) if use16 else None
         reserve = torch.empty(lib.ty_rnn_reserve_bytes(cell, T, N, H) // 4,
-                              dtype=torch.float32, device=x.device)
-        fn = lib.ty_lstm_forward if cell == _CELL_LSTM else lib.ty_gru_forward
-        with _lib.timed('rnn_fwd', x.device):
-            rc = fn(_lib.ptr(xproj), _lib.ptr(bias), _lib.ptr(w_hh_c), T, N, H, int(reverse),
-                    _lib.ptr(y), _lib.ptr(reserve), _lib.stream_ptr(x.device))
-        _lib.check(rc, 'ty_rnn_forward')
+                              dtype=torch.float32, device=dev)
+        with _lib.timed('rnn_fwd', dev):
+            rc = lib.ty_rnn_forward_ex(cell, _lib.ptr(xproj), _lib.ptr(bias), _lib.ptr(w_hh_c),
+                                       T, N, H, int(reverse), _lib.ptr(y), _lib.ptr(y16),
+                                       _lib.ptr(reserve), _lib.stream_ptr(dev))
+        _lib.check(rc, 'ty_rnn_forward_ex')
         _lib.count_launches(1)
-        ctx.save_for_backward(xo, wo, w_hh_c, y, reserve)
+        ctx.save_for_backward(xo, wo, w_hh_c, y, reserve, y16)
         ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H, I)
-        return y
+        if y16 is None:
+            y16 = y.new_empty(0)
+        ctx.mark_non_differentiable(y16)
+        return y, y16
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _unused):
         lib = _lib.lib()
-        xo, wo, w_hh_c, y, reserve = ctx.saved_tensors
+        xo, wo, w_hh_c, y, reserve, y16 = ctx.saved_tensors
         cell, reverse, has_bias, G, H, I = ctx.cfg
         T, N, _ = y.shape
         dev = y.device
+        use16 = y16 is not None
+        gdt = torch.bfloat16 if use16 else torch.float32
         dy = dy.contiguous().float()
-        dxproj = torch.empty(T, N, G * H, dtype=torch.float32, device=dev)
-        stream = _lib.stream_ptr(dev)
-        # the bias gradient (sum of dxproj over time and chunks) comes out of the kernel
+        # gradients w.r.t. the projections are only ever GEMM operands: the kernel
+        # writes them in the operand type; the bias gradient is summed in fp32 inside
+        do = torch.empty(T, N, G * H, dtype=gdt, device=dev)
+        dhn = torch.empty(T, N, H, dtype=gdt, device=dev) if cell == _CELL_GRU else None
         db = torch.zeros(G * H, dtype=torch.float32, device=dev) if has_bias else None
         with _lib.timed('rnn_bwd', dev):
-            if cell == _CELL_LSTM:
-                rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
-                                          _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
-                                          _lib.ptr(db), stream)
-                dhn = None
-            else:
-                dhn = torch.empty(T, N, H, dtype=torch.float32, device=dev)
-                rc = lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H, int(reverse),
-                                         _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxproj),
-                                         _lib.ptr(dhn), _lib.ptr(db), stream)
-        _lib.check(rc, 'ty_rnn_backward')
+            rc = lib.ty_rnn_backward_ex(cell, _lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H,
+                                        int(reverse), _lib.ptr(y), _lib.ptr(reserve),
+                                        _lib.ptr(do), _lib.ptr(dhn), int(use16), _lib.ptr(db),
+                                        _lib.stream_ptr(dev))
+        _lib.check(rc, 'ty_rnn_backward_ex')
         _lib.count_launches(1)
-        do = _operand(dxproj)                      # [T, N, G*H]
-        yo = _operand(y)
+        yo = y16 if use16 else y
         d2 = do.view(T * N, G * H)
         # h_{t-1} of every step is y shifted by one step along the loop direction
         if reverse:
@@ -168,12 +172,23 @@ class _Recurrence(torch.autograd.Function):
         if cell == _CELL_LSTM:
             dw_hh = _mm(d_cur.reshape(-1, G * H).t(), hp2)
         else:
-            dhn_o = _operand(dhn)
-            dhn_cur = dhn_o[:-1] if reverse else dhn_o[1:]
+            dhn_cur = dhn[:-1] if reverse else dhn[1:]
             dw_hh = torch.cat([
                 _mm(d_cur[:, :, :2 * H].reshape(-1, 2 * H).t(), hp2),
                 _mm(dhn_cur.reshape(-1, H).t(), hp2)], 0)
-        return dx, dw_ih, dw_hh, db, None, None
+        return dx, dw_ih, dw_hh, db, None, None, None
+
+
+def _run_recurrence(x, w_ih, w_hh, b_ih, cell, reverse):
+    """Apply the recurrence; the bf16 copy of the output rides along on the
+    tensor so the next recurrent layer can use it as its GEMM operand."""
+    x16 = getattr(x, '_ty_bf16', None)
+    if x16 is not None and (x16.shape != x.shape or x16.device != x.device):
+        x16 = None
+    y, y16 = _Recurrence.apply(x, w_ih, w_hh, b_ih, cell, reverse, x16)
+    if y16.numel():
+        y._ty_bf16 = y16
+    return y
 
 
 class Lstm(nn.Module):
@@ -211,8 +226,8 @@ class Lstm(nn.Module):
 
     def forward(self, x, reverse=False):
         m = self.lstm
-        return _Recurrence.apply(x, m.weight_ih_l0, m.weight_hh_l0,
-                                 m.bias_ih_l0 if self.has_bias else None, _CELL_LSTM, reverse)
+        return _run_recurrence(x, m.weight_ih_l0, m.weight_hh_l0,
+                               m.bias_ih_l0 if self.has_bias else None, _CELL_LSTM, reverse)
 
     def json(self):
         res = OrderedDict([('type', "LSTM"), ('activation', "tanh"), ('gate', "sigmoid"),
@@ -260,8 +275,8 @@ class GruMod(nn.Module):
 
     def forward(self, x, reverse=False):
         m = self.cudnn_gru
-        return _Recurrence.apply(x, m.weight_ih_l0, m.weight_hh_l0,
-                                 m.bias_ih_l0 if self.has_bias else None, _CELL_GRU, reverse)
+        return _run_recurrence(x, m.weight_ih_l0, m.weight_hh_l0,
+                               m.bias_ih_l0 if self.has_bias else None, _CELL_GRU, reverse)
 
     def json(self):
         res = OrderedDict([('type', "GruMod"), ('activation', "tanh"), ('gate', "sigmoid"),

@@ -26,6 +26,9 @@ NETWORK_METADATA.__new__.__defaults__ = (None, None, None)
 NETWORK_INFO = namedtuple('NETWORK_INFO', ('net', 'net_clone', 'metadata', 'stride'))
 MOD_INFO = namedtuple('MOD_INFO', ('mod_cat_weights', 'mod_factor'))
 
+#: use ctc.flipflop_train_loss (one fused operator) inside flipflop_loss
+FUSED_LOSS = True
+
 
 def parse_network_metadata(network):
     """train_flipflop.py:67-75"""
@@ -79,7 +82,12 @@ def prepare_random_batches(read_data, batch_chunk_len, sub_batch_size, target_su
 
 def flipflop_loss(outputs, seqs, seqlens, sharpen, mod_cats=None, can_mods_offsets=None,
                   mod_cat_weights=None):
-    """Per-chunk loss vector: CRF cost + logZ / nblk (train_flipflop.py:163-176)."""
+    """Per-chunk loss vector: CRF cost + logZ / nblk (train_flipflop.py:163-176).
+    FUSED_LOSS selects the single fused operator (same numbers, chains overlapped,
+    one gradient write) or the reference's two separate operators."""
+    if FUSED_LOSS:
+        return ctc.flipflop_train_loss(outputs, seqs, seqlens, sharpen, mod_cats,
+                                       can_mods_offsets, mod_cat_weights)
     nblk = float(outputs.shape[0])
     ntrans = outputs.shape[2]
     if mod_cats is not None:

@@ -28,7 +28,8 @@ def test_header_lists_expected_entry_points():
     for name in ['crf_flipflop_grad', 'crf_flipflop_cost', 'cat_mod_flipflop_grad',
                  'cat_mod_flipflop_cost', 'ty_crf_flipflop', 'ty_flipflop_logz',
                  'ty_flipflop_indices', 'ty_lstm_forward', 'ty_lstm_backward',
-                 'ty_gru_forward', 'ty_gru_backward']:
+                 'ty_gru_forward', 'ty_gru_backward', 'ty_rnn_forward_ex',
+                 'ty_rnn_backward_ex']:
         assert name in syms
 
 

@@ -299,3 +299,44 @@ def test_training_loss_matches_reference_composition(dev, oracle):
                                atol=1e-5)
     np.testing.assert_allclose(x.grad.cpu().numpy(), (g_ref + gz_ref / nblk) / nbatch,
                                rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize('ntrans', [40, 45])
+def test_fused_train_loss_equals_separate_operators(dev, oracle, ntrans):
+    """ctc.flipflop_train_loss == crf/cat-mod loss + logZ/nblk (values and gradient),
+    and both match the oracle composition."""
+    from taiyaki_b200 import ctc, layers
+    nblk, nbatch = 150, 7
+    scores = oracle.synth_scores(nblk, nbatch, ntrans, seed=31)
+    seqs, seqlen, raw = oracle.synth_seqs(nblk, nbatch, seed=32)
+    kw = {}
+    if ntrans == 45:
+        mod_cats = np.concatenate([(r == 1).astype(np.int64) * (np.arange(len(r)) % 2)
+                                   for r in raw])
+        off = np.array([0, 1, 3, 4, 5], dtype=np.int32)
+        w = np.array([1.0, 1.0, 0.6, 1.0, 1.0], dtype=np.float32)
+        kw = dict(mod_cats=torch.tensor(mod_cats), can_mods_offsets=off, mod_cat_weights=w)
+    st, sl = torch.tensor(seqs), torch.tensor(seqlen)
+    x1 = torch.tensor(scores, device=dev, requires_grad=True)
+    l1 = ctc.flipflop_train_loss(x1, st, sl, 1.5, **kw)
+    l1.mean().backward()
+    x2 = torch.tensor(scores, device=dev, requires_grad=True)
+    if ntrans == 45:
+        l2 = ctc.cat_mod_flipflop_loss(x2, st, sl, kw['mod_cats'], off, w, 1.5)
+    else:
+        l2 = ctc.crf_flipflop_loss(x2, st, sl, 1.5)
+    l2 = l2 + layers.flipflop_logpartition(x2[:, :, :40]) / nblk
+    l2.mean().backward()
+    np.testing.assert_allclose(l1.detach().cpu().numpy(), l2.detach().cpu().numpy(), rtol=1e-6,
+                               atol=1e-6)
+    np.testing.assert_allclose(x1.grad.cpu().numpy(), x2.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    if ntrans == 45:
+        c_ref, g_ref = oracle.cat_mod_flipflop_loss(scores, seqs, seqlen, mod_cats, off, w, 1.5,
+                                                    impl='f32')
+    else:
+        c_ref, g_ref = oracle.crf_flipflop_loss(scores, seqs, seqlen, 1.5, impl='f32')
+    lz, gz = oracle.c_flipflop_logz(np.ascontiguousarray(scores[:, :, :40]), impl='f32')
+    np.testing.assert_allclose(l1.detach().cpu().numpy(), c_ref + lz / nblk, rtol=RTOL, atol=1e-5)
+    g_ref = g_ref.copy()
+    g_ref[:, :, :40] += gz / nblk
+    np.testing.assert_allclose(x1.grad.cpu().numpy(), g_ref / nbatch, rtol=2e-4, atol=1e-7)
