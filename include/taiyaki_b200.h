@@ -188,6 +188,12 @@ int ty_rnn_backward_ex(int cell, const float *dy, const float *w_hh, int T, int 
                        void *dxproj, void *dhn, int grads_bf16, float *dbias,
                        void *stream);
 
+/* Scatter half of the time-major 1-D convolution backward (layers.py:744-850):
+ * dx[T][N][C] from the column gradient dcols[T_out][N][C*k] (window j of output
+ * step to covers input sample to*stride + j - pad_left). */
+int ty_col2im_time_major(const float *dcols, int Tout, int N, int C, int k,
+                         int stride, int pad_left, int T, float *dx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,8 @@ _SIGNATURES = {
     'ty_flipflop_train_loss': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int, c_float, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ty_col2im_time_major': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p]),
     'ty_rnn_reserve_bytes': (c_size_t, [c_int] * 4),
     'ty_rnn_forward_ex': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -371,10 +371,18 @@ class _ConvTimeMajor(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dcols = _mm(do, wo)                                     # [T_out*N, C*k]
-            dcols = dcols.view(Tout, N, C * k).permute(1, 2, 0)     # [N, C*k, T_out]
-            dxp = torch.nn.functional.fold(dcols, output_size=(1, Tp), kernel_size=(1, k),
-                                           stride=(1, stride))      # [N, C, 1, Tp]
-            dx = dxp[:, :, 0, padding[0]:padding[0] + T].permute(2, 0, 1)
+            if dcols.is_cuda:
+                dx = torch.empty(T, N, C, dtype=torch.float32, device=dcols.device)
+                rc = _lib.lib().ty_col2im_time_major(
+                    _lib.ptr(dcols), Tout, N, C, k, stride, padding[0], T, _lib.ptr(dx),
+                    _lib.stream_ptr(dcols.device))
+                _lib.check(rc, 'ty_col2im_time_major')
+                _lib.count_launches(1)
+            else:
+                dcols = dcols.view(Tout, N, C * k).permute(1, 2, 0)     # [N, C*k, T_out]
+                dxp = torch.nn.functional.fold(dcols, output_size=(1, Tp), kernel_size=(1, k),
+                                               stride=(1, stride))      # [N, C, 1, Tp]
+                dx = dxp[:, :, 0, padding[0]:padding[0] + T].permute(2, 0, 1)
         return dx, dw, db, None, None
 
 

@@ -29,7 +29,7 @@ def test_header_lists_expected_entry_points():
                  'cat_mod_flipflop_cost', 'ty_crf_flipflop', 'ty_flipflop_logz',
                  'ty_flipflop_indices', 'ty_lstm_forward', 'ty_lstm_backward',
                  'ty_gru_forward', 'ty_gru_backward', 'ty_rnn_forward_ex',
-                 'ty_rnn_backward_ex']:
+                 'ty_rnn_backward_ex', 'ty_col2im_time_major', 'ty_flipflop_train_loss']:
         assert name in syms
 
 
