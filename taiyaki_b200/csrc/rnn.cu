@@ -27,6 +27,10 @@
 // gradients) is fp32.
 #include <cuda_bf16.h>
 
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ty {
@@ -91,6 +95,11 @@ __device__ __forceinline__ void st_async_v2(uint32_t raddr, float x, float y, ui
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(addr));
 }
@@ -178,16 +187,29 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 }
 
 // Forward.  H multiple of 64, H <= 256.  Threads: 32 * H/64 (warp w owns 8 units).
+//
+// The input projection of a step is needed in the gate math, on the critical
+// path between two exchanges, and a global load issued one step ahead is not
+// there in time (measured: 675 of 1620 cycles per step were this wait).  Each
+// thread therefore streams ITS OWN 2*G values per step through a private slot
+// of a shared-memory ring with cp.async, kXLook steps ahead: no registers, no
+// scoreboard, no cross-thread synchronisation (a thread only reads what it
+// copied itself, after cp.async.wait_group).
+constexpr int kXRing = 4;    // ring slots (steps)
+constexpr int kXLook = 3;    // steps between issue and use
+
 template <int CELL, int H>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     rnn_forward_kernel(const RnnArgs a) {
     constexpr int G = Cell<CELL>::G;
     constexpr int U = H / kCluster;     // units per CTA
     constexpr int KT = H / 16;          // k tiles
-    constexpr int HS = H + 8;           // padded row (bf16) -> conflict-free ldmatrix
     constexpr int NTHR = H / 2;
 
-    __shared__ __align__(16) __nv_bfloat16 hs[2][kNB][HS];
+    // h_{t-1}, bf16, unit-major: 16 bytes (8 chunks) per unit; a warp's 8 units are 128
+    // contiguous bytes, which is what makes the remote stores of the exchange cheap
+    __shared__ __align__(128) __nv_bfloat16 hs[2][H][kNB];
+    __shared__ __align__(16) float xs[kXRing][2][NTHR][4];   // [slot][column][thread][gate]
     __shared__ __align__(8) uint64_t full[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,7 +245,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
         }
     }
 
-    for (int i = tid; i < 2 * kNB * HS; i += NTHR) (&hs[0][0][0])[i] = __float2bfloat16(0.f);
+    for (int i = tid; i < 2 * kNB * H; i += NTHR) (&hs[0][0][0])[i] = __float2bfloat16(0.f);
+#pragma unroll
+    for (int sl = 0; sl < kXRing; sl++) {
+        *reinterpret_cast<float4 *>(&xs[sl][0][tid][0]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(&xs[sl][1][tid][0]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -241,49 +268,40 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     }
 
     auto tindex = [&](int s) { return a.reverse ? T - 1 - s : s; };
-    auto xaddr = [&](int s) { return a.xproj + ((size_t)tindex(s) * N + b0) * (G * H) + unit; };
-    // `late` is a value produced at the very end of the step; (late & a.zero) is 0
-    // but neither nvcc nor ptxas can know, so the loads cannot be scheduled above
-    // the consumers of the current step's inputs (where they would share a
-    // scoreboard slot with the older loads and stall those consumers).
-    auto load_x = [&](float (&dst)[G][2], int s, uint32_t late) {
+    // start the copies of step s's projection values into ring slot s % kXRing
+    auto issue_x = [&](int s, int slot) {
         if (s < T) {
-            const float *base = xaddr(s) + (late & a.zero);
+            const float *base = a.xproj + ((size_t)tindex(s) * N + b0) * (G * H) + unit;
+            float *d0 = &xs[slot][0][tid][0], *d1 = &xs[slot][1][tid][0];
 #pragma unroll
             for (int g = 0; g < G; g++) {
-                dst[g][0] = v0 ? ld_nc_pinned(base + (size_t)g * H) : 0.f;
-                dst[g][1] = v1 ? ld_nc_pinned(base + (size_t)(G * H) + (size_t)g * H) : 0.f;
+                if (v0) cp_async4(d0 + g, base + (size_t)g * H);
+                if (v1) cp_async4(d1 + g, base + (size_t)(G * H) + (size_t)g * H);
             }
         }
-    };
-    auto prefetch_x = [&](int s) {     // pull a later step's projection rows into L2
-        if (s < T) {
-            const float *base = xaddr(s);
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                if (v0) prefetch_l2(base + (size_t)g * H);
-                if (v1) prefetch_l2(base + (size_t)(G * H) + (size_t)g * H);
-            }
-        }
+        cp_async_commit();     // one group per step, empty past the end: uniform counting
     };
 
     const uint32_t hs_base = smem_u32(&hs[0][0][0]);
     const uint32_t bar_base = smem_u32(&full[0]);
-    // ldmatrix source row for this lane: matrix (lane>>3) -> k offset 8*(lane>>3), row lane&7
-    const uint32_t ld_off = (uint32_t)(((lane & 7) * HS + 8 * (lane >> 3)) * 2);
-    // destination of this thread's packed pair of h values (see the exchange below)
-    const bool even = (r & 1) == 0;
-    const uint32_t send_off =
-        (uint32_t)((((even ? 2 * q : 2 * q + 1) * HS) + (even ? unit : unit - 1)) * 2);
+    // ldmatrix (transposed) source row for this lane: matrix lane>>3 = units 8*(lane>>3)..+7
+    // of a 32-unit group, row lane&7 = one unit (16 bytes: its 8 chunks)
+    const uint32_t ld_off = (uint32_t)(lane * 16);
+    // destination of this thread's h pair (one unit, chunks 2q and 2q+1)
+    const uint32_t send_off = (uint32_t)((unit * kNB + 2 * q) * 2);
 
-    // One time step.  `xp` holds this step's projection (loaded a step ago),
-    // `xn` receives the next step's, issued only after `xp` has been consumed.
-    auto step = [&](const int s, float (&xp)[G][2], float (&xn)[G][2]) {
+    // SLOT = s % kXRing as a compile-time constant (ring slot, buffer parity)
+    auto step = [&](const int s, auto slot_c) {
+        constexpr int SLOT = decltype(slot_c)::value;
         const int t = tindex(s);
-        const int cur = s & 1, nxt = cur ^ 1;
-        prefetch_x(s + 3);
+        constexpr int cur = SLOT & 1, nxt = cur ^ 1;
+        issue_x(s + kXLook, (SLOT + kXLook) % kXRing);
         if (tid == 0 && s + 1 < T)      // arm the barrier that collects h_t (phase of step s+1)
             mbar_arrive_expect_tx(&full[nxt], kCluster * kNB * U * 2);
+        cp_async_wait<kXLook>();        // this step's values have landed (issued kXLook steps ago)
+        const float4 x0 = *reinterpret_cast<const float4 *>(&xs[SLOT][0][tid][0]);
+        const float4 x1 = *reinterpret_cast<const float4 *>(&xs[SLOT][1][tid][0]);
+        const float xp[4][2] = {{x0.x, x1.x}, {x0.y, x1.y}, {x0.z, x1.z}, {x0.w, x1.w}};
         if (s > 0) {
             mbar_wait(&full[cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
@@ -296,20 +314,25 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             for (int c = 0; c < 4; c++)
 #pragma unroll
                 for (int e = 0; e < 4; e++) acc[m][c][e] = 0.f;
-        // element e of tile m: gate 2m + (e >> 1), column e & 1.  (For the GRU the
-        // n-gate bias belongs to the x side: it is added below, not to W_hn h.)
+        // element e of tile m: gate 2m + (e >> 1), column e & 1.  Chain 0 is seeded with
+        // the bias, chain 1 with the projection, so neither costs an addition.  (GRU: the
+        // x side of the n gate must stay outside W_hn h; it is added below.)
         acc[0][0][0] = bias[0]; acc[0][0][1] = bias[0];
         acc[0][0][2] = bias[1]; acc[0][0][3] = bias[1];
+        acc[0][1][0] = xp[0][0]; acc[0][1][1] = xp[0][1];
+        acc[0][1][2] = xp[1][0]; acc[0][1][3] = xp[1][1];
         if (CELL == kLstm) {
             acc[1][0][0] = bias[2]; acc[1][0][1] = bias[2];
             acc[1][0][2] = bias[3]; acc[1][0][3] = bias[3];
+            acc[1][1][0] = xp[2][0]; acc[1][1][1] = xp[2][1];
+            acc[1][1][2] = xp[3][0]; acc[1][1][3] = xp[3][1];
         }
 
-        const uint32_t hcur = hs_base + (uint32_t)(cur * kNB * HS * 2) + ld_off;
+        const uint32_t hcur = hs_base + (uint32_t)(cur * kNB * H * 2) + ld_off;
 #pragma unroll
         for (int kp = 0; kp < KT / 2; kp++) {
             uint32_t bf[4];
-            ldmatrix_x4(bf, hcur + kp * 64);
+            ldmatrix_x4_trans(bf, hcur + kp * 512);
             mma_bf16(acc[0][(2 * kp) & 3], A[0][2 * kp], bf[0], bf[1]);
             mma_bf16(acc[1][(2 * kp) & 3], A[1][2 * kp], bf[0], bf[1]);
             mma_bf16(acc[0][(2 * kp + 1) & 3], A[0][2 * kp + 1], bf[2], bf[3]);
@@ -323,17 +346,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 pre[m][e] = (acc[m][0][e] + acc[m][1][e]) + (acc[m][2][e] + acc[m][3][e]);
 
         float hnew[2];
-        uint32_t late_tok = 0;
 #pragma unroll
         for (int col = 0; col < 2; col++) {
             const bool valid = col == 0 ? v0 : v1;
             const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
             float4 sv;
             if (CELL == kLstm) {
-                const float gi = sigmoidf_(pre[0][col] + xp[0][col]);
-                const float gf = sigmoidf_(pre[0][2 + col] + xp[1][col]);
-                const float gg = tanhf_(pre[1][col] + xp[2][col]);
-                const float go = sigmoidf_(pre[1][2 + col] + xp[3][col]);
+                const float gi = sigmoidf_(pre[0][col]);
+                const float gf = sigmoidf_(pre[0][2 + col]);
+                const float gg = tanhf_(pre[1][col]);
+                const float go = sigmoidf_(pre[1][2 + col]);
                 const float c = gf * cst[col] + gi * gg;
                 cst[col] = c;
                 hnew[col] = go * tanhf_(c);
@@ -341,8 +363,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 if (valid) __stcs(cstate_out + cell, c);
             } else {
                 const float hn = pre[1][col];
-                const float gr = sigmoidf_(pre[0][col] + xp[0][col]);
-                const float gz = sigmoidf_(pre[0][2 + col] + xp[1][col]);
+                const float gr = sigmoidf_(pre[0][col]);
+                const float gz = sigmoidf_(pre[0][2 + col]);
                 const float gn = tanhf_(xp[2][col] + bias[2] + gr * hn);
                 const float h = (1.0f - gz) * gn + gz * cst[col];
                 cst[col] = h;
@@ -353,33 +375,232 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                 __stcs(reinterpret_cast<float4 *>(gates_out) + cell, sv);
                 a.y[cell] = hnew[col];
             }
-            late_tok ^= __float_as_uint(hnew[col]);
         }
         if (s + 1 < T) {
-            // Exchange h_t: lanes r and r^1 swap one value so that each thread
-            // owns two consecutive units of one chunk (a 4-byte bf16 pair), then
-            // stores it straight from registers into all 8 CTAs of the cluster
-            // (its own included); the receivers' mbarriers count the bytes.
-            const float give = even ? hnew[1] : hnew[0];
-            const float got = __shfl_xor_sync(kFullMask, give, 4);
-            const uint32_t pair = even ? pack_bf16(hnew[0], got) : pack_bf16(got, hnew[1]);
-            const uint32_t dst = hs_base + (uint32_t)(nxt * kNB * HS * 2) + send_off;
+            // Exchange h_t: the thread's two cells are one unit of two adjacent chunks,
+            // i.e. one 4-byte bf16 pair of the unit-major tile; it is stored straight from
+            // registers into all 8 CTAs of the cluster (its own included) and the
+            // receivers' mbarriers count the bytes.  A warp's 32 stores to one peer cover
+            // 128 contiguous bytes (tools/dsmem_bench.cu: 460 cycles per exchange round
+            // against 655 for eight 16-byte rows).
+            const uint32_t pair = pack_bf16(hnew[0], hnew[1]);
+            const uint32_t dst = hs_base + (uint32_t)(nxt * kNB * H * 2) + send_off;
             const uint32_t bar = bar_base + (uint32_t)(nxt * 8);
 #pragma unroll
             for (uint32_t peer = 0; peer < kCluster; peer++)
                 st_async_b32(mapa(dst, peer), pair, mapa(bar, peer));
-            // the same bf16 pair (units u, u+1 of one chunk) is the GEMM-operand copy of y
-            if (a.y16 && (even ? v0 : v1))
-                *reinterpret_cast<uint32_t *>(
-                    a.y16 + ((size_t)t * N + b0 + (even ? 0 : 1)) * H + (even ? unit : unit - 1)) = pair;
-        } else if (a.y16) {          // last step: no exchange, write the copy directly
+        }
+        if (a.y16) {     // bf16 copy of y: operand of the next layer's GEMMs
             if (v0) a.y16[((size_t)t * N + b0) * H + unit] = __float2bfloat16(hnew[0]);
             if (v1) a.y16[((size_t)t * N + b0 + 1) * H + unit] = __float2bfloat16(hnew[1]);
         }
+    };
+
+#pragma unroll
+    for (int s0 = 0; s0 < kXLook; s0++) issue_x(s0, s0);
+    static_assert(kXRing == 4 && kXLook < kXRing, "the loop below is unrolled by the ring size");
+    using std::integral_constant;
+    int s = 0;
+    for (; s + 3 < T; s += 4) {
+        step(s, integral_constant<int, 0>{});
+        step(s + 1, integral_constant<int, 1>{});
+        step(s + 2, integral_constant<int, 2>{});
+        step(s + 3, integral_constant<int, 3>{});
+    }
+    if (s < T) step(s, integral_constant<int, 0>{});
+    if (s + 1 < T) step(s + 1, integral_constant<int, 1>{});
+    if (s + 2 < T) step(s + 2, integral_constant<int, 2>{});
+    cp_async_wait<0>();
+    cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------
+// Forward, one-cell-per-thread variant.  Cluster of CL CTAs (8, or 16 with the
+// non-portable cluster size); CTA j owns U = H/CL units; warp w owns ONE m16
+// tile = 4 units x 4 gates, so the CTA has U/4 warps (8 at H=256, CL=8: two per
+// SM sub-partition, each with half the instruction stream of the kernel above).
+// Row g (= lane/4) of the tile is gate 2(g&1) of unit g/2 and row g+8 is gate
+// 2(g&1)+1 of the same unit: a thread's accumulators hold two gates of one unit
+// for two chunks; lanes l and l^4 swap two values so that each owns all four
+// gates of ONE (unit, chunk) cell.  The projection x and the bias seed the two
+// accumulator chains, so no addition follows the HMMAs.  GRU: row "gate 3" has
+// zero weights and is seeded with x_n + b_n -- it carries the x-side of the n
+// gate through the same swap.
+template <int CELL, int H, int CL>
+__global__ void __launch_bounds__(H / CL * 8, 1) rnn_forward_kernel2(const RnnArgs a) {
+    constexpr int G = Cell<CELL>::G;
+    constexpr int U = H / CL;           // units per CTA
+    constexpr int KT = H / 16;          // k tiles
+    constexpr int NTHR = U * 8;
+
+    __shared__ __align__(128) __nv_bfloat16 hs[2][H][kNB];   // unit-major, see rnn_forward_kernel
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, q = lane & 3;
+    const int odd = g8 & 1;                              // which gate pair this thread accumulates
+    const uint32_t rank = cluster_ctarank();
+    const int group = blockIdx.x / CL;
+    const int unit = rank * U + warp * 4 + (g8 >> 1);    // hidden unit of this thread's cell
+    const int T = a.T, N = a.N;
+    const int b0 = group * kNB + 2 * q;                  // chunk of accumulator column 0
+    const int bc = b0 + odd;                             // chunk of this thread's cell
+    const bool v0 = b0 < N, v1 = b0 + 1 < N, vc = bc < N;
+    float *const gates_out = a.reserve;
+    float *const cstate_out = a.reserve + (size_t)T * N * H * 4;
+
+    // gate of accumulator slot 0 / 1 (rows g8, g8+8); -1 = no weights / no x
+    const int gate_lo = 2 * odd, gate_hi = 2 * odd + 1;
+    const bool w_hi = gate_hi < G;
+    // x seeds: LSTM every slot; GRU: r, z in the even lanes; in the odd lanes slot 0
+    // (W_hn h) stays pure and slot 1 (zero weights) carries x_n + b_n
+    const int xg_lo = (CELL == kGru && odd) ? -1 : gate_lo;
+    const int xg_hi = (CELL == kGru && odd) ? 2 : gate_hi;
+
+    uint32_t A[KT][4];
+    {
+        const float *wlo = a.w_hh + ((size_t)gate_lo * H + unit) * H;
+        const float *whi = a.w_hh + ((size_t)(w_hi ? gate_hi : 0) * H + unit) * H;
+#pragma unroll
+        for (int kt = 0; kt < KT; kt++) {
+            const int k = 16 * kt + 2 * q;
+            A[kt][0] = pack_bf16(wlo[k], wlo[k + 1]);
+            A[kt][2] = pack_bf16(wlo[k + 8], wlo[k + 9]);
+            A[kt][1] = w_hi ? pack_bf16(whi[k], whi[k + 1]) : 0u;
+            A[kt][3] = w_hi ? pack_bf16(whi[k + 8], whi[k + 9]) : 0u;
+        }
+    }
+    for (int i = tid; i < 2 * kNB * H; i += NTHR) (&hs[0][0][0])[i] = __float2bfloat16(0.f);
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    cluster_sync_all();
+
+    float cst = 0.f;              // LSTM cell state / GRU previous h (fp32) of this thread's cell
+    uint32_t phase = 0u;
+    float bias_lo = 0.f, bias_hi = 0.f;
+    if (a.bias) {
+        if (xg_lo >= 0) bias_lo = a.bias[(size_t)xg_lo * H + unit];
+        bias_hi = a.bias[(size_t)xg_hi * H + unit];
+    }
+
+    auto tindex = [&](int s) { return a.reverse ? T - 1 - s : s; };
+    auto xaddr = [&](int s) { return a.xproj + ((size_t)tindex(s) * N + b0) * (G * H) + unit; };
+    // x[slot][col]; see rnn_forward_kernel for `late`
+    auto load_x = [&](float (&dst)[2][2], int s, uint32_t late) {
+        if (s < T) {
+            const float *base = xaddr(s) + (late & a.zero);
+            if (xg_lo >= 0) {
+                dst[0][0] = v0 ? ld_nc_pinned(base + (size_t)xg_lo * H) : 0.f;
+                dst[0][1] = v1 ? ld_nc_pinned(base + (size_t)(G * H) + (size_t)xg_lo * H) : 0.f;
+            }
+            dst[1][0] = v0 ? ld_nc_pinned(base + (size_t)xg_hi * H) : 0.f;
+            dst[1][1] = v1 ? ld_nc_pinned(base + (size_t)(G * H) + (size_t)xg_hi * H) : 0.f;
+        }
+    };
+    auto prefetch_x = [&](int s) {
+        if (s < T) {
+            const float *base = xaddr(s);
+            if (xg_lo >= 0) {
+                if (v0) prefetch_l2(base + (size_t)xg_lo * H);
+                if (v1) prefetch_l2(base + (size_t)(G * H) + (size_t)xg_lo * H);
+            }
+            if (v0) prefetch_l2(base + (size_t)xg_hi * H);
+            if (v1) prefetch_l2(base + (size_t)(G * H) + (size_t)xg_hi * H);
+        }
+    };
+
+    const uint32_t hs_base = smem_u32(&hs[0][0][0]);
+    const uint32_t bar_base = smem_u32(&full[0]);
+    const uint32_t ld_off = (uint32_t)(lane * 16);
+    // h exchange: lanes l, l^4 hold chunks 2q, 2q+1 of one unit -> one bf16 pair of the
+    // unit-major tile; the even lane serves the lower half of the peers, the odd one the
+    // upper half.  A warp's stores to one peer cover its private 64 contiguous bytes.
+    const uint32_t send_off = (uint32_t)((unit * kNB + 2 * q) * 2);
+    const uint32_t peer0 = odd ? (uint32_t)(CL / 2) : 0u;
+
+    auto step = [&](const int s, float (&xp)[2][2], float (&xn)[2][2]) {
+        const int t = tindex(s);
+        const int cur = s & 1, nxt = cur ^ 1;
+        prefetch_x(s + 3);
+        if (tid == 0 && s + 1 < T) mbar_arrive_expect_tx(&full[nxt], CL * kNB * U * 2);
+        if (s > 0) {
+            mbar_wait(&full[cur], (phase >> cur) & 1u);
+            phase ^= 1u << cur;
+        }
+        // c-fragment element e: slot e >> 1 (row g8 / g8+8), column e & 1
+        float acc[2][4];
+        acc[0][0] = (CELL == kGru && odd) ? 0.f : xp[0][0];
+        acc[0][1] = (CELL == kGru && odd) ? 0.f : xp[0][1];
+        acc[0][2] = xp[1][0]; acc[0][3] = xp[1][1];
+        acc[1][0] = bias_lo; acc[1][1] = bias_lo;
+        acc[1][2] = bias_hi; acc[1][3] = bias_hi;
+
+        const uint32_t hcur = hs_base + (uint32_t)(cur * kNB * H * 2) + ld_off;
+#pragma unroll
+        for (int kp = 0; kp < KT / 2; kp++) {
+            uint32_t bf[4];
+            ldmatrix_x4_trans(bf, hcur + kp * 512);
+            mma_bf16(acc[0], A[2 * kp], bf[0], bf[1]);
+            mma_bf16(acc[1], A[2 * kp + 1], bf[2], bf[3]);
+        }
+        float pre[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) pre[e] = acc[0][e] + acc[1][e];
+        // swap: even lanes keep column 0 and give column 1, odd lanes the reverse
+        const float give0 = odd ? pre[0] : pre[1];
+        const float give1 = odd ? pre[2] : pre[3];
+        const float got0 = __shfl_xor_sync(kFullMask, give0, 4);
+        const float got1 = __shfl_xor_sync(kFullMask, give1, 4);
+        // v[0..3] = pre-activations of gates 0..3 of this thread's cell
+        const float p0 = odd ? got0 : pre[0];
+        const float p1 = odd ? got1 : pre[2];
+        const float p2 = odd ? pre[1] : got0;
+        const float p3 = odd ? pre[3] : got1;
+
+        const size_t cell = ((size_t)t * N + bc) * H + unit;
+        float hnew;
+        float4 sv;
+        if (CELL == kLstm) {
+            const float gi = sigmoidf_(p0);
+            const float gf = sigmoidf_(p1);
+            const float gg = tanhf_(p2);
+            const float go = sigmoidf_(p3);
+            const float c = gf * cst + gi * gg;
+            cst = c;
+            hnew = go * tanhf_(c);
+            sv = make_float4(gi, gf, gg, go);
+            if (vc) __stcs(cstate_out + cell, c);
+        } else {
+            const float gr = sigmoidf_(p0);
+            const float gz = sigmoidf_(p1);
+            const float gn = tanhf_(p3 + gr * p2);
+            const float h = (1.0f - gz) * gn + gz * cst;
+            cst = h;
+            hnew = h;
+            sv = make_float4(gr, gz, gn, p2);
+        }
+        if (vc) {
+            __stcs(reinterpret_cast<float4 *>(gates_out) + cell, sv);
+            a.y[cell] = hnew;
+        }
+        const uint32_t late_tok = __float_as_uint(hnew);
+        if (s + 1 < T) {
+            const float other = __shfl_xor_sync(kFullMask, hnew, 4);
+            const uint32_t pair = odd ? pack_bf16(other, hnew) : pack_bf16(hnew, other);
+            const uint32_t dst = hs_base + (uint32_t)(nxt * kNB * H * 2) + send_off;
+            const uint32_t bar = bar_base + (uint32_t)(nxt * 8);
+#pragma unroll
+            for (uint32_t p = 0; p < CL / 2; p++)
+                st_async_b32(mapa(dst, peer0 + p), pair, mapa(bar, peer0 + p));
+        }
+        if (a.y16 && vc) a.y16[cell] = __float2bfloat16(hnew);
         load_x(xn, s + 1, late_tok);
     };
 
-    float xa[G][2], xb[G][2];
+    float xa[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, xb[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     load_x(xa, 0, 0u);
     prefetch_x(1);
     prefetch_x(2);
@@ -637,10 +858,80 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 }
 
 // ---------------------------------------------------------------------------
+// Forward variant: 0 = two cells per thread (rnn_forward_kernel), 1 = one cell per
+// thread, cluster of 8, 2 = one cell per thread, cluster of 16 where it fits.
+static int fwd_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TY_RNN_FWD");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <typename K>
+static cudaError_t launch_cluster(K kernel, int grid, int block, int cl, cudaStream_t s,
+                                  const RnnArgs &a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+// Can `groups` clusters of 16 CTAs be co-resident?  (One per GPC at most.)
+template <typename K>
+static bool cluster16_fits(K kernel, int block, int groups) {
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        max_clusters = 0;
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
+            cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(16 * 64);
+            cfg.blockDim = dim3(block);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 16;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess) max_clusters = n;
+        }
+        cudaGetLastError();
+        if (getenv("TY_RNN_DEBUG")) fprintf(stderr, "ty_rnn: max active clusters of 16: %d\n", max_clusters);
+    }
+    return groups <= max_clusters;
+}
+
 template <int CELL>
 static int launch_rnn(bool backward, const RnnArgs &a, int H, cudaStream_t s) {
     const int groups = (a.N + kNB - 1) / kNB;
     const dim3 grid(groups * kCluster);
+    const int variant = backward ? 0 : fwd_variant();
+    if (variant >= 1 && H == 256) {
+        cudaError_t e;
+        if (variant == 2 && cluster16_fits(rnn_forward_kernel2<CELL, 256, 16>, 128, groups)) {
+            e = launch_cluster(rnn_forward_kernel2<CELL, 256, 16>, groups * 16, 128, 16, s, a);
+        } else {
+            e = launch_cluster(rnn_forward_kernel2<CELL, 256, 8>, groups * 8, 256, 8, s, a);
+        }
+        if (e != cudaSuccess) {
+            set_error("rnn_forward_kernel2 launch: %s", cudaGetErrorString(e));
+            return TY_ECUDA;
+        }
+        return TY_OK;
+    }
 #define TY_RNN(HH)                                                                  \
     case HH:                                                                        \
         if (backward) rnn_backward_kernel<CELL, HH><<<grid, HH / 2, 0, s>>>(a);     \

@@ -102,8 +102,11 @@ def bench_crf(nblk, nbatch, ntrans, stride, tag):
     emit(what='logz_only', tag=tag, nblk=nblk, N=nbatch, ms_median=med, ms_min=mn)
 
 
-def bench_rnn(cell, T, N, H, tag):
+def bench_rnn(cell, T, N, H, tag, kernels_only=False):
     torch.manual_seed(0)
+    if kernels_only:
+        dy = torch.randn(T, N, H, device=dev)
+        return bench_rnn_kernels(cell, T, N, H, tag, dy)
     mod = (layers.Lstm(H, H) if cell == 'lstm' else layers.GruMod(H, H)).to(dev)
     nnmod = (torch.nn.LSTM(H, H) if cell == 'lstm' else torch.nn.GRU(H, H)).to(dev)
     x = torch.randn(T, N, H, device=dev, requires_grad=True)
@@ -133,6 +136,10 @@ def bench_rnn(cell, T, N, H, tag):
                  ms_min=mn, us_per_step=1e3 * med / T)
         except Exception as e:
             emit(what='rnn_layer', cell=cell, impl=name, tag=tag, error=str(e)[:300])
+    bench_rnn_kernels(cell, T, N, H, tag, dy)
+
+
+def bench_rnn_kernels(cell, T, N, H, tag, dy):
     # recurrence kernel alone (no projections)
     lib = _lib.lib()
     G = 4 if cell == 'lstm' else 3
@@ -153,7 +160,8 @@ def bench_rnn(cell, T, N, H, tag):
     for name, fn in [('kernel_fwd', f), ('kernel_bwd', b)]:
         med, mn = timeit(fn, iters=5, warmup=2)
         emit(what='rnn_kernel', cell=cell, impl=name, tag=tag, T=T, N=N, H=H, ms_median=med,
-             ms_min=mn, us_per_step=1e3 * med / T)
+             ms_min=mn, us_per_step=1e3 * med / T, variant=os.environ.get('TY_RNN_FWD', ''),
+             y_checksum=float(y.double().abs().sum()))
 
 
 if __name__ == '__main__':
@@ -165,6 +173,9 @@ if __name__ == '__main__':
     if 'rnn' in which:
         bench_rnn('lstm', 800, 64, 256, 'A')
         bench_rnn('gru', 2000, 64, 256, 'B')
+    if 'rnnk' in which:
+        bench_rnn('lstm', 800, 64, 256, 'A', kernels_only=True)
+        bench_rnn('gru', 2000, 64, 256, 'B', kernels_only=True)
     if 'sweep' in which:
         for nblk in (1000, 2000, 4000, 8000):
             bench_crf(nblk, 64, 40, 5, 'E%d' % nblk)
