@@ -630,6 +630,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
 
     __shared__ __align__(16) __nv_bfloat16 ds[kNB][DS];
     __shared__ __align__(16) float rs[2][kCluster][U][kNB];
+    __shared__ __align__(16) float4 gs[kXRing][2][NTHR];     // saved gates [slot][column][thread]
+    __shared__ __align__(16) float vs[kXRing][2][2][NTHR];   // dy | c_t (LSTM) or h_{t-1} (GRU)
     __shared__ __align__(8) uint64_t full[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -665,6 +667,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
         }
     }
     for (int i = tid; i < kNB * DS; i += NTHR) (&ds[0][0])[i] = __float2bfloat16(0.f);
+#pragma unroll
+    for (int sl = 0; sl < kXRing; sl++) {
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            gs[sl][col][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vs[sl][0][col][tid] = 0.f;
+            vs[sl][1][col][tid] = 0.f;
+        }
+    }
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -679,41 +690,29 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     for (int g = 0; g < G; g++) dbacc[g] = 0.f;
     auto tindex = [&](int sf) { return a.reverse ? T - 1 - sf : sf; };   // forward step -> time
 
-    // per-step inputs: saved gates, c_t, incoming gradient, c_{t-1} / h_{t-1}
-    struct In { float4 gt[2]; float c[2]; float dy[2]; float prev[2]; };
-    auto load_in = [&](In &d, int s, uint32_t late) {
-        if (s >= T) return;
-        const int sf = T - 1 - s;                 // forward step being differentiated
-        const int t = tindex(sf);
-        const size_t lz = late & a.zero;          // 0, opaque: see rnn_forward_kernel
+    // Per-step inputs (saved gates, c_t or h_{t-1}, incoming gradient) stream through
+    // thread-private slots of a shared-memory ring with cp.async, kXLook steps ahead
+    // (see rnn_forward_kernel).  LSTM: c_{t-1} is simply the next slot's c.
+    auto issue_in = [&](int s, int slot) {
+        if (s < T) {
+            const int sf = T - 1 - s;                 // forward step being differentiated
+            const int t = tindex(sf);
 #pragma unroll
-        for (int col = 0; col < 2; col++) {
-            const bool valid = col == 0 ? v0 : v1;
-            const size_t cell = ((size_t)t * N + b0 + col) * H + unit + lz;
-            d.gt[col] = valid ? ld_nc_pinned4(gates_in + cell) : make_float4(0.f, 0.f, 0.f, 0.f);
-            d.c[col] = (valid && CELL == kLstm) ? ld_nc_pinned(cstate_in + cell) : 0.f;
-            d.dy[col] = valid ? ld_nc_pinned(a.dy + cell) : 0.f;
-            float pv = 0.f;
-            if (valid && sf > 0) {
-                const size_t pcell = ((size_t)tindex(sf - 1) * N + b0 + col) * H + unit + lz;
-                pv = CELL == kLstm ? ld_nc_pinned(cstate_in + pcell)      // c_{t-1}
-                                   : ld_nc_pinned(a.y + pcell);           // h_{t-1}
-            }
-            d.prev[col] = pv;
-        }
-    };
-    auto prefetch_in = [&](int s) {
-        if (s >= T) return;
-        const int t = tindex(T - 1 - s);
-#pragma unroll
-        for (int col = 0; col < 2; col++) {
-            if (col == 0 ? v0 : v1) {
-                const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
-                prefetch_l2(gates_in + cell);
-                prefetch_l2(a.dy + cell);
-                if (CELL == kLstm) prefetch_l2(cstate_in + cell);
+            for (int col = 0; col < 2; col++) {
+                if (col == 0 ? v0 : v1) {
+                    const size_t cell = ((size_t)t * N + b0 + col) * H + unit;
+                    cp_async16(&gs[slot][col][tid], gates_in + cell);
+                    cp_async4(&vs[slot][0][col][tid], a.dy + cell);
+                    if (CELL == kLstm) {
+                        cp_async4(&vs[slot][1][col][tid], cstate_in + cell);
+                    } else if (sf > 0) {
+                        const size_t pcell = ((size_t)tindex(sf - 1) * N + b0 + col) * H + unit;
+                        cp_async4(&vs[slot][1][col][tid], a.y + pcell);     // h_{t-1}
+                    }
+                }
             }
         }
+        cp_async_commit();
     };
 
     const uint32_t ds_base = smem_u32(&ds[0][0]);
@@ -721,15 +720,30 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
     const uint32_t rs_base = smem_u32(&rs[0][0][0][0]);
     const uint32_t bar_base = smem_u32(&full[0]);
 
-    auto step = [&](const int s, In &in, In &nxt_in) {
+    auto step = [&](const int s, auto slot_c) {
+        constexpr int SLOT = decltype(slot_c)::value;
+        constexpr int cur = SLOT & 1, nxt = cur ^ 1;
         const int sf = T - 1 - s;
         const int t = tindex(sf);
-        const int cur = s & 1, nxt = cur ^ 1;
-        prefetch_in(s + 3);
+        issue_in(s + kXLook, (SLOT + kXLook) % kXRing);
         if (tid == 0 && s + 1 < T) mbar_arrive_expect_tx(&full[nxt], kCluster * U * kNB * 4);
+        // this step's group and the next one's (for c_{t-1}) have landed
+        cp_async_wait<kXLook - 1>();
+        struct { float4 gt[2]; float c[2]; float dy[2]; float prev[2]; } in;
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            in.gt[col] = gs[SLOT][col][tid];
+            in.dy[col] = vs[SLOT][0][col][tid];
+            if (CELL == kLstm) {
+                in.c[col] = vs[SLOT][1][col][tid];
+                in.prev[col] = sf > 0 ? vs[(SLOT + 1) % kXRing][1][col][tid] : 0.f;   // c_{t-1}
+            } else {
+                in.c[col] = 0.f;
+                in.prev[col] = sf > 0 ? vs[SLOT][1][col][tid] : 0.f;                  // h_{t-1}
+            }
+        }
 
         float dh[2] = {in.dy[0], in.dy[1]};
-        uint32_t late_tok = 0;
         if (s > 0) {
             mbar_wait(&full[cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
@@ -789,7 +803,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
                     dbacc[g] += dg[g];
                 }
             }
-            late_tok ^= __float_as_uint(dg[0]) ^ __float_as_uint(carry[col]);
         }
         if (s + 1 < T) {
             __syncthreads();
@@ -837,19 +850,21 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2, 1)
             // `full` implies it (the barrier needs this CTA's own partials too),
             // except for the pad rows, which are never rewritten.
         }
-        load_in(nxt_in, s + 1, late_tok);   // after this step's inputs were consumed (see forward)
     };
 
-    In ia, ib;
-    load_in(ia, 0, 0u);
-    prefetch_in(1);
-    prefetch_in(2);
+    for (int s0 = 0; s0 < kXLook; s0++) issue_in(s0, s0);
+    using std::integral_constant;
     int s = 0;
-    for (; s + 1 < T; s += 2) {
-        step(s, ia, ib);
-        step(s + 1, ib, ia);
+    for (; s + 3 < T; s += 4) {
+        step(s, integral_constant<int, 0>{});
+        step(s + 1, integral_constant<int, 1>{});
+        step(s + 2, integral_constant<int, 2>{});
+        step(s + 3, integral_constant<int, 3>{});
     }
-    if (s < T) step(s, ia, ib);
+    if (s < T) step(s, integral_constant<int, 0>{});
+    if (s + 1 < T) step(s + 1, integral_constant<int, 1>{});
+    if (s + 2 < T) step(s + 2, integral_constant<int, 2>{});
+    cp_async_wait<0>();
     if (a.dbias) {
 #pragma unroll
         for (int g = 0; g < G; g++) atomicAdd(a.dbias + (size_t)g * H + unit, dbacc[g]);
