@@ -188,6 +188,27 @@ int ty_rnn_backward_ex(int cell, const float *dy, const float *w_hh, int T, int 
                        void *dxproj, void *dhn, int grads_bf16, float *dbias,
                        void *stream);
 
+/* UNIT-MAJOR forms (taiyaki_b200/csrc/rnn_ws.cu: warp-specialised kernels with
+ * a dedicated I/O warp).  Same semantics as the _ex forms, different layout of
+ * the projection tensors: the G gates of a (chunk, unit) cell are adjacent,
+ *     xproj       [T][N][H][G] fp32    = x (P W_ih)^T,  P = gate-major -> unit-major
+ *                                        row permutation of W_ih (row u*G+g <- g*H+u)
+ *     dxproj_bf16 [T][N][H][G] bf16    gradient of xproj
+ *     dhid_bf16   [T][N][H][3] bf16    GRU only: (dr, dz, d(W_hn h)), the gradient
+ *                                        of the hidden-side product h W_hh^T
+ * so a CTA's share of a chunk is one contiguous run.  bias, w_hh and dbias stay
+ * gate-major ([G*H]), i.e. they are the parameters themselves; `reserve` has
+ * ty_rnn_reserve_bytes() bytes and is private to the forward / backward pair.
+ * The weight gradients the caller forms from dxproj / dhid come out with the
+ * same row permutation P. */
+int ty_rnn_forward_um(int cell, const float *xproj, const float *bias,
+                      const float *w_hh, int T, int N, int H, int reverse,
+                      float *y, void *y_bf16, void *reserve, void *stream);
+int ty_rnn_backward_um(int cell, const float *dy, const float *w_hh, int T, int N,
+                       int H, int reverse, const float *y, const void *reserve,
+                       void *dxproj_bf16, void *dhid_bf16, float *dbias,
+                       void *stream);
+
 /* Scatter half of the time-major 1-D convolution backward (layers.py:744-850):
  * dx[T][N][C] from the column gradient dcols[T_out][N][C*k] (window j of output
  * step to covers input sample to*stride + j - pad_left). */

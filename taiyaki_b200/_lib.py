@@ -49,6 +49,10 @@ _SIGNATURES = {
     'ty_rnn_backward_ex': (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                    c_void_p]),
+    'ty_rnn_forward_um': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ty_rnn_backward_um': (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ty_lstm_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
     'ty_lstm_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,

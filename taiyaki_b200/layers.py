@@ -94,13 +94,33 @@ def _operand(t):
 
 # ---------------------------------------------------------------------------
 # recurrence
-class _Recurrence(torch.autograd.Function):
-    """y = RNN(x) with the sequential part in csrc/rnn.cu.
+def _unit_major(w, G):
+    """Row permutation gate-major [G*H, K] -> unit-major [H*G, K] (row u*G+g <- g*H+u)."""
+    GH, K = w.shape
+    return w.view(G, GH // G, K).transpose(0, 1).reshape(GH, K)
 
-    forward:  xproj = x W_ih^T (one GEMM) -> ty_{lstm,gru}_forward (adds b_ih)
-    backward: ty_{lstm,gru}_backward gives d xproj, the bias gradient (and the
-              hidden-side n-gate gradient for the GRU); weight / input
-              gradients are dense GEMMs over all time steps.
+
+def _gate_major(w, G):
+    """Inverse of `_unit_major`."""
+    GH, K = w.shape
+    return w.view(GH // G, G, K).transpose(0, 1).reshape(GH, K)
+
+
+#: 'ws' = warp-specialised kernels behind the unit-major ABI (csrc/rnn_ws.cu, bf16
+#: projections only); 'legacy' = one-role kernels behind the gate-major ABI (csrc/rnn.cu)
+RNN_IMPL = 'ws'
+
+
+class _Recurrence(torch.autograd.Function):
+    """y = RNN(x) with the sequential part in csrc/rnn_ws.cu (or csrc/rnn.cu).
+
+    forward:  xproj = x W_ih^T (one GEMM) -> ty_rnn_forward_* (adds b_ih)
+    backward: ty_rnn_backward_* gives d xproj, the bias gradient (and the
+              hidden-side gradient for the GRU); weight / input gradients are
+              dense GEMMs over all time steps.
+    With the unit-major kernels W_ih is row-permuted while it is converted to
+    the GEMM operand type, so the projection comes out as [T, N, H, G]; the
+    weight gradients are permuted back.
     """
 
     @staticmethod
@@ -111,12 +131,17 @@ class _Recurrence(torch.autograd.Function):
         G = 4 if cell == _CELL_LSTM else 3
         H = w_hh.shape[1]
         use16 = PROJECTION_DTYPE == 'bf16'
+        um = use16 and RNN_IMPL == 'ws'
         w_hh_c = w_hh.detach().contiguous().float()
         if use16 and x16 is not None:
             xo = x16.view(T * N, I)            # bf16 copy written by the producing layer
         else:
             xo = _operand(x.contiguous().float().view(T * N, I))
-        wo = _operand(w_ih.detach())
+        if um:     # permute the rows while converting: one small copy kernel
+            wo = torch.empty(G * H, I, dtype=torch.bfloat16, device=x.device)
+            wo.view(H, G, I).copy_(w_ih.detach().view(G, H, I).transpose(0, 1))
+        else:
+            wo = _operand(w_ih.detach())
         xproj = _mm(xo, wo.t())
         bias = b_ih.detach().contiguous().float() if b_ih is not None else None
         dev = x.device
@@ -124,14 +149,15 @@ class _Recurrence(torch.autograd.Function):
         y16 = torch.empty(T, N, H, dtype=torch.bfloat16, device=dev) if use16 else None
         reserve = torch.empty(lib.ty_rnn_reserve_bytes(cell, T, N, H) // 4,
                               dtype=torch.float32, device=dev)
+        fwd = lib.ty_rnn_forward_um if um else lib.ty_rnn_forward_ex
         with _lib.timed('rnn_fwd', dev):
-            rc = lib.ty_rnn_forward_ex(cell, _lib.ptr(xproj), _lib.ptr(bias), _lib.ptr(w_hh_c),
-                                       T, N, H, int(reverse), _lib.ptr(y), _lib.ptr(y16),
-                                       _lib.ptr(reserve), _lib.stream_ptr(dev))
-        _lib.check(rc, 'ty_rnn_forward_ex')
+            rc = fwd(cell, _lib.ptr(xproj), _lib.ptr(bias), _lib.ptr(w_hh_c),
+                     T, N, H, int(reverse), _lib.ptr(y), _lib.ptr(y16),
+                     _lib.ptr(reserve), _lib.stream_ptr(dev))
+        _lib.check(rc, 'ty_rnn_forward')
         _lib.count_launches(1)
         ctx.save_for_backward(xo, wo, w_hh_c, y, reserve, y16)
-        ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H, I)
+        ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H, I, um)
         if y16 is None:
             y16 = y.new_empty(0)
         ctx.mark_non_differentiable(y16)
@@ -141,7 +167,7 @@ class _Recurrence(torch.autograd.Function):
     def backward(ctx, dy, _unused):
         lib = _lib.lib()
         xo, wo, w_hh_c, y, reserve, y16 = ctx.saved_tensors
-        cell, reverse, has_bias, G, H, I = ctx.cfg
+        cell, reverse, has_bias, G, H, I, um = ctx.cfg
         T, N, _ = y.shape
         dev = y.device
         use16 = y16 is not None
@@ -150,8 +176,28 @@ class _Recurrence(torch.autograd.Function):
         # gradients w.r.t. the projections are only ever GEMM operands: the kernel
         # writes them in the operand type; the bias gradient is summed in fp32 inside
         do = torch.empty(T, N, G * H, dtype=gdt, device=dev)
-        dhn = torch.empty(T, N, H, dtype=gdt, device=dev) if cell == _CELL_GRU else None
         db = torch.zeros(G * H, dtype=torch.float32, device=dev) if has_bias else None
+        yo = y16 if use16 else y
+        # h_{t-1} of every step is y shifted by one step along the loop direction
+        sl_cur, sl_prev = (slice(None, -1), slice(1, None)) if reverse else \
+            (slice(1, None), slice(None, -1))
+        hp2 = yo[sl_prev].reshape(-1, H)
+        if um:
+            dhid = torch.empty(T, N, G * H, dtype=gdt, device=dev) if cell == _CELL_GRU else None
+            with _lib.timed('rnn_bwd', dev):
+                rc = lib.ty_rnn_backward_um(cell, _lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H,
+                                            int(reverse), _lib.ptr(y), _lib.ptr(reserve),
+                                            _lib.ptr(do), _lib.ptr(dhid), _lib.ptr(db),
+                                            _lib.stream_ptr(dev))
+            _lib.check(rc, 'ty_rnn_backward_um')
+            _lib.count_launches(1)
+            d2 = do.view(T * N, G * H)
+            dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
+            dw_ih = _gate_major(_mm(d2.t(), xo), G)
+            dh_side = do if cell == _CELL_LSTM else dhid
+            dw_hh = _gate_major(_mm(dh_side[sl_cur].reshape(-1, G * H).t(), hp2), G)
+            return dx, dw_ih, dw_hh, db, None, None, None
+        dhn = torch.empty(T, N, H, dtype=gdt, device=dev) if cell == _CELL_GRU else None
         with _lib.timed('rnn_bwd', dev):
             rc = lib.ty_rnn_backward_ex(cell, _lib.ptr(dy), _lib.ptr(w_hh_c), T, N, H,
                                         int(reverse), _lib.ptr(y), _lib.ptr(reserve),
@@ -159,23 +205,16 @@ class _Recurrence(torch.autograd.Function):
                                         _lib.stream_ptr(dev))
         _lib.check(rc, 'ty_rnn_backward_ex')
         _lib.count_launches(1)
-        yo = y16 if use16 else y
         d2 = do.view(T * N, G * H)
-        # h_{t-1} of every step is y shifted by one step along the loop direction
-        if reverse:
-            d_cur, h_prev = do[:-1], yo[1:]
-        else:
-            d_cur, h_prev = do[1:], yo[:-1]
-        hp2 = h_prev.reshape(-1, H)
+        d_cur = do[sl_cur]
         dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
         dw_ih = _mm(d2.t(), xo)
         if cell == _CELL_LSTM:
             dw_hh = _mm(d_cur.reshape(-1, G * H).t(), hp2)
         else:
-            dhn_cur = dhn[:-1] if reverse else dhn[1:]
             dw_hh = torch.cat([
                 _mm(d_cur[:, :, :2 * H].reshape(-1, 2 * H).t(), hp2),
-                _mm(dhn_cur.reshape(-1, H).t(), hp2)], 0)
+                _mm(dhn[sl_cur].reshape(-1, H).t(), hp2)], 0)
         return dx, dw_ih, dw_hh, db, None, None, None
 
 

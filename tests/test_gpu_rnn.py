@@ -55,7 +55,22 @@ def ref_recurrence(cell, xproj, w_hh, reverse, emulate=True):
     return torch.stack(ys, 0)
 
 
-def kernel_forward(cell, xproj, w_hh, reverse):
+def to_unit_major(t, G):
+    """[..., G*H] gate-major -> [..., H*G] unit-major (the layout of ty_rnn_*_um)."""
+    lead = t.shape[:-1]
+    return t.reshape(*lead, G, -1).transpose(-1, -2).reshape(*lead, -1).contiguous()
+
+
+def to_gate_major(t, G):
+    lead = t.shape[:-1]
+    return t.reshape(*lead, -1, G).transpose(-1, -2).reshape(*lead, -1).contiguous()
+
+
+IMPLS = ['legacy', 'um']
+
+
+def kernel_forward(cell, xproj, w_hh, reverse, impl='legacy'):
+    """xproj is gate-major [T,N,G*H]; `um` permutes it to the unit-major ABI."""
     from taiyaki_b200 import _lib
     lib = _lib.lib()
     T, N, GH = xproj.shape
@@ -63,18 +78,37 @@ def kernel_forward(cell, xproj, w_hh, reverse):
     code = 0 if cell == 'lstm' else 1
     y = torch.empty(T, N, H, device=xproj.device)
     reserve = torch.empty(lib.ty_rnn_reserve_bytes(code, T, N, H) // 4, device=xproj.device)
-    fn = lib.ty_lstm_forward if cell == 'lstm' else lib.ty_gru_forward
-    rc = fn(_lib.ptr(xproj), None, _lib.ptr(w_hh), T, N, H, int(reverse), _lib.ptr(y),
-            _lib.ptr(reserve), _lib.stream_ptr(xproj.device))
+    if impl == 'um':
+        xu = to_unit_major(xproj, GH // H)
+        rc = lib.ty_rnn_forward_um(code, _lib.ptr(xu), None, _lib.ptr(w_hh), T, N, H,
+                                   int(reverse), _lib.ptr(y), None, _lib.ptr(reserve),
+                                   _lib.stream_ptr(xproj.device))
+    else:
+        fn = lib.ty_lstm_forward if cell == 'lstm' else lib.ty_gru_forward
+        rc = fn(_lib.ptr(xproj), None, _lib.ptr(w_hh), T, N, H, int(reverse), _lib.ptr(y),
+                _lib.ptr(reserve), _lib.stream_ptr(xproj.device))
     _lib.check(rc, 'forward')
     return y, reserve
 
 
-def kernel_backward(cell, dy, w_hh, reverse, y, reserve):
+def kernel_backward(cell, dy, w_hh, reverse, y, reserve, impl='legacy'):
+    """Returns the gradient of the gate-major xproj as fp32 (the `um` kernels
+    write it unit-major in bf16)."""
     from taiyaki_b200 import _lib
     lib = _lib.lib()
     T, N, H = dy.shape
     G = 4 if cell == 'lstm' else 3
+    code = 0 if cell == 'lstm' else 1
+    if impl == 'um':
+        dx16 = torch.empty(T, N, H * G, device=dy.device, dtype=torch.bfloat16)
+        dhid = torch.empty(T, N, H * G, device=dy.device, dtype=torch.bfloat16) if cell == 'gru' else None
+        rc = lib.ty_rnn_backward_um(code, _lib.ptr(dy), _lib.ptr(w_hh), T, N, H, int(reverse),
+                                    _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dx16),
+                                    _lib.ptr(dhid), None, _lib.stream_ptr(dy.device))
+        _lib.check(rc, 'backward')
+        dx = to_gate_major(dx16.float(), G)
+        dhn = to_gate_major(dhid.float(), G)[:, :, 2 * H:] if cell == 'gru' else None
+        return dx, dhn
     dx = torch.empty(T, N, G * H, device=dy.device)
     if cell == 'lstm':
         rc = lib.ty_lstm_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, int(reverse),
@@ -90,16 +124,17 @@ def kernel_backward(cell, dy, w_hh, reverse, y, reserve):
     return dx, dhn
 
 
+@pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('cell', ['lstm', 'gru'])
 @pytest.mark.parametrize('H,N,T,reverse', [
     (256, 8, 24, False), (256, 13, 17, True), (64, 3, 9, False), (128, 16, 11, True),
-    (192, 9, 7, False)])
-def test_forward_vs_emulated(dev, cell, H, N, T, reverse):
+    (192, 9, 7, False), (256, 64, 3, False), (128, 20, 1, True)])
+def test_forward_vs_emulated(dev, cell, H, N, T, reverse, impl):
     torch.manual_seed(H + N + T)
     G = 4 if cell == 'lstm' else 3
     xproj = torch.randn(T, N, G * H, device=dev)
     w_hh = torch.randn(G * H, H, device=dev) / np.sqrt(H)
-    y, _ = kernel_forward(cell, xproj, w_hh, reverse)
+    y, _ = kernel_forward(cell, xproj, w_hh, reverse, impl)
     ref = ref_recurrence(cell, xproj, w_hh, reverse, emulate=True)
     torch.cuda.synchronize()
     err = (y - ref).abs().max().item()
@@ -109,17 +144,19 @@ def test_forward_vs_emulated(dev, cell, H, N, T, reverse):
     assert (y - ref32).abs().max().item() < 5e-2
 
 
+@pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('cell', ['lstm', 'gru'])
 @pytest.mark.parametrize('H,N,T,reverse', [(256, 8, 20, False), (256, 11, 13, True),
-                                           (64, 5, 8, True)])
-def test_backward_vs_autograd_of_emulated(dev, cell, H, N, T, reverse):
+                                           (64, 5, 8, True), (192, 17, 6, False),
+                                           (128, 8, 1, False)])
+def test_backward_vs_autograd_of_emulated(dev, cell, H, N, T, reverse, impl):
     torch.manual_seed(7 + H + N)
     G = 4 if cell == 'lstm' else 3
     xproj = torch.randn(T, N, G * H, device=dev, requires_grad=True)
     w_hh = torch.randn(G * H, H, device=dev) / np.sqrt(H)
     dy = torch.randn(T, N, H, device=dev)
-    y, reserve = kernel_forward(cell, xproj.detach(), w_hh, reverse)
-    dx, dhn = kernel_backward(cell, dy, w_hh, reverse, y, reserve)
+    y, reserve = kernel_forward(cell, xproj.detach(), w_hh, reverse, impl)
+    dx, dhn = kernel_backward(cell, dy, w_hh, reverse, y, reserve, impl)
     ref = ref_recurrence(cell, xproj, w_hh, reverse, emulate=True)
     ref.backward(dy)
     torch.cuda.synchronize()
@@ -131,12 +168,14 @@ def test_backward_vs_autograd_of_emulated(dev, cell, H, N, T, reverse):
     assert rel < 1e-2, rel
 
 
+@pytest.mark.parametrize('impl', ['ws', 'legacy'])
 @pytest.mark.parametrize('cell', ['lstm', 'gru'])
 @pytest.mark.parametrize('reverse', [False, True])
-def test_module_vs_torch_nn(dev, cell, reverse):
+def test_module_vs_torch_nn(dev, cell, reverse, impl, monkeypatch):
     """Lstm / GruMod modules (forward + all parameter gradients) against
     torch.nn.LSTM / nn.GRU fp32 with the same weights."""
     from taiyaki_b200 import layers
+    monkeypatch.setattr(layers, 'RNN_IMPL', impl)
     torch.manual_seed(3)
     np.random.seed(3)
     T, N, I, H = 30, 8, 256, 256
@@ -167,13 +206,14 @@ def test_module_vs_torch_nn(dev, cell, reverse):
     assert rel < 3e-2, rel
 
 
-def test_long_sequence_stability(dev):
+@pytest.mark.parametrize('impl', IMPLS)
+def test_long_sequence_stability(dev, impl):
     """800 steps (BASELINE config A): outputs stay finite and track fp32."""
     torch.manual_seed(0)
     T, N, H = 800, 16, 256
     xproj = torch.randn(T, N, 4 * H, device=dev)
     w_hh = torch.randn(4 * H, H, device=dev) / np.sqrt(H)
-    y, _ = kernel_forward('lstm', xproj, w_hh, False)
+    y, _ = kernel_forward('lstm', xproj, w_hh, False, impl)
     ref = ref_recurrence('lstm', xproj, w_hh, False, emulate=False)
     torch.cuda.synchronize()
     assert torch.isfinite(y).all()

@@ -157,7 +157,12 @@ def bench_rnn_kernels(cell, T, N, H, tag, dy):
     else:
         f = lambda: lib.ty_gru_forward(_lib.ptr(xproj), None, _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), st)
         b = lambda: lib.ty_gru_backward(_lib.ptr(dy), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dxp), _lib.ptr(dhn), None, st)
-    for name, fn in [('kernel_fwd', f), ('kernel_bwd', b)]:
+    dx16 = torch.empty(T, N, G * H, device=dev, dtype=torch.bfloat16)
+    dh16 = torch.empty(T, N, G * H, device=dev, dtype=torch.bfloat16)
+    y16 = torch.empty(T, N, H, device=dev, dtype=torch.bfloat16)
+    fu = lambda: lib.ty_rnn_forward_um(code, _lib.ptr(xproj), None, _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(y16), _lib.ptr(reserve), st)
+    bu = lambda: lib.ty_rnn_backward_um(code, _lib.ptr(dy), _lib.ptr(w_hh), T, N, H, 0, _lib.ptr(y), _lib.ptr(reserve), _lib.ptr(dx16), _lib.ptr(dh16), None, st)
+    for name, fn in [('kernel_fwd', f), ('kernel_bwd', b), ('kernel_fwd_um', fu), ('kernel_bwd_um', bu)]:
         med, mn = timeit(fn, iters=5, warmup=2)
         emit(what='rnn_kernel', cell=cell, impl=name, tag=tag, T=T, N=N, H=H, ms_median=med,
              ms_min=mn, us_per_step=1e3 * med / T, variant=os.environ.get('TY_RNN_FWD', ''),

@@ -25,6 +25,13 @@ for _ in range(reps):
         ctc.crf_flipflop_cost_grad(scores, torch.tensor(seqs), torch.tensor(seqlen), 1.0, True)
     if 'logz' in which:
         layers.flipflop_logpartition(scores.detach().requires_grad_(True))
+    if 'gru' in which:
+        torch.manual_seed(0)
+        np.random.seed(0)
+        mod = layers.GruMod(256, 256).to(dev)
+        x = torch.randn(nblk, N, 256, device=dev, requires_grad=True)
+        y = mod(x)
+        y.backward(torch.ones_like(y))
     if 'rnn' in which:
         torch.manual_seed(0)
         np.random.seed(0)
