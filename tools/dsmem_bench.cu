@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(NT, 1) xchg(int rounds, int spin, unsigned *si
     const long long t0 = clock64();
     for (int s = 0; s < rounds; s++) {
         const int cur = s & 1, nxt = cur ^ 1;
-        if (M != 5 && tid == 0 && s + 1 < rounds) expect_tx(&full[nxt], CL * 512);
+        if (M != 5 && tid == 0 && s + 1 < rounds) expect_tx(&full[nxt], CL * (M == 10 ? 256 : M == 11 ? 128 : 512));
         if (s > 0) {
             if (M == 5) mbar_wait_acq(&full[cur], (phase >> cur) & 1u); else mbar_wait(&full[cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
@@ -93,6 +93,16 @@ __global__ void __launch_bounds__(NT, 1) xchg(int rounds, int spin, unsigned *si
                 // b32, 128 B contiguous per warp instruction
                 const uint32_t off = rank * 512 + warp * 128 + lane * 4;
                 for (uint32_t p = 0; p < CL; p++) st_async_b32(mapa(dst0 + off, p), acc, mapa(bar, p));
+            } else if (M == 10) {
+                // half the bytes: only lanes with q < 2 send (4 chunks per cluster)
+                const uint32_t off = rank * 512 + warp * 128 + lane * 4;
+                if ((lane & 3) < 2)
+                    for (uint32_t p = 0; p < CL; p++) st_async_b32(mapa(dst0 + off, p), acc, mapa(bar, p));
+            } else if (M == 11) {
+                // a quarter of the bytes: one warp sends
+                const uint32_t off = rank * 512 + lane * 4;
+                if (warp == 0)
+                    for (uint32_t p = 0; p < CL; p++) st_async_b32(mapa(dst0 + off, p), acc, mapa(bar, p));
             } else if (M == 2) {
                 // v2: 256 B contiguous per warp instruction; warp w covers half-blocks for peers
                 const uint32_t off = rank * 512 + (warp & 1) * 256 + lane * 8;
@@ -190,7 +200,7 @@ static int run(const char *name, int clusters, int rounds, int spin) {
 
 int main() {
     const int R = 4000;
-    for (int spin : {0, 200}) {
+    for (int spin : {0}) {
         for (int clusters : {8}) {
             run<8, 0>("b32 rows (as LSTM kernel)", clusters, R, spin);
             run<8, 1>("b32 128B-contiguous", clusters, R, spin);
@@ -204,6 +214,14 @@ int main() {
             run<8, 5>("st.cluster.v4 + release arrive", clusters, R, spin);
         }
     }
+    run<8, 10>("b32, 256 B per pair", 8, R, 0);
+    run<8, 10>("b32, 256 B per pair, 16 clusters", 16, R, 0);
+    run<8, 11>("b32, 128 B per pair", 8, R, 0);
+    run<8, 1>("b32 128B-contiguous, 16 clusters", 16, R, 0);
+    run<4, 1>("CL=4 b32 512 B per pair", 8, R, 0);
+    run<2, 1>("CL=2 b32 512 B per pair", 8, R, 0);
+    run<4, 3>("CL=4 v4 512 B per pair", 8, R, 0);
+    run<2, 11>("CL=2 b32 128 B per pair", 8, R, 0);
     run<16, 0>("b32 rows", 8, R, 0);
     run<16, 3>("v4.b32 512B-contiguous", 8, R, 0);
     run<16, 4>("staged + bulk copy 512B", 8, R, 0);
