@@ -173,7 +173,7 @@ def main():
                                      metadata=training.parse_network_metadata(net),
                                      stride=STRIDE)
     optimiser = torch.optim.AdamW(net.parameters(), lr=4e-3, betas=(0.9, 0.999),
-                                  weight_decay=0.01, eps=1e-6)
+                                  weight_decay=0.01, eps=1e-6, fused=True)
     step_fn = training.TrainStep(net_info, optimiser)
     nparam = sum(p.numel() for p in net.parameters() if p.requires_grad)
 

@@ -231,7 +231,8 @@ def load_network(args, alphabet_info, res_info, log):
     network_metadata = training.parse_network_metadata(network)
     stride = helpers.guess_model_stride(network)
     optimiser = torch.optim.AdamW(network.parameters(), lr=args.lr_max, betas=tuple(args.adam),
-                                  weight_decay=args.weight_decay, eps=args.eps)
+                                  weight_decay=args.weight_decay, eps=args.eps,
+                                  fused=True)   # one multi-tensor kernel per step
     lr_warmup = args.lr_min if args.lr_warmup is None else args.lr_warmup
     adam_beta1, _ = args.adam
     if args.warmup_batches >= args.niteration:

@@ -106,6 +106,39 @@ def _gate_major(w, G):
     return w.view(GH // G, G, K).transpose(0, 1).reshape(GH, K)
 
 
+#: When True (set by training.TrainStep around loss.backward()), the weight-gradient
+#: GEMMs of the recurrent layers run on a side stream, concurrently with the next
+#: layer's backward recurrence (which occupies 64 of the 148 SMs), and are added into
+#: `param.grad` there; `flush_weight_grads()` joins the side stream.  Off by default:
+#: plain autograd semantics (gradients returned through the graph).
+DEFER_WEIGHT_GRADS = False
+_pending = []          # (event, tensors kept alive until the join)
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = device.index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def flush_weight_grads():
+    """Make the current stream wait for every deferred weight-gradient update."""
+    global _pending
+    for ev, _keep in _pending:
+        torch.cuda.current_stream().wait_event(ev)
+    _pending = []
+
+
+def _accumulate_unit_major(param, dw_um, G):
+    """param.grad (gate-major) += dw (unit-major rows), in place."""
+    GH, K = dw_um.shape
+    if param.grad is None:
+        param.grad = torch.zeros_like(param)
+    param.grad.view(G, GH // G, K).transpose(0, 1).add_(dw_um.view(GH // G, G, K))
+
+
 #: 'ws' = warp-specialised kernels behind the unit-major ABI (csrc/rnn_ws.cu, bf16
 #: projections only); 'legacy' = one-role kernels behind the gate-major ABI (csrc/rnn.cu)
 RNN_IMPL = 'ws'
@@ -158,9 +191,11 @@ class _Recurrence(torch.autograd.Function):
         _lib.count_launches(1)
         ctx.save_for_backward(xo, wo, w_hh_c, y, reserve, y16)
         ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H, I, um)
+        ctx.weights = (w_ih, w_hh)
         if y16 is None:
             y16 = y.new_empty(0)
         ctx.mark_non_differentiable(y16)
+        ctx.set_materialize_grads(False)     # no zero tensor for the bf16 side output
         return y, y16
 
     @staticmethod
@@ -172,6 +207,8 @@ class _Recurrence(torch.autograd.Function):
         dev = y.device
         use16 = y16 is not None
         gdt = torch.bfloat16 if use16 else torch.float32
+        if dy is None:
+            dy = torch.zeros_like(y)
         dy = dy.contiguous().float()
         # gradients w.r.t. the projections are only ever GEMM operands: the kernel
         # writes them in the operand type; the bias gradient is summed in fp32 inside
@@ -192,9 +229,28 @@ class _Recurrence(torch.autograd.Function):
             _lib.check(rc, 'ty_rnn_backward_um')
             _lib.count_launches(1)
             d2 = do.view(T * N, G * H)
+            dh_side = do if cell == _CELL_LSTM else dhid
+            w_ih, w_hh = ctx.weights
+            if DEFER_WEIGHT_GRADS and w_ih.is_leaf and w_hh.is_leaf:
+                main = torch.cuda.current_stream(dev)
+                side = _side_stream(dev)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    dw_ih = _mm(d2.t(), xo)
+                    dw_hh = _mm(dh_side[sl_cur].reshape(-1, G * H).t(), hp2)
+                    if ctx.needs_input_grad[1]:
+                        _accumulate_unit_major(w_ih, dw_ih, G)
+                    if ctx.needs_input_grad[2]:
+                        _accumulate_unit_major(w_hh, dw_hh, G)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                _pending.append((done, (do, dhid, xo, yo, dw_ih, dw_hh)))
+                dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
+                return dx, None, None, db, None, None, None
             dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
             dw_ih = _gate_major(_mm(d2.t(), xo), G)
-            dh_side = do if cell == _CELL_LSTM else dhid
             dw_hh = _gate_major(_mm(dh_side[sl_cur].reshape(-1, G * H).t(), hp2), G)
             return dx, dw_ih, dw_hh, db, None, None, None
         dhn = torch.empty(T, N, H, dtype=gdt, device=dev) if cell == _CELL_GRU else None
@@ -472,6 +528,45 @@ class Convolution(nn.Module):
         return res
 
 
+class _ProjLinear(torch.autograd.Function):
+    """y = x W^T + b as a dense bf16 contraction with fp32 accumulation and fp32
+    result (the same operand policy as the recurrent layers' projections); the
+    bf16 copy of x written by a preceding recurrent layer is used when present."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, x16):
+        T, N, I = x.shape
+        xo = x16.view(T * N, I) if x16 is not None else _operand(x.reshape(T * N, I))
+        wo = _operand(weight.detach())
+        out = _mm(xo, wo.t())
+        if bias is not None:
+            out += bias.detach()
+        ctx.save_for_backward(xo, wo)
+        ctx.has_bias = bias is not None
+        return out.view(T, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xo, wo = ctx.saved_tensors
+        T, N, O = dy.shape
+        d2 = dy.reshape(T * N, O)
+        do = _operand(d2)
+        dx = _mm(do, wo).view(T, N, -1) if ctx.needs_input_grad[0] else None
+        dw = _mm(do.t(), xo)
+        db = d2.sum(0) if ctx.has_bias else None
+        return dx, dw, db, None
+
+
+def _proj_linear(linear, x):
+    """`linear(x)` for a time-major CUDA tensor through the bf16 projection path."""
+    if not x.is_cuda or x.dim() != 3 or PROJECTION_DTYPE != 'bf16':
+        return linear(x)
+    x16 = getattr(x, '_ty_bf16', None)
+    if x16 is not None and (x16.shape != x.shape or x16.device != x.device):
+        x16 = None
+    return _ProjLinear.apply(x, linear.weight, linear.bias, x16)
+
+
 class GlobalNormFlipFlop(nn.Module):
     """scale * fun(x W + b) transition scores (layers.py:1316-1411); global
     normalisation is the loss function's job."""
@@ -501,7 +596,7 @@ class GlobalNormFlipFlop(nn.Module):
             init_(self.linear.bias, truncated_normal(list(self.linear.bias.shape), sd=0.5))
 
     def forward(self, x):
-        return self.scale * self.activation(self.linear(x))
+        return self.scale * self.activation(_proj_linear(self.linear, x))
 
 
 class GlobalNormFlipFlopCatMod(nn.Module):
@@ -589,7 +684,7 @@ class GlobalNormFlipFlopCatMod(nn.Module):
         return torch.cat(mod_layers, dim=2)
 
     def forward(self, x):
-        y = self.linear(x)
+        y = _proj_linear(self.linear, x)
         trans_scores = 5.0 * activation.tanh(y[:, :, :self.ntrans_states])
         cat_mod_scores = y[:, :, self.ntrans_states:]
         assert cat_mod_scores.shape[2] == self.nmod_base + 1, (

@@ -28,6 +28,8 @@ MOD_INFO = namedtuple('MOD_INFO', ('mod_cat_weights', 'mod_factor'))
 
 #: use ctc.flipflop_train_loss (one fused operator) inside flipflop_loss
 FUSED_LOSS = True
+#: run the recurrent layers' weight-gradient GEMMs on a side stream during backward
+DEFER_WEIGHT_GRADS = True
 
 
 def parse_network_metadata(network):
@@ -124,7 +126,15 @@ def calculate_loss(net_info, batch_gen, sharpen, mod_cat_weights=None, mod_facto
                 lossvector = flipflop_loss(outputs, seqs, seqlens, sharpen)
             loss = lossvector.mean()
         if calc_grads:
-            loss.backward()
+            # weight-gradient GEMMs of the recurrent layers overlap the next layer's
+            # backward recurrence on a side stream (layers.DEFER_WEIGHT_GRADS)
+            prev = layers.DEFER_WEIGHT_GRADS
+            layers.DEFER_WEIGHT_GRADS = DEFER_WEIGHT_GRADS and loss.is_cuda
+            try:
+                loss.backward()
+            finally:
+                layers.DEFER_WEIGHT_GRADS = prev
+                layers.flush_weight_grads()
         total_fval = loss.detach() if total_fval is None else total_fval + loss.detach()
         total_samples += int(indata.nelement())
         total_bases += ctc._max_len(seqlens)[1]     # host value (or a registered hint)
