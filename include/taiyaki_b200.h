@@ -215,6 +215,35 @@ int ty_rnn_backward_um(int cell, const float *dy, const float *w_hh, int T, int 
 int ty_col2im_time_major(const float *dcols, int Tout, int N, int C, int k,
                          int stride, int pad_left, int T, float *dx, void *stream);
 
+/* Same with a row stride ld >= C*k of dcols (GEMM operands padded to 8 columns). */
+int ty_col2im_time_major_ld(const float *dcols, int ld, int Tout, int N, int C, int k,
+                            int stride, int pad_left, int T, float *dx, void *stream);
+
+/* Window gather of the convolution (layers.py:816-831) straight into the GEMM
+ * operand: cols[to*N + n][c*k + j] = x[to*stride + j - pad_left][n][c] as bf16,
+ * [Tout*N][ld] with ld a multiple of 8 and > C*k; column C*k is 1.0 (so the bias
+ * rides in the GEMM as column C*k of the weight operand and its gradient falls
+ * out of the weight-gradient GEMM), further columns 0. */
+int ty_im2col_time_major_bf16(const float *x, int T, int N, int C, int k, int stride,
+                              int pad_left, int Tout, int ld, void *cols_bf16,
+                              void *stream);
+
+/* Direct small convolutions (stride 1; the 1->4 and 4->16 channel, window 5
+ * layers of models/mLstm_flipflop.py), time-major fp32 [T][N][C].
+ * act: 0 linear, 1 tanh, 2 swish (taiyaki/activation.py).  forward writes the
+ * pre-activation z and a = act(z), both [T][N][Cout]; backward takes da, uses
+ * dz [T][N][Cout] as scratch, ACCUMULATES into dW [Cout][C][k] and db [Cout]
+ * (db may be NULL) and writes dx [T][N][C] unless it is NULL.
+ * ty_conv_small_supported() tells which (C, Cout, k) are instantiated. */
+int ty_conv_small_supported(int C, int Cout, int k);
+int ty_conv_small_forward(const float *x, const float *w, const float *b, int T, int N,
+                          int C, int Cout, int k, int pad_left, int act, float *z,
+                          float *a, void *stream);
+int ty_conv_small_backward(const float *da, const float *z, const float *x,
+                           const float *w, int T, int N, int C, int Cout, int k,
+                           int pad_left, int act, float *dz, float *dW, float *db,
+                           float *dx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,16 @@ _SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ty_col2im_time_major': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p]),
+    'ty_col2im_time_major_ld': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_void_p, c_void_p]),
+    'ty_im2col_time_major_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, c_int, c_void_p, c_void_p]),
+    'ty_conv_small_supported': (c_int, [c_int] * 3),
+    'ty_conv_small_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'ty_conv_small_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
     'ty_rnn_reserve_bytes': (c_size_t, [c_int] * 4),
     'ty_rnn_forward_ex': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -432,52 +432,118 @@ class Serial(nn.Module):
 class _ConvTimeMajor(torch.autograd.Function):
     """1D convolution of a time-major [T, N, C] tensor as window-gather + one
     dense GEMM, producing time-major [T_out, N, C_out] directly (no TBF<->BFT
-    permutes, layers.py:816-831).  Backward: weight gradient and column
-    gradient are GEMMs, the column gradient is scattered back with `fold`.
-    Same arithmetic as nn.Conv1d on the zero-padded signal."""
+    permutes, layers.py:816-831).  Same arithmetic as nn.Conv1d on the
+    zero-padded signal.  Wide layers (C*k >= 64, the strided feature layer):
+    the gather writes the bf16 GEMM operand directly (ty_im2col_time_major_bf16)
+    with a column of ones, so the bias is part of the GEMM and its gradient a
+    column of the weight-gradient GEMM.  Narrow layers: fp32 / TF32 operands."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding):
         T, N, C = x.shape
         Cout, _, k = weight.shape
-        xp = torch.nn.functional.pad(x, (0, 0, 0, 0, padding[0], padding[1]))
-        Tp = xp.shape[0]
+        Tp = T + padding[0] + padding[1]
         Tout = (Tp - k) // stride + 1
-        cols = xp.unfold(0, k, stride).reshape(Tout * N, C * k)     # [T_out*N, C*k]
-        wide = C * k >= 64
-        co = _operand(cols) if wide else cols
-        wo = weight.detach().reshape(Cout, C * k)
-        wo = _operand(wo) if wide else wo
-        out = _mm(co, wo.t())
-        if bias is not None:
-            out += bias.detach()
+        wide = C * k >= 64 and x.is_cuda and PROJECTION_DTYPE == 'bf16'
+        if wide:
+            ld = (C * k + 1 + 7) // 8 * 8
+            xc = x.detach().contiguous().float()
+            co = torch.empty(Tout * N, ld, dtype=torch.bfloat16, device=x.device)
+            rc = _lib.lib().ty_im2col_time_major_bf16(
+                _lib.ptr(xc), T, N, C, k, stride, padding[0], Tout, ld, _lib.ptr(co),
+                _lib.stream_ptr(x.device))
+            _lib.check(rc, 'ty_im2col_time_major_bf16')
+            _lib.count_launches(1)
+            wo = torch.zeros(Cout, ld, dtype=torch.bfloat16, device=x.device)
+            wo[:, :C * k] = weight.detach().reshape(Cout, C * k)
+            if bias is not None:
+                wo[:, C * k] = bias.detach()
+            out = _mm(co, wo.t())
+        else:
+            ld = C * k
+            xp = torch.nn.functional.pad(x, (0, 0, 0, 0, padding[0], padding[1]))
+            co = xp.unfold(0, k, stride).reshape(Tout * N, C * k)     # [T_out*N, C*k]
+            wo = weight.detach().reshape(Cout, C * k)
+            out = _mm(co, wo.t())
+            if bias is not None:
+                out += bias.detach()
         ctx.save_for_backward(co, wo)
-        ctx.cfg = (T, N, C, Cout, k, stride, padding, Tp, Tout, wide, bias is not None)
+        ctx.cfg = (T, N, C, Cout, k, stride, padding, Tp, Tout, wide, bias is not None, ld)
         return out.view(Tout, N, Cout)
 
     @staticmethod
     def backward(ctx, dout):
         co, wo = ctx.saved_tensors
-        T, N, C, Cout, k, stride, padding, Tp, Tout, wide, has_bias = ctx.cfg
+        T, N, C, Cout, k, stride, padding, Tp, Tout, wide, has_bias, ld = ctx.cfg
         d2 = dout.reshape(Tout * N, Cout)
-        db = d2.sum(0) if has_bias else None
         do = _operand(d2) if wide else d2
-        dw = _mm(do.t(), co).view(Cout, C, k)
+        dwf = _mm(do.t(), co)                                        # [Cout, ld]
+        if wide:
+            dw = dwf[:, :C * k].reshape(Cout, C, k)
+            db = dwf[:, C * k] if has_bias else None
+        else:
+            dw = dwf.view(Cout, C, k)
+            db = d2.sum(0) if has_bias else None
         dx = None
         if ctx.needs_input_grad[0]:
-            dcols = _mm(do, wo)                                     # [T_out*N, C*k]
+            dcols = _mm(do, wo)                                     # [T_out*N, ld]
             if dcols.is_cuda:
                 dx = torch.empty(T, N, C, dtype=torch.float32, device=dcols.device)
-                rc = _lib.lib().ty_col2im_time_major(
-                    _lib.ptr(dcols), Tout, N, C, k, stride, padding[0], T, _lib.ptr(dx),
+                rc = _lib.lib().ty_col2im_time_major_ld(
+                    _lib.ptr(dcols), ld, Tout, N, C, k, stride, padding[0], T, _lib.ptr(dx),
                     _lib.stream_ptr(dcols.device))
-                _lib.check(rc, 'ty_col2im_time_major')
+                _lib.check(rc, 'ty_col2im_time_major_ld')
                 _lib.count_launches(1)
             else:
                 dcols = dcols.view(Tout, N, C * k).permute(1, 2, 0)     # [N, C*k, T_out]
                 dxp = torch.nn.functional.fold(dcols, output_size=(1, Tp), kernel_size=(1, k),
                                                stride=(1, stride))      # [N, C, 1, Tp]
                 dx = dxp[:, :, 0, padding[0]:padding[0] + T].permute(2, 0, 1)
+        return dx, dw, db, None, None
+
+
+_ACT_CODES = {activation.linear: 0, activation.tanh: 1, activation.swish: 2}
+
+
+class _ConvSmall(torch.autograd.Function):
+    """Stride-1 convolution with few channels + activation as direct kernels
+    (csrc/conv.cu: conv_small_*): one launch forward, three backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad_left, act):
+        T, N, C = x.shape
+        Cout, _, k = weight.shape
+        xc = x.detach().contiguous().float()
+        wc = weight.detach().contiguous().float()
+        bc = bias.detach().contiguous().float() if bias is not None else None
+        z = torch.empty(T, N, Cout, dtype=torch.float32, device=x.device)
+        a = torch.empty_like(z)
+        rc = _lib.lib().ty_conv_small_forward(_lib.ptr(xc), _lib.ptr(wc), _lib.ptr(bc), T, N, C,
+                                              Cout, k, pad_left, act, _lib.ptr(z), _lib.ptr(a),
+                                              _lib.stream_ptr(x.device))
+        _lib.check(rc, 'ty_conv_small_forward')
+        _lib.count_launches(1)
+        ctx.save_for_backward(xc, wc, z)
+        ctx.cfg = (pad_left, act, bias is not None)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        xc, wc, z = ctx.saved_tensors
+        pad_left, act, has_bias = ctx.cfg
+        T, N, C = xc.shape
+        Cout, _, k = wc.shape
+        da = da.contiguous().float()
+        dz = torch.empty_like(z)
+        dw = torch.zeros_like(wc)
+        db = torch.zeros(Cout, dtype=torch.float32, device=xc.device) if has_bias else None
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        rc = _lib.lib().ty_conv_small_backward(
+            _lib.ptr(da), _lib.ptr(z), _lib.ptr(xc), _lib.ptr(wc), T, N, C, Cout, k, pad_left,
+            act, _lib.ptr(dz), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dx),
+            _lib.stream_ptr(xc.device))
+        _lib.check(rc, 'ty_conv_small_backward')
+        _lib.count_launches(3 if dx is not None else 2)
         return dx, dw, db, None, None
 
 
@@ -510,6 +576,11 @@ class Convolution(nn.Module):
 
     def forward(self, x):
         if x.is_cuda:
+            act = _ACT_CODES.get(self.activation, None)
+            if (self.stride == 1 and act is not None and x.dim() == 3 and
+                    self.padding[0] + self.padding[1] == self.winlen - 1 and
+                    _lib.lib().ty_conv_small_supported(self.insize, self.size, self.winlen)):
+                return _ConvSmall.apply(x, self.conv.weight, self.conv.bias, self.padding[0], act)
             out = _ConvTimeMajor.apply(x, self.conv.weight, self.conv.bias, self.stride,
                                        self.padding)
             return self.activation(out)

@@ -120,27 +120,57 @@ def test_train_flipflop_entry_point(dev, tmp_path):
     assert 'ksample/s' in (out / 'model.log').read_text()
 
 
+@pytest.mark.parametrize('fun', ['linear', 'swish', 'tanh'])
 @pytest.mark.parametrize('C,Cout,k,stride', [(1, 4, 5, 1), (4, 16, 5, 1), (16, 256, 19, 5),
-                                             (1, 256, 19, 2)])
-def test_convolution_matches_conv1d(dev, C, Cout, k, stride):
-    """layers.Convolution (window gather + GEMM, time-major) against nn.Conv1d on the
-    zero-padded signal (taiyaki/layers.py:791-831); wide layers use bf16 operands."""
-    from taiyaki_b200 import layers
-    from taiyaki_b200.activation import linear
+                                             (1, 256, 19, 2), (3, 8, 7, 1)])
+def test_convolution_matches_conv1d(dev, C, Cout, k, stride, fun):
+    """layers.Convolution against nn.Conv1d on the zero-padded signal followed by
+    the activation (taiyaki/layers.py:791-831): direct kernels for the small
+    stride-1 layers, window gather + GEMM otherwise (bf16 operands when wide)."""
+    from taiyaki_b200 import activation, layers
     torch.manual_seed(0)
     np.random.seed(0)
-    conv = layers.Convolution(C, Cout, k, stride=stride, fun=linear).to(dev)
+    f = getattr(activation, fun)
+    conv = layers.Convolution(C, Cout, k, stride=stride, fun=f).to(dev)
     x1 = torch.randn(403, 5, C, device=dev, requires_grad=True)
     x2 = x1.detach().clone().requires_grad_(True)
     y1 = conv(x1)
-    y2 = conv.conv(conv.pad(x2.permute(1, 2, 0))).permute(2, 0, 1)
+    y2 = f(conv.conv(conv.pad(x2.permute(1, 2, 0))).permute(2, 0, 1))
     assert y1.shape == y2.shape == (-(-403 // stride), 5, Cout)
     g = torch.randn_like(y2)
     y1.backward(g)
     gw1 = conv.conv.weight.grad.clone()
+    gb1 = conv.conv.bias.grad.clone()
     conv.zero_grad()
     y2.backward(g)
     tol = 2e-2 if C * k >= 64 else 1e-3
     assert (y1 - y2).abs().max().item() < tol * max(1.0, y2.abs().max().item())
     assert ((x1.grad - x2.grad).norm() / x2.grad.norm()).item() < tol
     assert ((gw1 - conv.conv.weight.grad).norm() / conv.conv.weight.grad.norm()).item() < tol
+    assert ((gb1 - conv.conv.bias.grad).norm() / conv.conv.bias.grad.norm()).item() < tol
+
+
+def test_deferred_weight_grads_match(dev):
+    """layers.DEFER_WEIGHT_GRADS (weight-gradient GEMMs on a side stream, added into
+    .grad there) gives the gradients plain autograd gives."""
+    from taiyaki_b200 import layers
+    torch.manual_seed(5)
+    np.random.seed(5)
+    net = layers.Serial([layers.Reverse(layers.Lstm(64, 64)), layers.GruMod(64, 64),
+                         layers.Lstm(64, 64)]).to(dev)
+    x = torch.randn(40, 9, 64, device=dev)
+    w = torch.randn(40, 9, 64, device=dev)
+    grads = []
+    for defer in (False, True):
+        net.zero_grad()
+        layers.DEFER_WEIGHT_GRADS = defer
+        try:
+            (net(x) * w).sum().backward()
+        finally:
+            layers.DEFER_WEIGHT_GRADS = False
+            layers.flush_weight_grads()
+        torch.cuda.synchronize()
+        grads.append([p.grad.clone() for p in net.parameters() if p.requires_grad])
+    assert len(grads[0]) == len(grads[1]) == 9
+    for a, b in zip(*grads):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
