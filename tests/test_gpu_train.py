@@ -131,6 +131,7 @@ def test_convolution_matches_conv1d(dev, C, Cout, k, stride, fun):
     torch.manual_seed(0)
     np.random.seed(0)
     f = getattr(activation, fun)
+    torch.backends.cudnn.allow_tf32 = False      # the nn.Conv1d reference in full fp32
     conv = layers.Convolution(C, Cout, k, stride=stride, fun=f).to(dev)
     x1 = torch.randn(403, 5, C, device=dev, requires_grad=True)
     x2 = x1.detach().clone().requires_grad_(True)
@@ -143,7 +144,13 @@ def test_convolution_matches_conv1d(dev, C, Cout, k, stride, fun):
     gb1 = conv.conv.bias.grad.clone()
     conv.zero_grad()
     y2.backward(g)
-    tol = 2e-2 if C * k >= 64 else 1e-3
+    from taiyaki_b200 import _lib
+    if stride == 1 and _lib.lib().ty_conv_small_supported(C, Cout, k):
+        tol = 1e-4          # direct fp32 kernels
+    elif C * k >= 64:
+        tol = 2e-2          # bf16 operands
+    else:
+        tol = 4e-3          # TF32 operands (what cuDNN does for the reference on Ampere+)
     assert (y1 - y2).abs().max().item() < tol * max(1.0, y2.abs().max().item())
     assert ((x1.grad - x2.grad).norm() / x2.grad.norm()).item() < tol
     assert ((gw1 - conv.conv.weight.grad).norm() / conv.conv.weight.grad.norm()).item() < tol
