@@ -12,6 +12,7 @@ Differences from the reference are confined to where the work happens: scores
 stay on the device through the loss, and the per-tensor `float(max|grad|)` host
 round trips of apply_clipping become one device reduction and one copy.
 """
+import os
 from collections import defaultdict, namedtuple
 
 import numpy as np
@@ -29,7 +30,8 @@ MOD_INFO = namedtuple('MOD_INFO', ('mod_cat_weights', 'mod_factor'))
 #: use ctc.flipflop_train_loss (one fused operator) inside flipflop_loss
 FUSED_LOSS = True
 #: run the recurrent layers' weight-gradient GEMMs on a side stream during backward
-DEFER_WEIGHT_GRADS = True
+#: (TY_DEFER_WGRAD=0 in the environment turns it off, for A/B timing)
+DEFER_WEIGHT_GRADS = os.environ.get('TY_DEFER_WGRAD', '1') != '0'
 
 
 def parse_network_metadata(network):
