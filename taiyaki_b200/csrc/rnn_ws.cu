@@ -7,7 +7,7 @@
 //     units [j*U, (j+1)*U), U = H/8, for all gates; its W_hh slice lives in
 //     registers as bf16 mma.sync A fragments; h_t (forward) / partial dL/dh
 //     (backward) cross the cluster as st.async + mbarrier complete_tx.
-// What is different (profiles/r2_rnn_stalls.md): in the one-role kernels a
+// What is different (profiles/r1_rnn_stalls.md): in the one-role kernels a
 // third of every step was the compute warp waiting on its OWN global-memory
 // instructions -- write-after-read scoreboard stalls on the operands of 8
 // cp.async, 8 st.global and 8 st.async per thread, constant-bank reloads and
