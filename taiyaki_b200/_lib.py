@@ -13,7 +13,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
-LIB_PATH = os.path.join(_HERE, 'libtaiyaki_b200.so')
+LIB_PATH = os.environ.get('TY_B200_LIB', os.path.join(_HERE, 'libtaiyaki_b200.so'))   # override: A/B builds
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17', '-Xcompiler', '-fPIC', '-shared']

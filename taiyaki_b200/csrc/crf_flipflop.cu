@@ -87,6 +87,30 @@ __device__ __forceinline__ float logaddexp2(float x, float y) {
     return fmaxf(x, y) + lg2f(1.0f + ex2f(-fabsf(x - y)));
 }
 
+// ---------------------------------------------------------------------------
+// Shared-memory accesses of the chain's step loop use 32-bit shared-window
+// addresses computed once and kept opaque: through generic pointers the compiler
+// re-derives the window base (S2R SR_CgaCtaId, ~25 cycles of latency) and the
+// thread index (S2R SR_TID.X) inside the loop, on the step's dependency chain.
+__device__ __forceinline__ float lds_v_f32(unsigned a) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v_f32(unsigned a, float v) {
+    asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(a), "f"(v));
+}
+__device__ __forceinline__ unsigned opaque(unsigned x) {   // keeps a loop-invariant value in a register
+    unsigned y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ unsigned pinned_tid() {         // not rematerialised as S2R in the loop
+    unsigned t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t;
+}
+
 // One chain.  Warp-specialised: warps 0..ncw-1 run the DP; the LAST warp is the
 // "transformer": it owns the cp.async ring, turns raw score rows into
 // w*sharp*log2(e) - c one step ahead, and keeps the offset bookkeeping, so the
@@ -100,13 +124,18 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
     __shared__ __align__(16) float wmaxs[2][32];
     __shared__ float s_end;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = (int)pinned_tid(), lane = tid & 31, warp = tid >> 5;
     const int ncw = (blockDim.x >> 5) - 1;          // DP warps
     const bool is_tx = warp == ncw;
     const int S = a.ntrans;
     const int nblk = a.nblk;
     const size_t ld = (size_t)a.nbatch * S;
     const int p0 = tid * P;
+    // shared-window addresses used inside the step loop (see lds_v_f32)
+    const unsigned tr_u32 = opaque((unsigned)__cvta_generic_to_shared(&tr[0][0]));
+    const unsigned raw_u32 = opaque((unsigned)__cvta_generic_to_shared(&raw[0][0]) + lane * 4);
+    const unsigned bnd_u32 = opaque((unsigned)__cvta_generic_to_shared(&bnd[0][0]));
+    const unsigned wmaxs_u32 = opaque((unsigned)__cvta_generic_to_shared(&wmaxs[0][0]));
 
     // ---- DP state: byte offsets into a transformed row (pad slot when invalid) ----
     int st[P], mv[P], mm[P];
@@ -150,13 +179,15 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
         src += tstep;
     };
     auto transform_row = [&](int k, int par, float c) {
+        const unsigned ra = raw_u32 + (unsigned)(k & (kRing - 1)) * (kRowPad * 4);
+        const unsigned ta = tr_u32 + (unsigned)par * (kRowPad * 4) + lane * 4;
         if (l0) {
-            const float w = raw[k & (kRing - 1)][lane];
-            tr[par][lane] = can0 ? fmaf(w, sc0, -c) : w * sc0;
+            const float w = lds_v_f32(ra);
+            sts_v_f32(ta, can0 ? fmaf(w, sc0, -c) : w * sc0);
         }
         if (l1) {
-            const float w = raw[k & (kRing - 1)][lane + 32];
-            tr[par][lane + 32] = can1 ? fmaf(w, sc1, -c) : w * sc1;
+            const float w = lds_v_f32(ra + 128);
+            sts_v_f32(ta + 128, can1 ? fmaf(w, sc1, -c) : w * sc1);
         }
     };
     float coff_run = 0.f;             // accumulated offset of the vector in registers
@@ -201,7 +232,7 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
             // m_{k-1}; two shifts (rows k-1, k) were applied since, so the shift
             // that re-centres is m_{k-1} - c_{k-1} - c_k.  (Subtracting the stale
             // max alone is an unstable recurrence.)
-            const float c_next = warp_max(wmaxs[PAR ^ 1][lane]) - c_cur - c_prev;
+            const float c_next = warp_max(lds_v_f32(wmaxs_u32 + (PAR ^ 1) * 128 + lane * 4)) - c_cur - c_prev;
             if (a.want_grad) {
                 if (lane == 0) *coff = coff_run;
                 coff += DIR == 0 ? 1 : -1;
@@ -213,7 +244,7 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
             cp_async_wait<kDepth - 1>();          // own copies of row k+1 have landed
             if (k + 1 < nblk) transform_row(k + 1, PAR ^ 1, c_next);
         } else {
-            if (lane == 0) wmaxs[PAR][warp] = pend_max;
+            if (lane == 0) sts_v_f32(wmaxs_u32 + PAR * 128 + warp * 4, pend_max);
             // spill alpha_t (DIR 0) / beta_{t+1} (DIR 1) for the posterior kernel
             if (a.want_grad) {
                 if (P % 4 == 0) {
@@ -229,35 +260,43 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
                 }
                 dst += dstep;
             }
-            // neighbour value across the thread boundary
+            // gathers from the transformed row first (volatile: they keep this order),
+            // then the neighbour value across the thread boundary
+            const unsigned row = tr_u32 + PAR * (kRowPad * 4);
+            float gs[P], gm[P];
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                gs[i] = lds_v_f32(row + st[i]);
+                gm[i] = lds_v_f32(row + mv[i]);
+            }
+            if (MOD) {
+#pragma unroll
+                for (int i = 0; i < P; i++) gm[i] = fmaf(lds_v_f32(row + mm[i]), mf[i], gm[i]);
+            }
             float nb;
             if (DIR == 0) {
                 nb = __shfl_up_sync(kFullMask, al[P - 1], 1);
-                if (lane == 0) nb = warp > 0 ? bnd[PAR ^ 1][warp - 1] : kNegLarge;
+                if (lane == 0) nb = warp > 0 ? lds_v_f32(bnd_u32 + (PAR ^ 1) * 128 + (warp - 1) * 4) : kNegLarge;
             } else {
                 nb = __shfl_down_sync(kFullMask, al[0], 1);
-                if (lane == 31) nb = warp + 1 < ncw ? bnd[PAR ^ 1][warp + 1] : kNegLarge;
+                if (lane == 31) nb = warp + 1 < ncw ? lds_v_f32(bnd_u32 + (PAR ^ 1) * 128 + (warp + 1) * 4) : kNegLarge;
             }
-            const char *row = reinterpret_cast<const char *>(tr[PAR]);
             float nw[P];
             float tmax = -3.0e38f;
 #pragma unroll
             for (int i = 0; i < P; i++) {
-                const float stay = al[i] + *reinterpret_cast<const float *>(row + st[i]);
                 float other;
                 if (DIR == 0) other = (i == 0) ? nb : al[i - 1];
                 else other = (i == P - 1) ? nb : al[i + 1];
-                float move = other + *reinterpret_cast<const float *>(row + mv[i]);
-                if (MOD) move = fmaf(*reinterpret_cast<const float *>(row + mm[i]), mf[i], move);
-                nw[i] = logaddexp2(stay, move);
+                nw[i] = logaddexp2(al[i] + gs[i], other + gm[i]);
                 tmax = fmaxf(tmax, nw[i]);
             }
 #pragma unroll
             for (int i = 0; i < P; i++) al[i] = nw[i];
             if (DIR == 0) {
-                if (lane == 31) bnd[PAR][warp] = al[P - 1];
+                if (lane == 31) sts_v_f32(bnd_u32 + PAR * 128 + warp * 4, al[P - 1]);
             } else {
-                if (lane == 0) bnd[PAR][warp] = al[0];
+                if (lane == 0) sts_v_f32(bnd_u32 + PAR * 128 + warp * 4, al[0]);
             }
             pend_max = warp_max(tmax);
         }
