@@ -60,6 +60,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ int pinned_tid_x() {   // not rematerialised as S2R inside the step loop
+    int t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -100,7 +105,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2 + 32, 1
     uint64_t *const xfull = full + 2;                                         // [kS]
     uint64_t *const ofull = xfull + kS;                                       // [kS]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = pinned_tid_x(), lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
     const int group = blockIdx.x / kCluster;
     const int T = a.T, N = a.N;
@@ -429,7 +434,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(H / 2 + 32, 1
     uint64_t *const ifull = full + 2;                                         // [kS]
     uint64_t *const ofull = ifull + kS;                                       // [kS]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = pinned_tid_x(), lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
     const int group = blockIdx.x / kCluster;
     const int T = a.T, N = a.N;
