@@ -155,6 +155,9 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log (version banner, NCCL_DEBUG=INFO)
+        # goes to stderr unless the caller chose a file
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=device)
     seed = 1 + rank                       # train_flipflop.py:266-268
     np.random.seed(seed)
