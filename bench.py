@@ -56,6 +56,12 @@ def parse():
     ap.add_argument('--ref-chunks', type=int, default=4,
                     help='chunks per step of the CPU reference sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    # the other BASELINE.json configurations (parity / sweep cases, not the contract line):
+    ap.add_argument('--model', default='mLstm_flipflop',
+                    choices=['mLstm_flipflop', 'mGru_flipflop', 'mGru_cat_mod_flipflop',
+                             'mLstm_cat_mod_flipflop'],
+                    help='model definition under models/ (default: the contract workload)')
+    ap.add_argument('--tsig', type=int, default=T_SIG, help='chunk length in samples (sweep E)')
     return ap.parse_args()
 
 
@@ -164,8 +170,18 @@ def main():
     torch.manual_seed(seed)
 
     # ---- model, optimiser (train_flipflop.py:332-429) ----
-    alphabet_info = AlphabetInfo('ACGT', 'ACGT')
-    net = helpers.load_model(os.path.join(ROOT, 'models', 'mLstm_flipflop.py'),
+    global T_SIG, STRIDE, NTRANS, WORKLOAD
+    cat_mod = 'cat_mod' in args.model
+    if args.model != 'mLstm_flipflop' or args.tsig != T_SIG:
+        args.no_cpu_baseline = True          # the CPU arm times the contract workload only
+        T_SIG = args.tsig
+        STRIDE = 5 if 'Lstm' in args.model else 2
+        NTRANS = 45 if cat_mod else 40
+        WORKLOAD = '%s size%d stride%d, T_sig=%d (nblk=%d), %d chunks/GPU, S=%d' % (
+            args.model, SIZE, STRIDE, T_SIG, -(-T_SIG // STRIDE), NCHUNK, NTRANS)
+    alphabet_info = (AlphabetInfo('ACGTZ', 'ACGTC', ['5mC']) if cat_mod
+                     else AlphabetInfo('ACGT', 'ACGT'))
+    net = helpers.load_model(os.path.join(ROOT, 'models', args.model + '.py'),
                              model_metadata={'reverse': False, 'standardize': True},
                              stride=STRIDE, winlen=19, insize=1, size=SIZE,
                              alphabet_info=alphabet_info).to(device)
@@ -177,11 +193,13 @@ def main():
                                      stride=STRIDE)
     optimiser = torch.optim.AdamW(net.parameters(), lr=4e-3, betas=(0.9, 0.999),
                                   weight_decay=0.01, eps=1e-6, fused=True)
-    step_fn = training.TrainStep(net_info, optimiser)
+    mod_info = training.MOD_INFO(np.ones(alphabet_info.nbase, dtype=np.float32), None) \
+        if cat_mod else None
+    step_fn = training.TrainStep(net_info, optimiser, mod_info=mod_info)
     nparam = sum(p.numel() for p in net.parameters() if p.requires_grad)
 
     # ---- synthetic batches through the reference's batching surface ----
-    reads = signal_mapping.synthetic_reads(48, seed=7 + rank)
+    reads = signal_mapping.synthetic_reads(48, seed=7 + rank, mod_fraction=0.5 if cat_mod else 0.0)
     fp = chunk_selection.sample_filter_parameters(reads, 200, T_SIG, 10.0, 10.0, 0.1, STRIDE, 1.1)
     nbatches = 4
     host_batches = list(training.prepare_random_batches(
@@ -191,14 +209,16 @@ def main():
     for indata, seqs, seqlens, mod_cats, nb, rej in host_batches:
         sl_dev = seqlens.to(device)
         ctc.hint_lengths(sl_dev, int(seqlens.max()), int(seqlens.sum()))
-        dev_batches.append((indata.to(device), seqs.to(device), sl_dev, None, nb, rej))
+        dev_batches.append((indata.to(device), seqs.to(device), sl_dev,
+                            None if mod_cats is None else mod_cats.to(device), nb, rej))
     h2d = int(sum(b[0].numel() * 4 + b[1].numel() * 8 + b[2].numel() * 8
                   for b in host_batches) / nbatches)
 
     def run(batches, steps, read_back):
         out = None
         for i in range(steps):
-            out = step_fn(iter([batches[i % len(batches)]]), sharpen=1.0, read_back=read_back)
+            out = step_fn(iter([batches[i % len(batches)]]), sharpen=1.0, mod_factor=1.0,
+                          read_back=read_back)
         return out
 
     def timed(batches, steps, read_back):
