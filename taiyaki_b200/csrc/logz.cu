@@ -61,7 +61,7 @@ __device__ __forceinline__ float max8(float v) {   // max over aligned groups of
     return v;
 }
 
-__global__ void __launch_bounds__(128) logz_chain_kernel(const LogzArgs a) {
+__global__ void __launch_bounds__(256) logz_chain_kernel(const LogzArgs a) {
     const int lane = threadIdx.x & 31;
     const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nchain = a.want_grad ? 2 * a.nbatch : a.nbatch;
@@ -212,7 +212,8 @@ extern "C" size_t ty_flipflop_logz_workspace_bytes(int nbase, int nblk, int nbat
 }
 
 // phases: bit 0 = lattice chains (logZ and, with grad_out, the stored vectors),
-//         bit 1 = posterior (gradient) from the stored vectors
+//         bit 1 = posterior (gradient) from the stored vectors,
+//         bit 2 = the chains run beside other latency-bound kernels: give them SMs of their own
 extern "C" int ty_flipflop_logz_phase(const float *scores, int ld, int nblk, int nbatch,
                                       int nbase, float logz_scale, float *logz_out,
                                       float grad_scale, float *grad_out, int ld_grad,
@@ -246,12 +247,26 @@ extern "C" int ty_flipflop_logz_phase(const float *scores, int ld, int nblk, int
     a.want_grad = want_grad;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int nchain = want_grad ? 2 * nbatch : nbatch;
-    // one chain (warp) per CTA spreads the latency-bound chains over the SMs
-    const int warps_per_cta = nchain <= 148 * 4 ? 1 : 4;
-    const int grid = (nchain + warps_per_cta - 1) / warps_per_cta;
     int rc = TY_OK;
     if (phases & 1) {
-        logz_chain_kernel<<<grid, 32 * warps_per_cta, 0, s>>>(a);
+        if (phases & 4) {
+            // Running beside the label-constrained chains (ty_flipflop_train_loss): 8 chains
+            // per CTA and a shared-memory reservation no other CTA fits next to, so these
+            // warps get SMs of their own instead of sharing a sub-partition with a DP warp
+            // of crf_chain_kernel (measured on the cat-mod shape: 2.04 -> see profiles).
+            static bool attr = false;
+            const int reserve = 200 * 1024;
+            if (!attr) {
+                cudaFuncSetAttribute(logz_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, reserve);
+                attr = true;
+            }
+            logz_chain_kernel<<<(nchain + 7) / 8, 256, reserve, s>>>(a);
+        } else {
+            // one chain (warp) per CTA spreads the latency-bound chains over the SMs
+            const int warps_per_cta = nchain <= 148 * 4 ? 1 : 4;
+            const int grid = (nchain + warps_per_cta - 1) / warps_per_cta;
+            logz_chain_kernel<<<grid, 32 * warps_per_cta, 0, s>>>(a);
+        }
         rc = check_launch("logz_chain_kernel");
     }
     if (rc || !want_grad || !(phases & 2)) return rc;
