@@ -42,8 +42,8 @@ sys.path.insert(0, ROOT)
 T_SIG, NCHUNK, SIZE, STRIDE, NTRANS = 4000, 64, 256, 5, 40
 METRIC = 'signal_samples_per_sec_flipflop_train_step'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the four loss kernels at this
-# workload, from one `ncu --set full` capture (profiles/r1_ncu_full_summary_v3.csv)
-NCU_TRAFFIC_BYTES = int((8.98 + 122.45 + 198.96 + 5.19 + 8.24 + 0.0 + 11.47 + 0.0) * 1e6)
+# workload, from one `ncu --set full` capture (profiles/r1_ncu_full_summary_v4.csv)
+NCU_TRAFFIC_BYTES = int((8.95 + 122.64 + 198.96 + 6.45 + 8.24 + 0.0 + 11.47 + 0.0) * 1e6)
 WORKLOAD = 'mLstm_flipflop size256 stride5, T_sig=4000 (nblk=800), 64 chunks/GPU, S=40'
 
 
@@ -274,7 +274,7 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': kname,
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': NCU_TRAFFIC_BYTES if key == 'loss_fwd_bwd' else None,
-                'traffic_source': 'profiles/r1_ncu_full_summary_v3.csv: dram read+write of crf_chain + '
+                'traffic_source': 'profiles/r1_ncu_full_summary_v4.csv: dram read+write of crf_chain + '
                                   'crf_post + logz_chain + logz_post, one launch each, config A',
                 'peak_source': peak_src, 'algorithmic_bytes': alg_bytes,
                 'avg_launch_ms': crf_avg, 'launches_timed': len(crf_ms),

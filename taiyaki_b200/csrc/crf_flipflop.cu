@@ -692,7 +692,7 @@ static void launch_chain(const CrfArgs &a, int max_seqlen, cudaStream_t s) {
     crf_chain_kernel<P, MOD><<<grid, threads, 0, s>>>(a);
 }
 
-int crf_pick_p(int max_seqlen);
+int crf_pick_p(int max_seqlen, bool mod);
 
 }  // namespace ty
 
@@ -704,15 +704,18 @@ extern "C" size_t ty_crf_flipflop_workspace_bytes(int ntrans, int nblk, int nbat
     return crf_layout(nblk, nbatch, max_seqlen, want_grad).total;
 }
 
-int ty::crf_pick_p(int max_seqlen) {
+int ty::crf_pick_p(int max_seqlen, bool mod) {
     // positions per thread: 4 keeps a 440-base chunk in four warps (one per
-    // SM sub-partition); longer chunks widen the thread block first.
+    // SM sub-partition); longer chunks widen the thread block first.  The cat-mod
+    // chain (three gathers per position) measures 7 % faster with 8 positions
+    // per thread and two DP warps (profiles/r1_microbench_v4.jsonl, tag B).
     const char *e = getenv("TY_CRF_P");   // tuning override, read per call
     const int forced = e ? atoi(e) : 0;
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) {
         const int cap = forced >= 8 ? 512 : 992;
         if ((max_seqlen + forced - 1) / forced <= cap) return forced;
     }
+    if (mod && max_seqlen <= 2048) return 8;
     if (max_seqlen <= 3968) return 4;
     if (max_seqlen <= 8191) return 16;
     return 0;
@@ -745,7 +748,7 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
         set_error("ty_crf_flipflop: workspace %zu < %zu bytes", workspace_bytes, w.total);
         return TY_EWORKSPACE;
     }
-    const int P = crf_pick_p(max_seqlen > 0 ? max_seqlen : 1);
+    const int P = crf_pick_p(max_seqlen > 0 ? max_seqlen : 1, modmoveidx != nullptr);
     if (P == 0) {
         set_error("ty_crf_flipflop: max_seqlen %d > 8191 unsupported", max_seqlen);
         return TY_EINVAL;
