@@ -481,7 +481,10 @@ __global__ void __launch_bounds__(P <= 4 ? 1024 : 544) crf_chain_kernel(const Cr
 // (c_crf_flipflop.c:401), so Z_t only has to be close.
 constexpr int kPostWarps = 8;
 
-template <bool MOD>
+// STAGED = false (chunks too long for the rows to fit in shared memory): the alpha /
+// beta rows are read where the chain kernel left them (L2 / HBM), only the entry lists
+// are staged -- slower per row, but no limit on the chunk length below the chain's own.
+template <bool MOD, bool STAGED>
 __global__ void __launch_bounds__(kPostWarps * 32) crf_post_kernel(const CrfArgs a) {
     extern __shared__ __align__(16) float dyn[];   // al[R][Ls], be[R][Ls+4], words[2Ls] (+ MOD extras)
     __shared__ float q[kPostWarps][kRowPad];       // w2 - Z_t (canonical), w2 (mod)
@@ -508,8 +511,8 @@ __global__ void __launch_bounds__(kPostWarps * 32) crf_post_kernel(const CrfArgs
 
     const int bes = Ls + 4;
     float *al = dyn;
-    float *be = al + (size_t)kPostWarps * Ls;
-    uint32_t *words = reinterpret_cast<uint32_t *>(be + (size_t)kPostWarps * bes);
+    float *be = al + (STAGED ? (size_t)kPostWarps * Ls : 0);
+    uint32_t *words = reinterpret_cast<uint32_t *>(be + (STAGED ? (size_t)kPostWarps * bes : 0));
     float *wmf = reinterpret_cast<float *>(words + 2 * Ls);        // MOD only
     uint32_t *words2 = reinterpret_cast<uint32_t *>(wmf + 2 * Ls); // MOD only
     float *wmf2 = reinterpret_cast<float *>(words2 + Ls);          // MOD only
@@ -517,14 +520,16 @@ __global__ void __launch_bounds__(kPostWarps * 32) crf_post_kernel(const CrfArgs
 
     // ---- stage: each warp its own row (float4, coalesced), all warps the entry lists ----
     if (r < nrow) {
-        const size_t g = ((size_t)b * a.nblk + t) * Ls;
-        const float4 *fa = reinterpret_cast<const float4 *>(a.fwd_ws + g);
-        const float4 *fbp = reinterpret_cast<const float4 *>(a.bwd_ws + g);
-        float4 *sa = reinterpret_cast<float4 *>(al + (size_t)r * Ls);
-        float4 *sb = reinterpret_cast<float4 *>(be + (size_t)r * bes);
-        for (int i = lane; i < (L + 3) / 4; i += 32) {
-            sa[i] = __ldcs(fa + i);
-            sb[i] = __ldcs(fbp + i);
+        if (STAGED) {
+            const size_t g = ((size_t)b * a.nblk + t) * Ls;
+            const float4 *fa = reinterpret_cast<const float4 *>(a.fwd_ws + g);
+            const float4 *fbp = reinterpret_cast<const float4 *>(a.bwd_ws + g);
+            float4 *sa = reinterpret_cast<float4 *>(al + (size_t)r * Ls);
+            float4 *sb = reinterpret_cast<float4 *>(be + (size_t)r * bes);
+            for (int i = lane; i < (L + 3) / 4; i += 32) {
+                sa[i] = __ldcs(fa + i);
+                sb[i] = __ldcs(fbp + i);
+            }
         }
         for (int s = lane; s < kRowPad; s += 32) {
             float v = 0.f;
@@ -554,8 +559,8 @@ __global__ void __launch_bounds__(kPostWarps * 32) crf_post_kernel(const CrfArgs
     __syncthreads();
     if (r >= nrow) return;
 
-    const float *ar = al + (size_t)r * Ls;
-    const float *br = be + (size_t)r * bes;
+    const float *ar = STAGED ? al + (size_t)r * Ls : a.fwd_ws + ((size_t)b * a.nblk + t) * Ls;
+    const float *br = STAGED ? be + (size_t)r * bes : a.bwd_ws + ((size_t)b * a.nblk + t) * Ls;
     const float *qr = q[r];
     float *binr = bins[r];
     {
@@ -794,24 +799,34 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
     int rc = check_launch("crf_chain_kernel");
     if (rc) return rc;
     if (want_grad) {
-        // one warp per row; alpha/beta rows + the chunk's entry lists in shared memory
-        size_t smem = (size_t)kPostWarps * (2 * (size_t)w.Ls + 4) * sizeof(float) +
-                      2 * (size_t)w.Ls * sizeof(uint32_t);
-        if (mod) smem += 2 * (size_t)w.Ls * sizeof(float) + (size_t)w.Ls * 8;
+        // one warp per row; alpha/beta rows + the chunk's entry lists in shared memory, or only
+        // the entry lists when the rows of a long chunk would not fit
+        size_t lists = 2 * (size_t)w.Ls * sizeof(uint32_t);
+        if (mod) lists += 2 * (size_t)w.Ls * sizeof(float) + (size_t)w.Ls * 8;
+        size_t smem = (size_t)kPostWarps * (2 * (size_t)w.Ls + 4) * sizeof(float) + lists;
+        const bool staged = smem <= 200 * 1024;
+        if (!staged) smem = lists;
         if (smem > 200 * 1024) {
             set_error("ty_crf_flipflop: max_seqlen %d needs %zu bytes of shared memory", max_seqlen, smem);
             return TY_EINVAL;
         }
         const dim3 grid((nblk + kPostWarps - 1) / kPostWarps, nbatch);
+#define TY_POST(M, ST)                                                                          \
+    do {                                                                                        \
+        static bool attr = false;                                                               \
+        if (!attr) {                                                                            \
+            cudaFuncSetAttribute(crf_post_kernel<M, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 200 * 1024);                                                   \
+            attr = true;                                                                        \
+        }                                                                                       \
+        crf_post_kernel<M, ST><<<grid, kPostWarps * 32, smem, s>>>(a);                           \
+    } while (0)
         if (mod) {
-            static bool attr = false;
-            if (!attr) { cudaFuncSetAttribute(crf_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-            crf_post_kernel<true><<<grid, kPostWarps * 32, smem, s>>>(a);
+            if (staged) TY_POST(true, true); else TY_POST(true, false);
         } else {
-            static bool attr = false;
-            if (!attr) { cudaFuncSetAttribute(crf_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-            crf_post_kernel<false><<<grid, kPostWarps * 32, smem, s>>>(a);
+            if (staged) TY_POST(false, true); else TY_POST(false, false);
         }
+#undef TY_POST
         rc = check_launch("crf_post_kernel");
     }
     return rc;

@@ -177,12 +177,14 @@ def test_live_oracle_parity(dev, oracle, nblk, nbatch, lengths):
 
 
 def test_very_long_chunk_against_fp64(dev, oracle):
-    """3000 blocks x 2600 positions (21 DP warps per chain): fp32 round-off of the
-    recursion itself is visible at this length -- the reference's own fp32 C is
-    1e-3 relative away from fp64 on the small posterior entries -- so the check
-    is against fp64 with a floor of 3e-4 of a row's mass, and the kernel must not
-    be further from fp64 than three times the reference C is."""
-    nblk, nbatch, lengths = 3000, 2, [2600, 150]
+    """3400 blocks x 3100 positions (25 DP warps per chain; the posterior reads
+    the alpha / beta rows from global memory because they no longer fit in
+    shared memory): fp32 round-off of the recursion itself is visible at this
+    length -- the reference's own fp32 C is 1e-3 relative away from fp64 on the
+    small posterior entries -- so the check is against fp64 with a floor of 2e-3
+    of a row's mass, and the kernel must not be further from fp64 than three
+    times the reference C is."""
+    nblk, nbatch, lengths = 3400, 2, [3100, 150]
     scores = oracle.synth_scores(nblk, nbatch, 40, seed=nblk)
     seqs, seqlen, _ = oracle.synth_seqs(nblk, nbatch, seed=nblk + 1, lengths=lengths)
     c64, g64 = oracle.crf_flipflop_loss(scores, seqs, seqlen, 1.0, impl='f64')
@@ -190,7 +192,7 @@ def test_very_long_chunk_against_fp64(dev, oracle):
     c32, g32 = oracle.crf_flipflop_loss(scores, seqs, seqlen, 1.0, impl=impl)
     cost, grad = gpu_crf(dev, scores, seqs, seqlen, 1.0)
     np.testing.assert_allclose(cost, c64, rtol=RTOL, atol=1e-6)
-    np.testing.assert_allclose(grad, g64, rtol=RTOL, atol=3e-4 / nblk)
+    np.testing.assert_allclose(grad, g64, rtol=RTOL, atol=2e-3 / nblk)
     np.testing.assert_allclose(grad.sum(2), -1.0 / nblk, rtol=1e-5)      # rows are posteriors / nblk
     ours, theirs = np.abs(grad - g64).max(), np.abs(g32 - g64).max()
     assert ours <= 3 * theirs + 1e-9, (ours, theirs)
