@@ -36,6 +36,20 @@ def flipflop_code(labels, alphabet_length=4):
     return x
 
 
+def flipflop_code_batch(labels, starts, alphabet_length=4):
+    """`flipflop_code` of several concatenated label sequences in one pass;
+    `starts` are the offsets of the sequences (a homopolymer run never crosses one)."""
+    labels = np.asarray(labels)
+    if labels.size == 0:
+        return labels.astype(np.int64)
+    move = np.ediff1d(labels, to_begin=1) != 0
+    move[np.asarray(starts, dtype=np.int64)] = True
+    cumulative_flipflops = (1 - move).cumsum()
+    offsets = np.maximum.accumulate(move * cumulative_flipflops)
+    flop = (cumulative_flipflops - offsets) % 2 == 1
+    return (labels + alphabet_length * flop).astype(np.int64)
+
+
 def nstate_flipflop(nbase):
     """Number of transitions 2L(L+1) (flipflopfings.py:146-168)."""
     return 2 * nbase * (nbase + 1)

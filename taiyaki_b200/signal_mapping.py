@@ -88,11 +88,15 @@ class SignalMapping:
         return len(self.Reference)
 
     def get_mapped_dacs_region(self):
-        valid = self.Ref_to_signal[np.logical_and(self.Ref_to_signal >= 0,
-                                                  self.Ref_to_signal <= self.siglen)]
-        if len(valid) == 0:
-            return 0, 0
-        return valid[0], valid[-1]
+        """(first, last) mapped sample (signal_mapping.py:208-225); cached: the arrays of a
+        read do not change while it is being sampled from."""
+        region = getattr(self, '_mapped_region', None)
+        if region is None:
+            valid = self.Ref_to_signal[np.logical_and(self.Ref_to_signal >= 0,
+                                                      self.Ref_to_signal <= self.siglen)]
+            region = (0, 0) if len(valid) == 0 else (int(valid[0]), int(valid[-1]))
+            self._mapped_region = region
+        return region
 
     def get_reference_locations(self, signal_location_vector):
         if isinstance(signal_location_vector, tuple):

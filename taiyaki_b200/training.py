@@ -62,24 +62,26 @@ def prepare_random_batches(read_data, batch_chunk_len, sub_batch_size, target_su
                 len(chunk_batch), sub_batch_size))
         if not all(chunk.seq_len > 0.0 for chunk in chunk_batch):
             raise Exception('Error: zero length sequence')
-        stacked_current = np.vstack([revop(chunk.current) for chunk in chunk_batch]).T
-        indata = torch.tensor(stacked_current, device='cpu', dtype=torch.float32).unsqueeze(2)
+        # [T, N] float32, filled column by column (torch.tensor() of a transposed float64
+        # stack, as the reference builds it, costs ~50 ms for 64 x 4000 samples)
+        stacked_current = np.empty((len(chunk_batch[0].current), len(chunk_batch)), dtype=np.float32)
+        for i, chunk in enumerate(chunk_batch):
+            stacked_current[:, i] = revop(chunk.current)
+        indata = torch.from_numpy(stacked_current).unsqueeze(2)
         if pin and torch.cuda.is_available():
             indata = indata.pin_memory()
-        seqs, seqlens = [], []
-        mod_cats = [] if net_info.metadata.is_cat_mod else None
-        for chunk in chunk_batch:
-            chunk_labels = revop(chunk.sequence)
-            seqlens.append(len(chunk_labels))
-            if net_info.metadata.is_cat_mod:
-                mod_cats.append(np.ascontiguousarray(net_info.metadata.mod_labels[chunk_labels]))
-                chunk_labels = np.ascontiguousarray(net_info.metadata.can_labels[chunk_labels])
-            seqs.append(flipflopfings.flipflop_code(
-                np.ascontiguousarray(chunk_labels).astype(np.int64), alphabet_info.ncan_base))
-        seqs = torch.tensor(np.concatenate(seqs), dtype=torch.long, device='cpu')
-        seqlens = torch.tensor(seqlens, dtype=torch.long, device='cpu')
+        seqlens = [len(chunk.sequence) for chunk in chunk_batch]
+        labels = np.concatenate([revop(chunk.sequence) for chunk in chunk_batch]).astype(np.int64)
+        mod_cats = None
         if net_info.metadata.is_cat_mod:
-            mod_cats = torch.tensor(np.concatenate(mod_cats), dtype=torch.long, device='cpu')
+            mod_cats = torch.from_numpy(np.ascontiguousarray(
+                net_info.metadata.mod_labels[labels]).astype(np.int64))
+            labels = np.ascontiguousarray(net_info.metadata.can_labels[labels]).astype(np.int64)
+        # flip-flop coding of all chunks at once: runs cannot cross a chunk boundary
+        starts = np.cumsum([0] + seqlens[:-1])
+        seqs = torch.from_numpy(flipflopfings.flipflop_code_batch(
+            labels, starts, alphabet_info.ncan_base))
+        seqlens = torch.tensor(seqlens, dtype=torch.long, device='cpu')
         total_sub_batches += 1
         yield indata, seqs, seqlens, mod_cats, len(chunk_batch), batch_rejections
 
