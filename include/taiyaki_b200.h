@@ -244,6 +244,32 @@ int ty_conv_small_backward(const float *da, const float *z, const float *x,
                            int pad_left, int act, float *dz, float *dW, float *db,
                            float *dx, void *stream);
 
+/* ----------------------------------------------------------------------
+ * Training-batch assembly on the device (taiyaki/chunk_selection.py:29-95,
+ * signal_mapping.py:459-554 and :680-716, bin/train_flipflop.py:101-135) for
+ * reads resident in HBM: concatenated DACs (int16), Ref_to_signal (int32,
+ * reflen + 1 entries per read) and Reference (int16) with int64 offset arrays
+ * of R + 1 entries, lin [R][2] with current = dacs * lin[r][0] + lin[r][1].
+ * The caller draws M candidate (read, first sample) pairs in attempt order
+ * (first sample < 0: read shorter than the chunk); the first N that pass the
+ * filters fill the batch.  filters_host: HOST pointer to {filter_mean_dwell,
+ * filter_max_dwell, median_meandwell, mad_meandwell, path_buffer} or NULL.
+ * Outputs (device): indata [T][N] fp32 (time reversed if reverse != 0), seqs
+ * (flip-flop coded, concatenated in slot order) and optionally mod_cats (with
+ * the two label tables of a cat-mod model), seqlen [N], seqoff [N + 1], counts
+ * [ty_batch_counts_len()] = per-reason attempt counts (pass, emptysequence,
+ * emptysignal, tooshort, nullmapping, pathbuffer, meandwell, maxdwell),
+ * accepted, attempts.  scratch: 3 M + N int32. */
+int ty_batch_counts_len(void);
+int ty_sample_chunks(const int16_t *dacs, const int64_t *dacs_off, const int32_t *r2s,
+                     const int64_t *r2s_off, const int16_t *ref, const int64_t *ref_off,
+                     const float *lin, const int32_t *cand_read,
+                     const int32_t *cand_start, int M, int N, int T,
+                     const float *filters_host, int model_stride, int reverse, int nbase,
+                     const int32_t *can_labels, const int32_t *mod_labels,
+                     float *indata, int64_t *seqs, int64_t *mod_cats, int64_t *seqlen,
+                     int64_t *seqoff, int32_t *counts, int32_t *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
