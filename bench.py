@@ -280,7 +280,28 @@ def main():
                 'avg_launch_ms': crf_avg, 'launches_timed': len(crf_ms),
                 'share_of_step': crf_avg / (ms_dev / K),
                 'note': 'latency-bound sequential DP (nblk dependent steps); see DESIGN.md 4.1'}
-    extra = {'rnn_fwd_kernel_ms_avg': float(np.mean(rnn_ms)) if rnn_ms else None,
+    # ---- batch assembly (outside the timed legs): host numpy path vs device kernels ----
+    batching = None
+    if rank == 0:
+        from taiyaki_b200 import device_batching
+        t0 = time.time()
+        nb = len(list(training.prepare_random_batches(reads, T_SIG, NCHUNK, 5, alphabet_info, fp,
+                                                      net_info, None)))
+        host_ms = (time.time() - t0) * 1e3 / nb
+        store = device_batching.DeviceReadStore(reads, device)
+        list(device_batching.prepare_random_batches(store, T_SIG, NCHUNK, 2, alphabet_info, fp,
+                                                    net_info, None))
+        torch.cuda.synchronize()
+        t0 = time.time()
+        nb = len(list(device_batching.prepare_random_batches(store, T_SIG, NCHUNK, 10,
+                                                             alphabet_info, fp, net_info, None)))
+        torch.cuda.synchronize()
+        batching = {'host_ms_per_batch': host_ms,
+                    'device_ms_per_batch': (time.time() - t0) * 1e3 / nb,
+                    'note': 'batch assembly (chunk sampling, filters, stacking, flip-flop coding) '
+                            'for one step; not inside the timed legs'}
+    extra = {'batching': batching,
+             'rnn_fwd_kernel_ms_avg': float(np.mean(rnn_ms)) if rnn_ms else None,
              'rnn_bwd_kernel_ms_avg': float(np.mean(rnnb_ms)) if rnnb_ms else None,
              'rnn_layers': 5, 'trainable_params': nparam, 'loss': loss}
 

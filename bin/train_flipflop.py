@@ -31,8 +31,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from taiyaki_b200 import (chunk_selection, helpers, layers, maths, signal_mapping,  # noqa: E402
-                          training)
+from taiyaki_b200 import (chunk_selection, device_batching, helpers, layers, maths,  # noqa: E402
+                          signal_mapping, training)
 from taiyaki_b200.alphabet import AlphabetInfo  # noqa: E402
 
 DOTROWLENGTH = 50
@@ -50,7 +50,7 @@ RESOURCE_INFO = namedtuple('RESOURCE_INFO', ('is_multi_gpu', 'is_lead_process', 
 OPTIM_INFO = namedtuple('OPTIM_INFO', ('optimiser', 'lr_warmup', 'lr_scheduler', 'rolling_mads'))
 TRAIN_PARAMS = namedtuple('TRAIN_PARAMS', (
     'niteration', 'sharpen', 'chunk_len_min', 'chunk_len_max', 'min_sub_batch_size',
-    'sub_batches', 'save_every', 'outdir', 'full_filter_status'))
+    'sub_batches', 'save_every', 'outdir', 'full_filter_status', 'host_batching'))
 SHARPEN = namedtuple('SHARPEN', ('min', 'max', 'niter'))
 MOD_FACTOR = namedtuple('MOD_FACTOR', ('start', 'final', 'niter'))
 LOGS = namedtuple('LOGS', ('main', 'batch', 'validation'))
@@ -109,6 +109,9 @@ def get_train_flipflop_parser():
     g.add_argument('--overwrite', default=False, action='store_true')
     g.add_argument('--quiet', default=False, action='store_true')
     g.add_argument('--save_every', type=int, default=2500)
+    g.add_argument('--host_batching', default=False, action='store_true',
+                   help='Assemble training batches with the numpy path of the reference '
+                        'instead of on the device (taiyaki_b200.device_batching)')
     g = p.add_argument_group('Modified Base Arguments')
     g.add_argument('--mod_factor', default=(8.0, 1.0, 50000), nargs=3, type=float,
                    metavar=('start', 'final', 'niter'))
@@ -331,6 +334,12 @@ def train_model(train_params, net_info, optim_info, res_info, read_data, alphabe
     """The hot loop, train_flipflop.py:532-627."""
     step = training.TrainStep(net_info, optim_info.optimiser, optim_info.rolling_mads,
                               mod_info=mod_info)
+    # reads resident in HBM: batches are assembled by three kernel launches instead of
+    # ~7 ms of single-threaded numpy per batch (the step itself takes ~6.5 ms)
+    store = None
+    device = next(net_info.net.parameters()).device
+    if device.type == 'cuda' and not train_params.host_batching:
+        store = device_batching.DeviceReadStore(read_data, device)
     score_smoothed = helpers.WindowedExpSmoother()
     total_bases = total_samples = 0
     rejection_dict = defaultdict(int)
@@ -348,9 +357,14 @@ def train_model(train_params, net_info, optim_info, res_info, read_data, alphabe
                            net_info.stride) * net_info.stride
         sub_batch_size = int(train_params.min_sub_batch_size * train_params.chunk_len_max /
                              batch_chunk_len + 0.5)
-        main_batch_gen = training.prepare_random_batches(
-            read_data, batch_chunk_len, sub_batch_size, train_params.sub_batches, alphabet_info,
-            filter_params, net_info, logs.main)
+        if store is not None:
+            main_batch_gen = device_batching.prepare_random_batches(
+                store, batch_chunk_len, sub_batch_size, train_params.sub_batches, alphabet_info,
+                filter_params, net_info, logs.main)
+        else:
+            main_batch_gen = training.prepare_random_batches(
+                read_data, batch_chunk_len, sub_batch_size, train_params.sub_batches,
+                alphabet_info, filter_params, net_info, logs.main)
         (chunk_count, _, chunk_samples, chunk_bases, batch_rejections), fval, grad_maxs = step(
             main_batch_gen, sharpen, mod_factor, read_back=True)
         assert np.isfinite(fval), (
@@ -395,7 +409,8 @@ def main(args):
                                                   filter_params, net_info, logs.main)
     train_params = TRAIN_PARAMS(args.niteration, SHARPEN(*args.sharpen), args.chunk_len_min,
                                 args.chunk_len_max, args.min_sub_batch_size, args.sub_batches,
-                                args.save_every, args.outdir, args.full_filter_status)
+                                args.save_every, args.outdir, args.full_filter_status,
+                                args.host_batching)
     train_model(train_params, net_info, optim_info, res_info, read_data, alphabet_info,
                 filter_params, mod_info, reporting_batch_list, logs)
     if res_info.is_multi_gpu:
