@@ -270,6 +270,14 @@ int ty_sample_chunks(const int16_t *dacs, const int64_t *dacs_off, const int32_t
                      float *indata, int64_t *seqs, int64_t *mod_cats, int64_t *seqlen,
                      int64_t *seqoff, int32_t *counts, int32_t *scratch, void *stream);
 
+/* Best path over the flip-flop lattice (taiyaki/decode.py:79-115,
+ * cupy_extensions/flipflop.py:387-518): scores [T][N][S] fp32 -> fwd
+ * [T+1][N][2 nbase] max-scores (flip states start at 0, flop states at -1e30),
+ * traceback [T][N][2 nbase] int64 (best predecessor state, lowest index on a
+ * tie), path [T+1][N] int64.  nbase == 4. */
+int ty_flipflop_viterbi(const float *scores, int T, int N, int nbase, float *fwd,
+                        int64_t *traceback, int64_t *path, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,8 @@ _SIGNATURES = {
     'ty_conv_small_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
+    'ty_flipflop_viterbi': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     'ty_batch_counts_len': (c_int, []),
     'ty_sample_chunks': (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_void_p] + [c_int] * 3 +
                          [c_void_p] * 10),

@@ -234,5 +234,28 @@ def main():
     print('cat-mod tables:', cm_names)
 
 
+def make_decode():
+    """Viterbi paths and posterior transition probabilities of the reference's own
+    PyTorch implementations (taiyaki/decode.py:_flipflop_viterbi, flipflop_make_trans
+    with _never_use_cupy=True) on seeded random scores -> tests/golden/decode.npz."""
+    from taiyaki import decode as ref_decode
+    out = {}
+    for tag, (T, N, seed, scale) in {'a': (50, 3, 11, 1.0), 'b': (200, 3, 12, 5.0),
+                                     'c': (1, 2, 13, 1.0)}.items():
+        g = torch.Generator().manual_seed(seed)
+        scores = scale * torch.randn(T, N, 40, generator=g)
+        fwd, tb, path = ref_decode._flipflop_viterbi(scores)
+        trans = ref_decode.flipflop_make_trans(scores, _never_use_cupy=True)
+        out[tag + '_scores'] = scores.numpy()
+        out[tag + '_fwd'] = fwd.numpy()
+        out[tag + '_tb'] = tb.numpy().astype(np.int8)
+        out[tag + '_path'] = path.numpy().astype(np.int8)
+        out[tag + '_trans'] = trans.numpy()
+    np.savez_compressed(os.path.join(HERE, 'decode.npz'), **out)
+    print('decode.npz', {k: v.shape for k, v in out.items() if k.startswith('b_')})
+
+
 if __name__ == '__main__':
-    main()
+    if sys.argv[1:] != ['decode']:      # `make_golden.py decode` regenerates decode.npz only
+        main()
+    make_decode()
