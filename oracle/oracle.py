@@ -318,6 +318,31 @@ def flipflop_logpartition(scores, want_grad=False, impl='f32'):
 # --------------------------------------------------------------------------
 # synthetic inputs shared by tests and bench
 # --------------------------------------------------------------------------
+def flipflop_viterbi(scores):
+    """Best flip-flop path, numpy restatement of taiyaki/decode.py:79-115
+    (_flipflop_viterbi): fwd [T+1,N,2nb] (flip states 0, flop states -1e30), traceback
+    [T,N,2nb] (best predecessor, first maximum), path [T+1,N]."""
+    scores = np.asarray(scores, dtype=np.float32)
+    T, N, S = scores.shape
+    nb = nbase_flipflop(S)
+    fwd = np.zeros((T + 1, N, 2 * nb), dtype=np.float32)
+    fwd[0, :, nb:] = -1e30                       # constants.py:8 LARGE_VAL
+    tb = np.zeros((T, N, 2 * nb), dtype=np.int64)
+    for t in range(T):
+        to_flip = scores[t, :, :S - 2 * nb].reshape(N, nb, 2 * nb)
+        cand = fwd[t][:, None, :] + to_flip      # decode.py:104-106
+        fwd[t + 1, :, :nb] = cand.max(2)
+        tb[t, :, :nb] = cand.argmax(2)
+        flop = (fwd[t] + scores[t, :, -2 * nb:]).reshape(N, 2, nb)     # decode.py:107-110
+        fwd[t + 1, :, nb:] = flop.max(1)
+        tb[t, :, nb:] = nb * flop.argmax(1) + np.arange(nb)
+    path = np.zeros((T + 1, N), dtype=np.int64)
+    path[T] = fwd[T].argmax(1)
+    for t in range(T - 1, -1, -1):               # decode.py:114-116
+        path[t] = tb[t, np.arange(N), path[t + 1]]
+    return fwd, tb, path
+
+
 def synth_scores(nblk, nbatch, ntrans=40, seed=0, can_nmods=None):
     """5*tanh(N(0,1)) transition scores; for cat-mod (ntrans > 40) the extra
     columns are per-canonical-base log-softmax groups (layers.py:1611-1640)."""

@@ -159,3 +159,18 @@ def test_restatement_vs_reference_c_live(oracle):
     b = oracle.crf_flipflop_loss(2 * scores, seqs, seqlen, 1.0, want_grad=False, impl='ref')
     np.testing.assert_allclose(a, b / 2, rtol=1e-6)
     assert np.all(g_ref <= 0)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_decode_golden_vs_restatement(oracle, tag):
+    """tests/golden/decode.npz (the reference's PyTorch Viterbi and make_trans) against the
+    numpy Viterbi restatement and the C partition-function gradient."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'decode.npz'))
+    scores = g[tag + '_scores']
+    fwd, tb, path = oracle.flipflop_viterbi(scores)
+    np.testing.assert_array_equal(path, g[tag + '_path'])
+    np.testing.assert_array_equal(tb, g[tag + '_tb'])
+    np.testing.assert_allclose(fwd, g[tag + '_fwd'], rtol=1e-6, atol=1e-5)
+    _, trans = oracle.c_flipflop_logz(np.ascontiguousarray(scores), want_grad=True, impl='f64')
+    np.testing.assert_allclose(trans, g[tag + '_trans'], rtol=2e-4, atol=2e-6)
