@@ -300,7 +300,23 @@ def main():
                     'device_ms_per_batch': (time.time() - t0) * 1e3 / nb,
                     'note': 'batch assembly (chunk sampling, filters, stacking, flip-flop coding) '
                             'for one step; not inside the timed legs'}
-    extra = {'batching': batching,
+    # the recurrent kernels are the only tensor-core work of the path: achieved
+    # TFLOP/s of the per-step products against the sustained bf16 peak, for context
+    rnn_tensor = None
+    if rnn_ms and rnnb_ms and args.model == 'mLstm_flipflop':
+        try:
+            tpeak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops_sustained'])
+            tsrc = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        except Exception:
+            tpeak, tsrc = 1377.0, 'fallback (SURVEY 8d)'
+        flops = 2.0 * nblk * NCHUNK * 4 * SIZE * SIZE          # W_hh h per layer and direction
+        rnn_tensor = {
+            'bound': 'tensor (latency-bound recurrence: nblk dependent steps, DESIGN.md 4.5)',
+            'fwd_tflops': flops / (np.mean(rnn_ms) * 1e-3) / 1e12,
+            'bwd_tflops': flops / (np.mean(rnnb_ms) * 1e-3) / 1e12,
+            'peak_tflops': tpeak, 'peak_source': tsrc,
+            'frac_fwd': flops / (np.mean(rnn_ms) * 1e-3) / 1e12 / tpeak}
+    extra = {'batching': batching, 'rnn_tensor': rnn_tensor,
              'rnn_fwd_kernel_ms_avg': float(np.mean(rnn_ms)) if rnn_ms else None,
              'rnn_bwd_kernel_ms_avg': float(np.mean(rnnb_ms)) if rnnb_ms else None,
              'rnn_layers': 5, 'trainable_params': nparam, 'loss': loss}
