@@ -120,7 +120,7 @@ def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the train step on this box's
     host cores, bounded sample of the same workload."""
     if rank != 0:
-        return
+        return None
     from oracle import oracle, ref_train_step
     oracle.build()
     steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
@@ -139,17 +139,44 @@ def reference_arm(args, rank, world):
         'e2e': {'value': r['samples_per_s'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
+    return line
+
+
+class QuietStdout:
+    """stdout carries exactly ONE JSON line: while the work runs, file descriptor 1 points
+    at stderr, so C-level chatter (NCCL's version banner, library warnings) lands there."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def emit(line):
     print(json.dumps(line))
+    sys.stdout.flush()
 
 
 def main():
+    with QuietStdout():
+        line = run_arm()
+    if line is not None:
+        emit(line)
+
+
+def run_arm():
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        reference_arm(args, rank, world)
-        return
+        return reference_arm(args, rank, world)
 
     import torch
     import torch.distributed as dist
@@ -324,7 +351,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -358,9 +385,10 @@ def main():
         'cpu_baseline': cpu_baseline,
         'detail': extra,
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line
+
 
 
 if __name__ == '__main__':
