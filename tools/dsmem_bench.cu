@@ -198,8 +198,86 @@ static int run(const char *name, int clusters, int rounds, int spin) {
     return 0;
 }
 
+// Two-phase reception: every sender serves its peers in rotated order (rank+1, rank+2, ...,
+// itself last), the first four through barrier A of the receiver, the last four through
+// barrier B.  If the sender's egress is what spreads the arrivals, A completes early and the
+// receiver can start on that half while B is still in flight.  TWO = false: same rotated
+// order, one barrier, all the work after it.
+template <int CL, bool TWO>
+__global__ void __launch_bounds__(128, 1) xchg2(int rounds, int work, unsigned *sink, long long *cycles) {
+    __shared__ __align__(128) unsigned char buf[2][CL * 512];
+    __shared__ __align__(8) uint64_t fullA[2], fullB[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = ctarank();
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(&fullA[i], 1); mbar_init(&fullB[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();
+    const uint32_t b_base = smem_u32(&buf[0][0]);
+    const uint32_t barA = smem_u32(&fullA[0]), barB = smem_u32(&fullB[0]);
+    uint32_t phase = 0, acc = tid;
+    const long long t0 = clock64();
+    for (int s = 0; s < rounds; s++) {
+        const int cur = s & 1, nxt = cur ^ 1;
+        if (tid == 0 && s + 1 < rounds) {
+            if (TWO) { expect_tx(&fullA[nxt], CL / 2 * 512); expect_tx(&fullB[nxt], CL / 2 * 512); }
+            else expect_tx(&fullA[nxt], CL * 512);
+        }
+        if (s > 0) {
+            mbar_wait(&fullA[cur], (phase >> cur) & 1u);
+            acc += *reinterpret_cast<volatile uint32_t *>(&buf[cur][(tid * 4) % (CL * 512)]);
+            if (TWO) {
+                for (int i = 0; i < work / 2; i++) acc = acc * 1664525u + 1013904223u;
+                mbar_wait(&fullB[cur], (phase >> cur) & 1u);
+                acc += *reinterpret_cast<volatile uint32_t *>(&buf[cur][(tid * 4 + 2048) % (CL * 512)]);
+                for (int i = 0; i < work / 2; i++) acc = acc * 1664525u + 1013904223u;
+            } else {
+                for (int i = 0; i < work; i++) acc = acc * 1664525u + 1013904223u;
+            }
+            phase ^= 1u << cur;
+        }
+        if (s + 1 < rounds) {
+            const uint32_t off = rank * 512 + warp * 128 + lane * 4;
+            const uint32_t dst0 = b_base + nxt * (CL * 512) + off;
+#pragma unroll
+            for (uint32_t p = 0; p < CL; p++) {
+                const uint32_t peer = (rank + 1 + p) & (CL - 1);
+                const uint32_t bar = ((TWO && p >= CL / 2) ? barB : barA) + nxt * 8;
+                st_async_b32(mapa(dst0, peer), acc, mapa(bar, peer));
+            }
+        }
+    }
+    const long long t1 = clock64();
+    if (tid == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+    if (acc == 0x12345678u) *sink = acc;
+    cluster_sync_all();
+}
+
+template <int CL, bool TWO>
+static int run2(const char *name, int clusters, int rounds, int work) {
+    unsigned *sink; long long *cyc;
+    CK(cudaMalloc(&sink, 4)); CK(cudaMalloc(&cyc, 8));
+    auto k = xchg2<CL, TWO>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(128);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    for (int it = 0; it < 3; it++) { CK(cudaLaunchKernelEx(&cfg, k, rounds, work, sink, cyc)); CK(cudaDeviceSynchronize()); }
+    long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("CL=%2d clusters=%d work=%4d %-40s %7.1f cycles/round\n", CL, clusters, work, name, (double)c / rounds);
+    cudaFree(sink); cudaFree(cyc);
+    return 0;
+}
+
 int main() {
     const int R = 4000;
+    for (int work : {0, 60, 120}) {
+        run2<8, false>("rotated order, one barrier", 8, R, work);
+        run2<8, true>("rotated order, two-phase reception", 8, R, work);
+    }
     for (int spin : {0}) {
         for (int clusters : {8}) {
             run<8, 0>("b32 rows (as LSTM kernel)", clusters, R, spin);
