@@ -25,6 +25,20 @@ for _ in range(reps):
         ctc.crf_flipflop_cost_grad(scores, torch.tensor(seqs), torch.tensor(seqlen), 1.0, True)
     if 'logz' in which:
         layers.flipflop_logpartition(scores.detach().requires_grad_(True))
+    if 'aux' in which:      # batching, decode and convolution kernels
+        from taiyaki_b200 import chunk_selection, decode, device_batching, signal_mapping, training
+        from taiyaki_b200.activation import swish
+        reads = signal_mapping.synthetic_reads(24, seed=7)
+        fp = chunk_selection.sample_filter_parameters(reads, 100, 4000, 10.0, 10.0, 0.1, 5, 1.1)
+        store = device_batching.DeviceReadStore(reads, dev)
+        md = training.NETWORK_METADATA(False, True, False)
+        store.sample(64, 4000, fp, md, 4)
+        decode.flipflop_viterbi(scores)
+        decode.flipflop_make_trans(scores)
+        net = layers.Serial([layers.Convolution(1, 4, 5, fun=swish), layers.Convolution(4, 16, 5, fun=swish),
+                             layers.Convolution(16, 256, 19, stride=5, fun=swish)]).to(dev)
+        xin = torch.randn(4000, N, 1, device=dev, requires_grad=True)
+        net(xin).sum().backward()
     if 'gru' in which:
         torch.manual_seed(0)
         np.random.seed(0)
