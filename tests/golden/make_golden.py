@@ -255,7 +255,104 @@ def make_decode():
     print('decode.npz', {k: v.shape for k, v in out.items() if k.startswith('b_')})
 
 
+def make_basecall():
+    """Chunking / stitching / quality strings / path -> bases of the reference's own
+    Python (taiyaki/basecall_helpers.py, qscores.py, flipflopfings.path_to_str) and the
+    post-network flow of bin/basecall.py:216-243 (process_read after the model call)
+    on seeded inputs -> tests/golden/basecall.npz.
+
+    Two shims, neither touching the arithmetic: `taiyaki.helpers` cannot be imported
+    under Python 3.12 (`import imp`), so a stub module with the two names
+    basecall_helpers imports is registered first; `qscores.qchar_from_qscore` calls
+    ndarray.tostring(), removed in numpy 2 -- it is replaced by the same expression
+    with tobytes()."""
+    import types
+    stub = types.ModuleType('taiyaki.helpers')
+    stub.get_model_device = stub.guess_model_stride = None
+    sys.modules.setdefault('taiyaki.helpers', stub)
+    from taiyaki import basecall_helpers as ref_bh
+    from taiyaki import decode as ref_decode
+    from taiyaki import qscores as ref_q
+
+    def qchar_from_qscore(score, zerochar=33):
+        asciicodes = (np.array(score) + zerochar + 0.5).astype(np.int8)
+        return asciicodes.tobytes().decode('ascii')
+    ref_q.qchar_from_qscore = qchar_from_qscore
+
+    out = {}
+    rng = np.random.RandomState(21)
+    cases = {'a': (10000, 1000, 100, 5), 'b': (1000, 1000, 100, 5), 'c': (999, 1000, 100, 5),
+             'd': (2345, 500, 0, 2), 'e': (5003, 1000, 500, 5), 'f': (1001, 1000, 100, 2),
+             'g': (7777, 800, 700, 4)}
+    for tag, (nsample, chunk_size, overlap, stride) in cases.items():
+        signal = rng.standard_normal(nsample).astype('f4')
+        chunks, cs, ce = ref_bh.chunk_read(signal, chunk_size, overlap)
+        out[tag + '_cfg'] = np.array([nsample, chunk_size, overlap, stride])
+        out[tag + '_signal'] = signal
+        out[tag + '_chunks'] = chunks
+        out[tag + '_starts'] = cs
+        out[tag + '_ends'] = ce
+        T = chunks.shape[0] // stride
+        net_out = torch.tensor(rng.standard_normal((T, chunks.shape[1], 3)).astype('f4'))
+        path = torch.tensor(rng.randint(0, 8, size=(T + 1, chunks.shape[1])))
+        out[tag + '_out'] = net_out.numpy()
+        out[tag + '_path'] = path.numpy().astype(np.int8)
+        out[tag + '_stitched'] = ref_bh.stitch_chunks(net_out, cs, ce, stride).numpy()
+        out[tag + '_stitched_path'] = ref_bh.stitch_chunks(path, cs, ce, stride).numpy().astype(np.int8)
+        out[tag + '_stitched_path_ps'] = ref_bh.stitch_chunks(
+            path, cs, ce, stride, path_stitching=True).numpy().astype(np.int8)
+
+    # post-network flow of process_read: scores of the chunks of a 9000-sample read
+    stride, chunk_size, overlap, nsample = 5, 1000, 100, 9000
+    _, cs, ce = ref_bh.chunk_read(np.zeros(nsample, dtype='f4'), chunk_size, overlap)
+    g = torch.Generator().manual_seed(31)
+    scores = 3.0 * torch.randn(chunk_size // stride, len(cs), 40, generator=g)
+    out['flow_scores'] = scores.numpy()
+    out['flow_starts'], out['flow_ends'] = cs, ce
+    out['flow_cfg'] = np.array([nsample, chunk_size, overlap, stride])
+    for tag, posterior, temperature in (('post', True, 1.0), ('raw', False, 1.0), ('temp', True, 0.5)):
+        trans = scores * temperature
+        if posterior:
+            trans = (ref_decode.flipflop_make_trans(trans, _never_use_cupy=True) + 1e-8).log()
+        _, _, chunk_best_paths = ref_decode._flipflop_viterbi(trans)
+        best_path = ref_bh.stitch_chunks(chunk_best_paths, cs, ce, stride).numpy()
+        basecall = ref_fff.path_to_str(best_path, alphabet='ACGT', include_first_source=False)
+        if posterior:
+            # process_read hands the LOG posterior weights to errprobs_from_trans
+            # (bin/basecall.py:216-217, 231-232); without --posterior the raw scores give
+            # negative "probabilities" and NaN quality values, so no vector is kept for that
+            chunk_errprobs = ref_q.errprobs_from_trans(trans, chunk_best_paths)
+            errprobs = ref_bh.stitch_chunks(chunk_errprobs, cs, ce, stride)
+            assert bool(((errprobs[1:] > 0) & (errprobs[1:] < 1)).all())
+            qstring = ref_q.path_errprobs_to_qstring(errprobs, best_path, 1.0, 0.0)
+            assert len(basecall) == len(qstring)
+            out['flow_%s_errprobs' % tag] = errprobs.numpy()
+            out['flow_%s_qstring' % tag] = np.array(qstring)
+        if tag == 'post':
+            out['flow_post_trans'] = trans.numpy()
+        out['flow_%s_chunk_paths' % tag] = chunk_best_paths.numpy().astype(np.int8)
+        out['flow_%s_path' % tag] = best_path.astype(np.int8)
+        out['flow_%s_basecall' % tag] = np.array(basecall)
+    # errprobs_from_trans on genuine posterior weights (the documented use)
+    post = ref_decode.flipflop_make_trans(scores[:, :3], _never_use_cupy=True)
+    _, _, paths = ref_decode._flipflop_viterbi(scores[:, :3])
+    out['q_trans'] = post.numpy()
+    out['q_paths'] = paths.numpy().astype(np.int8)
+    out['q_errprobs'] = ref_q.errprobs_from_trans(post, paths).numpy()
+    out['q_qchars'] = np.array(ref_q.qchar_from_errprob(np.array([0.5, 0.1, 0.011, 1e-4, 0.9999]), 1.0, 0.0))
+    out['q_qchars_cal'] = np.array(ref_q.qchar_from_errprob(np.array([0.5, 0.1, 0.011, 1e-4]), 0.9, 1.5))
+    np.savez_compressed(os.path.join(HERE, 'basecall.npz'), **out)
+    print('basecall.npz', os.path.getsize(os.path.join(HERE, 'basecall.npz')), 'bytes;',
+          'flow basecall lengths', [len(str(out['flow_%s_basecall' % t])) for t in ('post', 'raw', 'temp')])
+
+
 if __name__ == '__main__':
-    if sys.argv[1:] != ['decode']:      # `make_golden.py decode` regenerates decode.npz only
-        main()
-    make_decode()
+    # `make_golden.py decode` / `make_golden.py basecall` regenerate that file only
+    if sys.argv[1:] == ['basecall']:
+        make_basecall()
+    else:
+        if sys.argv[1:] != ['decode']:
+            main()
+        make_decode()
+        if sys.argv[1:] != ['decode']:
+            make_basecall()
