@@ -6,10 +6,11 @@ hot path on the B200-native kernels of taiyaki_b200.
 
     train_flipflop.py [flags] model.py input
 
-`input` is a mapped-signal source.  HDF5 (taiyaki/mapped_signal_files.py) needs
-h5py, which this image does not have; `synthetic:NREADS[:5mC]` generates
-r9.4.1-like reads in memory (taiyaki_b200/signal_mapping.py) and goes through
-the same chunk_selection / prepare_random_batches path.
+`input` is a mapped-signal source: a mapped-signal HDF5 file, per-read or batched
+(taiyaki/mapped_signal_files.py; read by taiyaki_b200/mapped_signal_files.py over a
+plain-Python HDF5 decoder, this image has no h5py), or `synthetic:NREADS[:5mC]`,
+which generates r9.4.1-like reads in memory (taiyaki_b200/signal_mapping.py).  Both
+go through the same chunk_selection / prepare_random_batches path.
 
 Multi-GPU: one process per GPU, `torchrun --nproc-per-node G bin/train_flipflop.py ...`
 (LOCAL_RANK from the environment, or --local_rank as in the reference,
@@ -22,6 +23,7 @@ import os
 import sys
 import time
 from collections import defaultdict, namedtuple
+from itertools import islice
 from shutil import copyfile
 
 import numpy as np
@@ -31,8 +33,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from taiyaki_b200 import (chunk_selection, device_batching, helpers, layers, maths,  # noqa: E402
-                          signal_mapping, training)
+from taiyaki_b200 import (chunk_selection, device_batching, helpers, layers,  # noqa: E402
+                          mapped_signal_files, maths, signal_mapping, training)
 from taiyaki_b200.alphabet import AlphabetInfo  # noqa: E402
 
 DOTROWLENGTH = 50
@@ -92,6 +94,7 @@ def get_train_flipflop_parser():
     g.add_argument('--filter_min_pass_fraction', default=0.5, type=float)
     g.add_argument('--filter_path_buffer', default=1.1, type=float)
     g.add_argument('--limit', default=None, type=int)
+    g.add_argument('--input_strand_list', default=None)
     g.add_argument('--reverse', default=False, type=auto_bool)
     g.add_argument('--sample_nreads_before_filtering', type=int, default=100000)
     g.add_argument('--chunk_len_min', default=3000, type=int)
@@ -116,7 +119,7 @@ def get_train_flipflop_parser():
     g.add_argument('--mod_factor', default=(8.0, 1.0, 50000), nargs=3, type=float,
                    metavar=('start', 'final', 'niter'))
     p.add_argument('model', help='File to read python model (or checkpoint) from')
-    p.add_argument('input', help='Mapped-signal source (synthetic:NREADS[:5mC])')
+    p.add_argument('input', help='Mapped-signal HDF5 file, or synthetic:NREADS[:5mC]')
     return p
 
 
@@ -179,13 +182,38 @@ def parse_init_args(args):
     return RESOURCE_INFO(is_multi_gpu, is_lead_process, device), logs
 
 
+def get_read_ids(filename):
+    """read_id column of a tab-separated strand list (helpers.py:200-209)."""
+    with open(filename) as fh:
+        header = fh.readline().rstrip('\n').split('\t')
+        col = header.index('read_id')
+        return [line.rstrip('\n').split('\t')[col] for line in fh if line.strip()]
+
+
 def load_data(args, log, res_info):
-    """train_flipflop.py:283-329 with an in-memory synthetic source."""
+    """train_flipflop.py:283-329; mapped-signal HDF5 or the in-memory synthetic source."""
     log.write('* Loading data from {}\n'.format(args.input))
     if not args.input.startswith('synthetic:'):
-        raise RuntimeError(
-            'Only synthetic:NREADS[:5mC] inputs are available: reading mapped-signal HDF5 needs '
-            'h5py, which is not installed in this image')
+        # mapped-signal HDF5, per-read or batched (train_flipflop.py:285-303)
+        if args.input_strand_list is not None:
+            read_ids = list(set(get_read_ids(args.input_strand_list)))
+            log.write(('* Will train from a subset of {} strands, determined ' +
+                       'by read_ids in input strand list\n').format(len(read_ids)))
+        else:
+            log.write('* Reads not filtered by id\n')
+            read_ids = None
+        if args.limit is not None:
+            log.write('* Limiting number of strands to {}\n'.format(args.limit))
+        with mapped_signal_files.MappedSignalReader(args.input) as msr:
+            alphabet_info = msr.get_alphabet_information()
+            read_data = list(islice(msr.reads(read_ids), args.limit))
+        log.write('* Using alphabet definition: {}\n'.format(str(alphabet_info)))
+        if len(read_data) == 0:
+            log.write('* No reads remaining for training, exiting.\n')
+            sys.exit(1)
+        log.write('* Loaded {} reads.\n'.format(len(read_data)))
+        mod_cat_weights = np.ones(alphabet_info.nbase, dtype=np.float32)
+        return read_data, alphabet_info, training.MOD_INFO(mod_cat_weights, MOD_FACTOR(*args.mod_factor))
     parts = args.input.split(':')
     nreads = int(parts[1])
     with_mods = len(parts) > 2 and parts[2].lower() == '5mc'

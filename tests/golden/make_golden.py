@@ -346,13 +346,93 @@ def make_basecall():
           'flow basecall lengths', [len(str(out['flow_%s_basecall' % t])) for t in ('post', 'raw', 'temp')])
 
 
+def make_real():
+    """Real r9.4.1 reads (the reference's test/data/mapped_signal_file/mapped_reads_{0,1}.hdf5,
+    7 reads from the walkthrough data set) -> tests/golden/real_reads.npz:
+
+      * the arrays and attributes of every read, as decoded by taiyaki_b200/hdf5_min.py (the
+        reference cannot read the files here either -- no h5py); each decoded read is built
+        into the REFERENCE's signal_mapping.SignalMapping and must pass its own check();
+      * the reference's chunk sampling on them (chunk_selection.sample_filter_parameters and
+        sample_chunks under a fixed numpy seed): filter parameters, and per chunk the read,
+        start sample, standardised current, sequence, dwell statistics, rejection reason;
+      * the reference's C loss (crf_flipflop_grad via oracle/_ref) on seeded random scores
+        with the flip-flop coded REAL label sequences of the accepted chunks."""
+    from taiyaki import chunk_selection as ref_cs
+    from taiyaki import signal_mapping as ref_sm
+    from taiyaki_b200 import hdf5_min
+    out = {}
+    reads = []
+    names = []
+    for fn in ('mapped_reads_0', 'mapped_reads_1'):
+        f = hdf5_min.File(os.path.join(REF, 'test/data/mapped_signal_file', fn + '.hdf5'))
+        assert int(f.attrs['version']) == 8 and f.attrs['alphabet'] == 'ACGT'
+        out[fn + '_read_ids'] = np.array(f['Reads'].keys())
+        for rid in f['Reads'].keys():
+            g = f['Reads/' + rid]
+            d = {k: g[k][()] for k in g.keys()}
+            d.update(g.attrs)
+            assert d['read_id'] == rid
+            sm = ref_sm.SignalMapping(**d)
+            assert sm.check() == ref_sm.SignalMapping.pass_str, sm.check()
+            reads.append(sm)
+            names.append(rid)
+            for k in ('Dacs', 'Ref_to_signal', 'Reference'):
+                out['read_%s_%s' % (rid, k)] = d[k]
+            out['read_%s_attrs' % rid] = np.array([d['shift_frompA'], d['scale_frompA'], d['range'],
+                                                    d['offset'], d['digitisation']], dtype=np.float64)
+    out['read_ids'] = np.array(names)
+    chunk_len, stride, nsample = 1000, 5, 40
+    np.random.seed(17)
+    fp = ref_cs.sample_filter_parameters(reads, 100, chunk_len, 10.0, 10.0, 0.1, stride, 1.1)
+    out['fp_median_meandwell'] = np.float64(fp.median_meandwell)
+    out['fp_mad_meandwell'] = np.float64(fp.mad_meandwell)
+    out['fp_args'] = np.array([100, chunk_len, 10.0, 10.0, 0.1, stride, 1.1])
+    np.random.seed(18)
+    # tighter filters than the defaults so that some real chunks are rejected
+    fp2 = fp._replace(filter_mean_dwell=1.5, filter_max_dwell=6.0)
+    chunks, rejections = ref_cs.sample_chunks(reads, nsample, chunk_len, fp2)
+    out['chunk_seed'] = np.array([17, 18])
+    out['chunk_filter'] = np.array([1.5, 6.0])
+    out['chunk_read'] = np.array([names.index(c.read_id) for c in chunks])
+    out['chunk_start'] = np.array([c.start_sample for c in chunks])
+    out['chunk_current'] = np.stack([c.current for c in chunks]).astype(np.float64)
+    out['chunk_seqlen'] = np.array([len(c.sequence) for c in chunks])
+    out['chunk_seq'] = np.concatenate([c.sequence for c in chunks]).astype(np.int16)
+    out['chunk_mean_dwell'] = np.array([c.mean_dwell for c in chunks], dtype=np.float64)
+    out['chunk_max_dwell'] = np.array([c.max_dwell for c in chunks], dtype=np.float64)
+    out['rejection_keys'] = np.array(sorted(rejections))
+    out['rejection_counts'] = np.array([rejections[k] for k in sorted(rejections)])
+    # loss on the real label sequences of the first 8 accepted chunks
+    nb = 8
+    nblk = chunk_len // stride
+    seqs = np.concatenate([ref_fff.flipflop_code(c.sequence.astype(np.int64), 4)
+                           for c in chunks[:nb]]).astype(np.int64)
+    seqlen = out['chunk_seqlen'][:nb].astype(np.int64)
+    scores = oracle.synth_scores(nblk, nb, 40, seed=41)
+    mv, st = ref_indices(seqs, seqlen, 4)
+    sc, gr = oracle.c_crf_flipflop_grad(scores, mv, st, seqlen, 'ref')
+    out['loss_scores'] = scores
+    out['loss_seqs'] = seqs
+    out['loss_seqlen'] = seqlen
+    out['loss_score'] = sc
+    out['loss_grad'] = gr
+    np.savez_compressed(os.path.join(HERE, 'real_reads.npz'), **out)
+    print('real_reads.npz', os.path.getsize(os.path.join(HERE, 'real_reads.npz')), 'bytes;',
+          len(reads), 'reads;', len(chunks), 'chunks; rejections', dict(rejections),
+          '; median/mad mean dwell', fp.median_meandwell, fp.mad_meandwell, '; L', seqlen)
+
+
 if __name__ == '__main__':
     # `make_golden.py decode` / `make_golden.py basecall` regenerate that file only
     if sys.argv[1:] == ['basecall']:
         make_basecall()
+    elif sys.argv[1:] == ['real']:
+        make_real()
     else:
         if sys.argv[1:] != ['decode']:
             main()
         make_decode()
         if sys.argv[1:] != ['decode']:
             make_basecall()
+            make_real()
