@@ -1,0 +1,173 @@
+"""Test-only writer of the HDF5 subset the batched mapped-signal format uses
+(taiyaki/mapped_signal_files.py:562-679 through h5py's default settings): superblock 0,
+version-1 object headers, old-style groups (B-tree + SNOD + local heap), chunked datasets
+with shuffle + deflate, variable-length strings in a global heap collection, scalar
+attributes.  Written from the HDF5 file-format specification, independently of
+taiyaki_b200/hdf5_min.py's parsing code, to exercise the reader on layouts the reference's
+per-read fixture files do not contain."""
+import struct
+import zlib
+
+import numpy as np
+
+UNDEF = 0xFFFFFFFFFFFFFFFF
+GCOL_BYTES = 1 << 16
+
+
+def _pad8(b):
+    return b + bytes(-len(b) % 8)
+
+
+class Writer:
+    def __init__(self):
+        self.buf = bytearray(96 + GCOL_BYTES)    # superblock and heap collection written last
+        self.gcol = 96
+        self.strings = []                        # global heap objects
+
+    def alloc(self, data):
+        self.buf += bytes(-len(self.buf) % 8)
+        addr = len(self.buf)
+        self.buf += data
+        return addr
+
+    # ---- messages
+    @staticmethod
+    def dataspace(shape):
+        return struct.pack('<BBB5x', 1, len(shape), 0) + b''.join(struct.pack('<Q', s) for s in shape)
+
+    @staticmethod
+    def datatype(dtype):
+        if dtype == 'vlen_str':
+            base = struct.pack('<BBBBI', 0x13, 0, 0, 0, 1)             # 1-byte string
+            return struct.pack('<BBBBI', 0x19, 0x01, 0x01, 0, 16) + base
+        dt = np.dtype(dtype)
+        if dt.kind in 'iu':
+            return struct.pack('<BBBBIHH', 0x10, 0x08 if dt.kind == 'i' else 0, 0, 0, dt.itemsize,
+                               0, 8 * dt.itemsize)
+        if dt.kind == 'f' and dt.itemsize == 8:
+            return struct.pack('<BBBBIHHBBBBI', 0x11, 0x20, 0x3f, 0, 8, 0, 64, 52, 11, 0, 52, 1023)
+        if dt.kind == 'f' and dt.itemsize == 4:
+            return struct.pack('<BBBBIHHBBBBI', 0x11, 0x20, 0x1f, 0, 4, 0, 32, 23, 8, 0, 23, 127)
+        raise ValueError(dtype)
+
+    def vlen_refs(self, values):
+        """16-byte (length, collection address, index) elements."""
+        out = b''
+        for v in values:
+            raw = v.encode('utf-8')
+            self.strings.append(raw)
+            out += struct.pack('<IQI', len(raw), self.gcol, len(self.strings))
+        return out
+
+    def header(self, messages):
+        body = b''
+        for mtype, data in messages:
+            data = _pad8(data)
+            body += struct.pack('<HHB3x', mtype, len(data), 0) + data
+        return self.alloc(struct.pack('<BBHII4x', 1, 0, len(messages), 1, len(body)) + body)
+
+    def attribute(self, name, value):
+        if isinstance(value, str):
+            dt, data = self.datatype('vlen_str'), self.vlen_refs([value])
+        else:
+            arr = np.asarray(value)
+            dt, data = self.datatype(arr.dtype), arr.tobytes()
+        space = self.dataspace(())
+        nm = name.encode() + b'\0'
+        return (0x0C, struct.pack('<BxHHH', 1, len(nm), len(dt), len(space)) +
+                _pad8(nm) + _pad8(dt) + _pad8(space) + data)
+
+    # ---- objects
+    def dataset(self, values, chunk, shuffle=True):
+        """1-D chunked dataset, deflate (+ shuffle for numeric types)."""
+        if isinstance(values, np.ndarray):
+            dt_msg, esize, raw = self.datatype(values.dtype), values.dtype.itemsize, values.tobytes()
+        else:
+            dt_msg, esize, raw, shuffle = self.datatype('vlen_str'), 16, self.vlen_refs(values), False
+        n = len(raw) // esize
+        entries = []
+        for start in range(0, max(n, 1), chunk):
+            piece = raw[start * esize:(start + chunk) * esize]
+            piece += bytes(chunk * esize - len(piece))               # edge chunks are full size
+            if shuffle:
+                piece = np.frombuffer(piece, dtype='u1').reshape(-1, esize).T.tobytes()
+            piece = zlib.compress(piece, 4)
+            entries.append((len(piece), start, self.alloc(piece)))
+        node = b'TREE' + struct.pack('<BBHQQ', 1, 0, len(entries), UNDEF, UNDEF)
+        for size, start, addr in entries:
+            node += struct.pack('<IIQQ', size, 0, start, 0) + struct.pack('<Q', addr)
+        node += struct.pack('<IIQQ', 0, 0, ((n + chunk - 1) // chunk) * chunk, 0)
+        btree = self.alloc(node)
+        layout = struct.pack('<BBB', 3, 2, 2) + struct.pack('<Q', btree) + struct.pack('<II', chunk, esize)
+        filters = b''
+        nfilt = 0
+        if shuffle:
+            filters += struct.pack('<HHHH', 2, 0, 1, 1) + struct.pack('<I', esize) + bytes(4)
+            nfilt += 1
+        filters += struct.pack('<HHHH', 1, 0, 1, 1) + struct.pack('<I', 4) + bytes(4)
+        nfilt += 1
+        pipeline = struct.pack('<BB6x', 1, nfilt) + filters
+        return self.header([(0x01, self.dataspace((n,))), (0x03, dt_msg), (0x0B, pipeline),
+                            (0x08, layout)])
+
+    def group(self, links, attrs=(), per_node=8):
+        """Old-style group; `links` name -> object header address."""
+        names = sorted(links)
+        heap_data = bytearray(b'\0' * 8)
+        offsets = {}
+        for nm in names:
+            offsets[nm] = len(heap_data)
+            heap_data += _pad8(nm.encode() + b'\0')
+        data_addr = self.alloc(bytes(heap_data))
+        heap = self.alloc(b'HEAP' + struct.pack('<B3xQQQ', 0, len(heap_data), UNDEF, data_addr))
+        children = []
+        for i in range(0, len(names), per_node):
+            part = names[i:i + per_node]
+            snod = b'SNOD' + struct.pack('<BxH', 1, len(part))
+            for nm in part:
+                snod += struct.pack('<QQII16x', offsets[nm], links[nm], 0, 0)
+            children.append((self.alloc(snod), offsets[part[-1]]))
+        node = b'TREE' + struct.pack('<BBHQQ', 0, 0, len(children), UNDEF, UNDEF) + struct.pack('<Q', 0)
+        for addr, last in children:
+            node += struct.pack('<QQ', addr, last)
+        btree = self.alloc(node)
+        msgs = [(0x11, struct.pack('<QQ', btree, heap))] + [self.attribute(k, v) for k, v in attrs]
+        return self.header(msgs), btree, heap
+
+    def close(self, root_header, root_btree, root_heap, filename):
+        coll = b''
+        for i, raw in enumerate(self.strings):
+            coll += struct.pack('<HHIQ', i + 1, 1, 0, len(raw)) + _pad8(raw)
+        head = b'GCOL' + struct.pack('<B3xQ', 1, GCOL_BYTES)
+        free = GCOL_BYTES - len(head) - len(coll)
+        assert free >= 16, 'global heap collection of the test writer is full'
+        coll += struct.pack('<HHIQ', 0, 0, 0, free)
+        self.buf[self.gcol:self.gcol + len(head) + len(coll)] = head + coll
+        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
+        sb += struct.pack('<QQQQ', 0, UNDEF, len(self.buf), UNDEF)
+        sb += struct.pack('<QQII', 0, root_header, 1, 0) + struct.pack('<QQ', root_btree, root_heap)
+        self.buf[:96] = sb
+        with open(filename, 'wb') as fh:
+            fh.write(bytes(self.buf))
+
+
+def write_batched_mapped_signal_file(filename, reads, batch_size=3, chunk=1000):
+    """The layout BatchHDF5Writer produces: /Batches/Batch_n/<field>[, <field>_lengths]."""
+    w = Writer()
+    batches = {}
+    for b, first in enumerate(range(0, len(reads), batch_size)):
+        part = reads[first:first + batch_size]
+        links = {}
+        for k, dt in (('Dacs', np.int16), ('Ref_to_signal', np.int32), ('Reference', np.int16)):
+            links[k] = w.dataset(np.concatenate([getattr(r, k) for r in part]).astype(dt), chunk)
+            links[k + '_lengths'] = w.dataset(
+                np.array([len(getattr(r, k)) for r in part], dtype=np.int32), chunk)
+        for k in ('shift_frompA', 'scale_frompA', 'range', 'offset', 'digitisation'):
+            links[k] = w.dataset(np.array([getattr(r, k) for r in part], dtype=np.float64), chunk)
+        links['read_id'] = w.dataset([r.read_id for r in part], chunk)
+        batches['Batch_%d' % b] = w.group(links, per_node=5)[0]
+    top = {'Batches': w.group(batches)[0],
+           'read_ids': w.dataset([r.read_id for r in reads], chunk)}
+    root = w.group(top, attrs=[('version', np.int64(8)), ('alphabet', 'ACGT'),
+                               ('collapse_alphabet', 'ACGT'), ('mod_long_names', '')])
+    w.close(*root, filename)

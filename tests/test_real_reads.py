@@ -93,6 +93,33 @@ def test_train_entry_point_loads_hdf5(tmp_path):
         '34bebf28-d997-446e-8dda-ce707a266c2d', 'cb8a6688-0ddb-42ff-ad7e-de004d738790']
 
 
+def test_batched_mapped_signal_file(g, tmp_path):
+    """The batched layout (the reference writer's default: concatenated arrays per batch,
+    chunked + shuffle + deflate, variable-length read ids) written by the test-only writer
+    from the real reads and read back through BatchHDF5Reader."""
+    from taiyaki_b200 import mapped_signal_files
+    from .hdf5_write_min import write_batched_mapped_signal_file
+    reads = golden_reads(g)
+    fn = str(tmp_path / 'batched.hdf5')
+    write_batched_mapped_signal_file(fn, reads, batch_size=3, chunk=7000)
+    with mapped_signal_files.MappedSignalReader(fn) as msr:
+        assert isinstance(msr, mapped_signal_files.BatchHDF5Reader)
+        assert msr.batch_names == ['Batch_0', 'Batch_1', 'Batch_2']
+        assert msr.get_read_ids() == [r.read_id for r in reads]
+        assert msr.get_alphabet_information().alphabet == 'ACGT' and msr.check() == 'pass'
+        got = list(msr.reads())
+        assert [r.read_id for r in got] == [r.read_id for r in reads]
+        for a, b in zip(got, reads):
+            np.testing.assert_array_equal(a.Dacs, b.Dacs)
+            np.testing.assert_array_equal(a.Ref_to_signal, b.Ref_to_signal)
+            np.testing.assert_array_equal(a.Reference, b.Reference)
+            assert (a.shift_frompA, a.scale_frompA, a.range, a.offset, a.digitisation) == (
+                b.shift_frompA, b.scale_frompA, b.range, b.offset, b.digitisation)
+        pick = [reads[5].read_id, reads[0].read_id]
+        assert sorted(r.read_id for r in msr.reads(pick)) == sorted(pick)
+        np.testing.assert_array_equal(msr.get_read(reads[4].read_id).Dacs, reads[4].Dacs)
+
+
 def test_hdf5_errors(tmp_path):
     from taiyaki_b200 import hdf5_min
     p = tmp_path / 'x.hdf5'
