@@ -278,6 +278,21 @@ int ty_sample_chunks(const int16_t *dacs, const int64_t *dacs_off, const int32_t
 int ty_flipflop_viterbi(const float *scores, int T, int N, int nbase, float *fwd,
                         int64_t *traceback, int64_t *path, void *stream);
 
+/* Best alignment of label sequences to flip-flop transition scores -- the max-product
+ * twin of the training DP (taiyaki/flipflop_remap.py:6-86, map_to_crf_viterbi).
+ * nread reads per call, one CTA each: read r has T_r = t_off[r+1]-t_off[r] blocks of
+ * scores [T_r][S] fp32 (rows t_off[r]..), M_r = m_off[r+1]-m_off[r] positions with
+ * stay_idx[m_off[r]..] and step_idx[m_off[r]-r ..] (M_r - 1 entries), traceback
+ * workspace tb_ws[tb_off[r] ..] of T_r * M_r bytes.  Outputs: score[r] fp64 (position
+ * scores are fp64 as in the reference), path[t_off[r]+r ..] of T_r + 1 int32 sequence
+ * positions, -1 in the clipped start / end stretches (localpen).  dp_ws: 2 * sum M
+ * doubles, used (and required) only when max_m positions do not fit in shared memory
+ * (about 12.9k); may be NULL otherwise.  S <= 255. */
+int ty_flipflop_remap(const float *scores, const int64_t *t_off, const int32_t *step_idx,
+                      const int32_t *stay_idx, const int64_t *m_off, const int64_t *tb_off,
+                      int nread, int S, int max_m, double localpen, double *score,
+                      int32_t *path, uint8_t *tb_ws, double *dp_ws, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

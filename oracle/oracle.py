@@ -343,6 +343,61 @@ def flipflop_viterbi(scores):
     return fwd, tb, path
 
 
+def map_to_crf_viterbi(scores, step_index, stay_index, localpen=1e30):
+    """Best alignment of a label sequence to transition scores, numpy restatement of
+    taiyaki/flipflop_remap.py:6-86 with an explicit [T+1, M] decision table instead of
+    packed bits.  Position scores are float64 (the reference's np.full default dtype),
+    `start` / `end` are the clipping states that cost `localpen` per skipped block.
+    Returns (score, path[T+1]) with -1 where the alignment sits in start / end."""
+    scores = np.asarray(scores)
+    step_index = np.asarray(step_index, dtype=np.int64)
+    stay_index = np.asarray(stay_index, dtype=np.int64)
+    T, M = len(scores), len(stay_index)
+    assert len(step_index) == M - 1
+    big = 1e30                                             # constants.py:8
+    vec = np.full(M, -big)
+    vec[0] = 0.0                                           # :31-33
+    start, end, end_at = 0.0, -big, 0                      # :35-37
+    moved = np.zeros((T + 1, M), dtype=np.uint8)           # :39
+    for t in range(T):
+        w_stay = scores[t, stay_index]                     # :44-45
+        w_step = scores[t, step_index]
+        stay = vec + w_stay                                # :50
+        step = vec[:-1] + w_step                           # :53
+        leave_start = start - localpen                     # :56
+        start = start + max(w_stay[0], -localpen)          # :57
+        remain = end + max(w_stay[-1], -localpen)          # :67
+        into_end = vec[-1] - localpen                      # :68
+        nxt = stay.copy()                                  # :60-62
+        nxt[1:] = np.maximum(nxt[1:], step)
+        nxt[0] = max(nxt[0], start)
+        moved[t + 1, 1:] = stay[1:] < step                 # :63-64
+        moved[t + 1, 0] = 1 if leave_start > stay[0] else 0
+        if into_end > remain:                              # :69-71
+            end_at = t
+        end = max(remain, into_end)
+        vec = nxt
+    path = np.full(T + 1, -1, dtype=int)                   # :73
+    t, m = (T, M - 1) if vec[-1] > end else (end_at, M - 1)    # :74-79
+    while t >= 0 and m >= 0:                               # :81-85
+        path[t] = m
+        m -= int(moved[t, m])
+        t -= 1
+    return max(vec[-1], end), path
+
+
+def remap_indices(bases, nbase=4):
+    """(step_index, stay_index) of an integer base sequence (flipflop_remap.py:132-140)."""
+    bases = np.asarray(bases, dtype=np.int64)
+    move = np.ediff1d(bases, to_begin=1) != 0
+    run = (1 - move).cumsum()
+    flops = (run - np.maximum.accumulate(move * run)) % 2 == 1     # flipflopfings.py:34-53
+    stay = np.where(flops, bases + (2 * nbase + 1) * nbase, bases + 2 * nbase * bases)
+    frm = (bases + flops * nbase)[:-1]
+    to = np.maximum(bases, nbase * flops)[1:]
+    return frm + 2 * nbase * to, stay
+
+
 def synth_scores(nblk, nbatch, ntrans=40, seed=0, can_nmods=None):
     """5*tanh(N(0,1)) transition scores; for cat-mod (ntrans > 40) the extra
     columns are per-canonical-base log-softmax groups (layers.py:1611-1640)."""

@@ -55,6 +55,7 @@ _SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p]),
     'ty_flipflop_viterbi': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    'ty_flipflop_remap': (c_int, [c_void_p] * 6 + [c_int] * 3 + [ctypes.c_double] + [c_void_p] * 5),
     'ty_batch_counts_len': (c_int, []),
     'ty_sample_chunks': (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_void_p] + [c_int] * 3 +
                          [c_void_p] * 10),

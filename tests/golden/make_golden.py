@@ -423,12 +423,63 @@ def make_real():
           '; median/mad mean dwell', fp.median_meandwell, fp.mad_meandwell, '; L', seqlen)
 
 
+def make_remap():
+    """Alignments of the reference's taiyaki/flipflop_remap.py on seeded random scores and
+    on the two tables of its unit test (test/unit/test_flipflop_remap.py:8-90)
+    -> tests/golden/remap.npz.
+
+    Shim: under numpy 2 the traceback line `m -= move` (flipflop_remap.py:85) wraps the
+    uint8 `move` around instead of reaching -1 when the path leaves through the start
+    state, and the function raises IndexError.  The module source is loaded with that one
+    statement changed to `m -= int(move)`; nothing else differs from the file on disk."""
+    import types
+    src = open(os.path.join(REF, 'taiyaki/flipflop_remap.py')).read()
+    assert src.count('m -= move') == 1
+    ref = types.ModuleType('ref_flipflop_remap')
+    exec(compile(src.replace('m -= move', 'm -= int(move)'), 'flipflop_remap.py', 'exec'), ref.__dict__)
+    out = {}
+    rng = np.random.RandomState(51)
+    cases = {'a': (6, 4, -0.5, 3.0), 'b': (50, 12, 1e30, 3.0), 'c': (80, 10, 0.5, 3.0),
+             'd': (200, 60, 2.0, 3.0), 'e': (40, 1, 0.3, 3.0), 'f': (30, 29, 1e30, 3.0),
+             'g': (300, 40, 0.0, 3.0), 'h': (300, 100, 1.0, 5.0), 'i': (120, 30, 0.2, 1.0),
+             'j': (257, 129, 1e30, 2.0), 'k': (64, 33, 0.7, 0.5)}
+    for tag, (T, L, pen, scale) in cases.items():
+        seq = ''.join('ACGT'[i] for i in rng.randint(0, 4, size=L))
+        if tag in 'hj':        # homopolymer runs exercise the flop coding
+            seq = ''.join(c * int(k) for c, k in zip(seq[:L // 2], rng.randint(1, 4, size=L // 2)))[:L]
+        sc = (scale * rng.standard_normal((T, 40))).astype('f4')
+        score, path = ref.flipflop_remap(sc, seq, localpen=pen)
+        out[tag + '_scores'] = sc
+        out[tag + '_seq'] = np.array(seq)
+        out[tag + '_localpen'] = np.float64(pen)
+        out[tag + '_score'] = np.float64(score)
+        out[tag + '_path'] = path.astype(np.int32)
+    # unit-test tables: alphabet AB, 12 transitions; expected values are the test's own
+    lt = np.zeros((6, 12), dtype='f4')
+    for t, k in enumerate((8, 10, 6, 5, 1, 0)):
+        lt[t, k] = 1
+    score, path = ref.flipflop_remap(lt, 'AABA', alphabet='AB', localpen=-0.5)
+    assert score == 6.0 and path.tolist() == [0, 1, 1, 2, 2, 3, 3]
+    out['kat1_scores'], out['kat1_seq'], out['kat1_score'], out['kat1_path'] = lt, np.array('AABA'), score, path
+    lt = np.zeros((5, 12), dtype='f4')
+    lt[2, 5] = 1
+    lt[3, 1] = 1
+    score, path = ref.flipflop_remap(lt, 'BA', alphabet='AB', localpen=-0.5)
+    assert score == 3.5 and path.tolist() == [-1, -1, 0, 0, 1, -1]
+    out['kat2_scores'], out['kat2_seq'], out['kat2_score'], out['kat2_path'] = lt, np.array('BA'), score, path
+    np.savez_compressed(os.path.join(HERE, 'remap.npz'), **out)
+    print('remap.npz', os.path.getsize(os.path.join(HERE, 'remap.npz')), 'bytes;',
+          {t: (float(out[t + '_score']), int((out[t + '_path'] == -1).sum())) for t in cases})
+
+
 if __name__ == '__main__':
     # `make_golden.py decode` / `make_golden.py basecall` regenerate that file only
     if sys.argv[1:] == ['basecall']:
         make_basecall()
     elif sys.argv[1:] == ['real']:
         make_real()
+    elif sys.argv[1:] == ['remap']:
+        make_remap()
     else:
         if sys.argv[1:] != ['decode']:
             main()
@@ -436,3 +487,4 @@ if __name__ == '__main__':
         if sys.argv[1:] != ['decode']:
             make_basecall()
             make_real()
+            make_remap()

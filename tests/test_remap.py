@@ -1,0 +1,136 @@
+"""Remapping DP (csrc/remap.cu, taiyaki_b200/flipflop_remap.py) against
+tests/golden/remap.npz -- alignments of the reference's taiyaki/flipflop_remap.py
+(make_golden.py remap) including the two tables of its own unit test.  The DP is adds and
+maxima of fp32 scores promoted to fp64: scores and paths are compared bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'remap.npz')
+CASES = 'abcdefghijk'
+
+
+@pytest.fixture(scope='module')
+def g():
+    return np.load(GOLDEN)
+
+
+def test_oracle_matches_reference(g):
+    from oracle import oracle
+    for tag in CASES:
+        bases = np.array(['ACGT'.find(b) for b in str(g[tag + '_seq'])])
+        step, stay = oracle.remap_indices(bases, 4)
+        score, path = oracle.map_to_crf_viterbi(g[tag + '_scores'], step, stay, float(g[tag + '_localpen']))
+        assert score == float(g[tag + '_score'])
+        np.testing.assert_array_equal(path, g[tag + '_path'])
+    for tag in ('kat1', 'kat2'):       # test/unit/test_flipflop_remap.py:8-90
+        bases = np.array(['AB'.find(b) for b in str(g[tag + '_seq'])])
+        step, stay = oracle.remap_indices(bases, 2)
+        score, path = oracle.map_to_crf_viterbi(g[tag + '_scores'], step, stay, -0.5)
+        assert score == float(g[tag + '_score'])
+        np.testing.assert_array_equal(path, g[tag + '_path'])
+    assert float(g['kat1_score']) == 6.0 and float(g['kat2_score']) == 3.5
+
+
+def test_remap_indices_mirror(g):
+    from oracle import oracle
+    from taiyaki_b200 import flipflop_remap
+    for tag in CASES:
+        seq = str(g[tag + '_seq'])
+        step, stay = flipflop_remap.remap_indices(seq)
+        ostep, ostay = oracle.remap_indices(np.array(['ACGT'.find(b) for b in seq]), 4)
+        np.testing.assert_array_equal(step, ostep)
+        np.testing.assert_array_equal(stay, ostay)
+    step, stay = flipflop_remap.remap_indices('AABA', 'AB')       # the unit test's low-level indices
+    assert list(step) == [8, 6, 1] and list(stay) == [0, 10, 5, 0]
+
+
+# ------------------------------------------------------------------ GPU
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    from taiyaki_b200 import _lib
+    _lib.lib()
+    return torch.device('cuda:0')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', list(CASES))
+def test_remap_golden(g, dev, tag):
+    from taiyaki_b200 import flipflop_remap
+    score, path = flipflop_remap.flipflop_remap(g[tag + '_scores'], str(g[tag + '_seq']),
+                                                localpen=float(g[tag + '_localpen']))
+    assert score == float(g[tag + '_score'])
+    np.testing.assert_array_equal(path, g[tag + '_path'])
+
+
+@pytest.mark.gpu
+def test_remap_unit_test_tables(g, dev):
+    from taiyaki_b200 import flipflop_remap
+    for tag in ('kat1', 'kat2'):
+        score, path = flipflop_remap.flipflop_remap(torch.tensor(g[tag + '_scores'], device=dev),
+                                                    str(g[tag + '_seq']), alphabet='AB', localpen=-0.5)
+        assert score == float(g[tag + '_score'])
+        assert path.tolist() == g[tag + '_path'].tolist()
+    score2, path2 = flipflop_remap.map_to_crf_viterbi(g['kat1_scores'], [8, 6, 1], [0, 10, 5, 0], localpen=-0.5)
+    assert score2 == 6.0 and path2.tolist() == [0, 1, 1, 2, 2, 3, 3]
+
+
+@pytest.mark.gpu
+def test_remap_batch_equals_single(g, dev):
+    """All golden reads (ragged T and M) in one launch."""
+    from taiyaki_b200 import flipflop_remap
+    for pen in (1e30, 0.5):
+        tags = [t for t in CASES]
+        res = flipflop_remap.flipflop_remap_batch([g[t + '_scores'] for t in tags],
+                                                  [str(g[t + '_seq']) for t in tags], localpen=pen)
+        from oracle import oracle
+        for t, (score, path) in zip(tags, res):
+            bases = np.array(['ACGT'.find(b) for b in str(g[t + '_seq'])])
+            step, stay = oracle.remap_indices(bases, 4)
+            oscore, opath = oracle.map_to_crf_viterbi(g[t + '_scores'], step, stay, pen)
+            assert score == oscore
+            np.testing.assert_array_equal(path, opath)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('T,L,pen', [(8000, 3500, 1e30), (6000, 2500, 2.0), (15000, 13500, 1e30),
+                                     (300, 400, 1e30)])
+def test_remap_full_size(dev, T, L, pen):
+    """Read-sized inputs (the third beyond the shared-memory capacity, i.e. the
+    global-memory variant; the last with more positions than blocks, where no complete
+    path exists): bit-identical to the oracle, the path is monotone and covers every
+    position, and a planted high-scoring global alignment is recovered exactly."""
+    from oracle import oracle
+    from taiyaki_b200 import flipflop_remap
+    rng = np.random.RandomState(T + L)
+    bases = rng.randint(0, 4, size=L)
+    seq = ''.join('ACGT'[b] for b in bases)
+    step, stay = flipflop_remap.remap_indices(seq)
+    scores = rng.standard_normal((T, 40)).astype('f4')
+    planted = None
+    if L < T:      # plant: dwell pattern summing to T, +6 on the planted transitions
+        cuts = np.sort(rng.choice(np.arange(1, T), size=L - 1, replace=False))
+        pos = np.zeros(T + 1, dtype=int)
+        pos[cuts] = 1
+        planted = np.cumsum(pos)
+        for t in range(T):
+            a, b = planted[t], planted[t + 1]
+            scores[t, stay[a] if a == b else step[a]] += 6.0
+    score, path = flipflop_remap.flipflop_remap(torch.tensor(scores, device=dev), seq, localpen=pen)
+    oscore, opath = oracle.map_to_crf_viterbi(scores, step, stay, pen)
+    assert score == oscore
+    np.testing.assert_array_equal(path, opath)
+    if planted is None:
+        assert score < -1e29
+        return
+    p = path[path >= 0]
+    assert p[0] == 0 and p[-1] == L - 1 and np.all(np.diff(p) >= 0) and np.all(np.diff(p) <= 1)
+    if pen >= 1e29:
+        np.testing.assert_array_equal(path, planted)
+    else:
+        gscore, _ = flipflop_remap.flipflop_remap(scores, seq, localpen=1e30)
+        assert score >= gscore
