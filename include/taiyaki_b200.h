@@ -287,7 +287,7 @@ int ty_flipflop_viterbi(const float *scores, int T, int N, int nbase, float *fwd
  * scores are fp64 as in the reference), path[t_off[r]+r ..] of T_r + 1 int32 sequence
  * positions, -1 in the clipped start / end stretches (localpen).  dp_ws: 2 * sum M
  * doubles, used (and required) only when max_m positions do not fit in shared memory
- * (about 12.9k); may be NULL otherwise.  S <= 255. */
+ * (about 12.7k); may be NULL otherwise.  S <= 255. */
 int ty_flipflop_remap(const float *scores, const int64_t *t_off, const int32_t *step_idx,
                       const int32_t *stay_idx, const int64_t *m_off, const int64_t *tb_off,
                       int nread, int S, int max_m, double localpen, double *score,

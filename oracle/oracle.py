@@ -349,7 +349,9 @@ def map_to_crf_viterbi(scores, step_index, stay_index, localpen=1e30):
     packed bits.  Position scores are float64 (the reference's np.full default dtype),
     `start` / `end` are the clipping states that cost `localpen` per skipped block.
     Returns (score, path[T+1]) with -1 where the alignment sits in start / end."""
-    scores = np.asarray(scores)
+    # float64 throughout: what the reference computes under its pinned numpy 1.18, where the
+    # scalar start / end updates promote the fp32 score like the vector updates do
+    scores = np.asarray(scores, dtype=np.float64)
     step_index = np.asarray(step_index, dtype=np.int64)
     stay_index = np.asarray(stay_index, dtype=np.int64)
     T, M = len(scores), len(stay_index)

@@ -12,7 +12,8 @@
 // a double-buffered score row live in shared memory (M <= ~12.9k positions; longer reads
 // run the same loop on a global-memory workspace); one barrier per block of signal; the
 // next row is fetched into a register during the step.  Traceback decisions are one byte
-// per (block, position), written coalesced, followed by thread 0 at the end.
+// per (block, position), written coalesced, followed at the end by warp 0 through 32-block
+// windows.
 #include "common.cuh"
 
 namespace ty {
@@ -112,18 +113,41 @@ __global__ void __launch_bounds__(1024) remap_kernel(const RemapArgs a) {
         __syncthreads();
     }
 
-    if (tid == 0) {
-        const double *fin = (T & 1) ? buf1 : buf0;
-        const double last = fin[M - 1];
-        int n, m = M - 1;
-        if (last > end_score) n = T; else n = alignment_end;                    // :74-79
-        while (n >= 0 && m >= 0) {                                              // :81-85
-            path[n] = m;
-            const int move = n > 0 ? tb[(size_t)(n - 1) * M + m] : 0;
-            m -= move;
-            n -= 1;
+    // ---- traceback (:73-85) by warp 0.  The position drops by at most one per block, so the
+    // next 32 decisions lie in a 32-row x 33-column window of the table ending at (n, m): the
+    // lanes fetch it with independent loads (one memory latency per 32 blocks instead of one
+    // per block), lane 0 walks it.
+    if (tid < 32) {
+        __shared__ uint8_t win[32][36];
+        const int lane = tid;
+        int n = 0, m = M - 1;
+        if (lane == 0) {
+            const double *fin = (T & 1) ? buf1 : buf0;
+            const double last = fin[M - 1];
+            n = last > end_score ? T : alignment_end;                           // :74-79
+            a.score[r] = fmax(last, end_score);
         }
-        a.score[r] = fmax(last, end_score);
+        n = __shfl_sync(kFullMask, n, 0);
+        while (n >= 0 && m >= 0) {
+            const int rn = n - lane;            // row of the decision table this lane fetches
+#pragma unroll
+            for (int c = 0; c < 33; c++) {
+                const int col = m - 32 + c;
+                win[lane][c] = (rn > 0 && col >= 0) ? tb[(size_t)(rn - 1) * M + col] : 0;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const int m0 = m;
+                for (int j = 0; j < 32 && n >= 0 && m >= 0; j++) {
+                    path[n] = m;
+                    m -= win[j][m - m0 + 32];
+                    n -= 1;
+                }
+            }
+            n = __shfl_sync(kFullMask, n, 0);
+            m = __shfl_sync(kFullMask, m, 0);
+            __syncwarp();                       // the window is rewritten next round
+        }
     }
 }
 
@@ -148,7 +172,7 @@ extern "C" int ty_flipflop_remap(const float *scores, const int64_t *t_off, cons
     threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
     const size_t smem = (size_t)a.mp * 18 + (size_t)2 * Sp * 4;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (smem <= 227 * 1024) {
+    if (smem + 2048 <= 227 * 1024) {          // 2 KB left for the traceback window
         if (smem > 48 * 1024 &&
             cudaFuncSetAttribute(remap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)

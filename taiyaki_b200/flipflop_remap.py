@@ -59,12 +59,13 @@ def map_to_crf_viterbi_batch(scores_list, step_list, stay_list, localpen=LARGE_V
     tb = torch.empty(max(int(tb_off[-1]), 1), dtype=torch.uint8, device=dev)
     max_m = int(M.max())
     dp = None
-    if max_m > 12800:         # beyond the shared-memory capacity: global-memory score vectors
+    if max_m > 12000:         # near / beyond the shared-memory capacity: global-memory score vectors
         dp = torch.empty(2 * int(m_off[-1]), dtype=torch.float64, device=dev)
-    rc = lib.ty_flipflop_remap(_lib.ptr(scores), _lib.ptr(offs[:n1]), _lib.ptr(step), _lib.ptr(stay),
-                               _lib.ptr(offs[n1:2 * n1]), _lib.ptr(offs[2 * n1:]), nread, S, max_m,
-                               float(localpen), _lib.ptr(score), _lib.ptr(path), _lib.ptr(tb),
-                               _lib.ptr(dp), _lib.stream_ptr(dev))
+    with _lib.timed('remap', dev):
+        rc = lib.ty_flipflop_remap(_lib.ptr(scores), _lib.ptr(offs[:n1]), _lib.ptr(step),
+                                   _lib.ptr(stay), _lib.ptr(offs[n1:2 * n1]), _lib.ptr(offs[2 * n1:]),
+                                   nread, S, max_m, float(localpen), _lib.ptr(score), _lib.ptr(path),
+                                   _lib.ptr(tb), _lib.ptr(dp), _lib.stream_ptr(dev))
     _lib.check(rc, 'ty_flipflop_remap')
     _lib.count_launches(1)
     score_h = score.cpu().numpy()

@@ -431,7 +431,13 @@ def make_remap():
     Shim: under numpy 2 the traceback line `m -= move` (flipflop_remap.py:85) wraps the
     uint8 `move` around instead of reaching -1 when the path leaves through the start
     state, and the function raises IndexError.  The module source is loaded with that one
-    statement changed to `m -= int(move)`; nothing else differs from the file on disk."""
+    statement changed to `m -= int(move)`; nothing else differs from the file on disk.
+
+    Precision: the reference pins numpy 1.18 (requirements.txt:9), where the scalar updates
+    `start_score + max(stay_scores[0], -localpen)` (:57, :67) promote the fp32 score to
+    float64 like the vector updates do.  numpy 2 keeps such scalar sums in float32.  The fp32
+    scores are therefore handed over as float64 (an exact conversion), which gives the
+    pinned-numpy arithmetic -- all float64 -- under either numpy."""
     import types
     src = open(os.path.join(REF, 'taiyaki/flipflop_remap.py')).read()
     assert src.count('m -= move') == 1
@@ -448,7 +454,7 @@ def make_remap():
         if tag in 'hj':        # homopolymer runs exercise the flop coding
             seq = ''.join(c * int(k) for c, k in zip(seq[:L // 2], rng.randint(1, 4, size=L // 2)))[:L]
         sc = (scale * rng.standard_normal((T, 40))).astype('f4')
-        score, path = ref.flipflop_remap(sc, seq, localpen=pen)
+        score, path = ref.flipflop_remap(sc.astype('f8'), seq, localpen=pen)
         out[tag + '_scores'] = sc
         out[tag + '_seq'] = np.array(seq)
         out[tag + '_localpen'] = np.float64(pen)
