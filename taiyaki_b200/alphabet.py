@@ -54,6 +54,10 @@ class AlphabetInfo(object):
             assert self.mod_long_names is not None
             assert self.nmod_base == len(self.mod_long_names)
 
+    def collapse_sequence(self, sequence_with_mods):
+        """Modified bases -> their canonical bases (alphabet.py:120-124)."""
+        return sequence_with_mods.translate(self.translation_table)
+
     def contains_modified_bases(self):
         return len(self.mod_long_names) > 0
 

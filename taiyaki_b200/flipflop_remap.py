@@ -15,7 +15,9 @@ LARGE_VAL = 1e30
 def remap_indices(sequence, alphabet=DEFAULT_ALPHABET):
     """(step_index, stay_index) of a base sequence (flipflop_remap.py:132-140)."""
     nbase = len(alphabet)
-    bases = np.array([alphabet.find(b) for b in sequence])
+    lut = np.full(256, -1, dtype=np.int64)          # str.find: -1 for a letter not in the alphabet
+    lut[np.frombuffer(alphabet.encode('latin-1'), dtype=np.uint8)[::-1]] = np.arange(nbase)[::-1]
+    bases = lut[np.frombuffer(sequence.encode('latin-1'), dtype=np.uint8)]
     flops = flipflopfings.flopmask(bases)
     stay_index = np.where(flops, bases + (2 * nbase + 1) * nbase, bases + 2 * nbase * bases)
     from_base = (bases + flops * nbase)[:-1]

@@ -1,0 +1,86 @@
+"""Remapping reads to their references with a flip-flop model -- the flow of
+taiyaki/prepare_mapping_funcs.py:24-109 (`oneread_remap`) behind bin/prepare_mapped_reads.py,
+for raw signals passed in (fast5 reading is out of scope): trim and standardise with the
+per-read parameters, run the network over the whole read, align the reference to the
+transition scores (csrc/remap.cu), turn the block path into Ref_to_signal.
+
+`remap_reads` does this for a list of reads with ONE remapping launch for all of them (one
+CTA per read) instead of one worker process per read."""
+import enum
+
+import numpy as np
+import torch
+
+from . import flipflop_remap, helpers
+from .signal_mapping import SignalMapping
+
+
+class RemapResult(enum.Enum):
+    """Possible results of remapping a read (prepare_mapping_funcs.py:14-21)."""
+    SUCCESS = 'Success!'
+    READ_ID_INFO_NOT_FOUND = 'No information for read id found in file.'
+    NO_REF_FOUND = 'No fasta reference found.'
+    NO_PARAMS = 'No per-read params provided.'
+    NETWORK_ERROR = 'Failure applying basecall network to remap read.'
+    REF_TOO_LONG = 'Reference exceeded maximum allowed read length.'
+
+
+def trim_bounds(nsample, trim_start, trim_end):
+    """(signalstart, signalend_exc) of taiyaki/signal.py:77-95 (set_trim_absolute)."""
+    if trim_start < 0 or trim_end < 0:
+        raise Exception("Can't trim a negative amount off the end of a signal vector.")
+    if trim_start + trim_end >= nsample:
+        trim_start, trim_end = 0, 0
+    return trim_start, nsample - trim_end
+
+
+def remap_reads(reads, model, per_read_params_dict, alphabet_info, max_read_length=None,
+                localpen=0.0, model_stride=None):
+    """`reads`: list of dicts with read_id, dacs (untrimmed int16), offset, range,
+    digitisation and ref (reference string, possibly with modified bases, or None).
+    Returns [(read dictionary or None, RemapResult)] in the same order -- what
+    `oneread_remap` returns per read."""
+    device = helpers.get_model_device(model)
+    if model_stride is None:
+        model_stride = helpers.guess_model_stride(model)
+    results = [None] * len(reads)
+    todo = []
+    with torch.no_grad():
+        for i, read in enumerate(reads):
+            read_ref = read.get('ref')
+            if read_ref is None:
+                results[i] = (None, RemapResult.NO_REF_FOUND)
+                continue
+            if max_read_length is not None and len(read_ref) > max_read_length:
+                results[i] = (None, RemapResult.REF_TOO_LONG)
+                continue
+            params = per_read_params_dict.get(read['read_id'])
+            if params is None:
+                results[i] = (None, RemapResult.NO_PARAMS)
+                continue
+            dacs = np.asarray(read['dacs'])
+            start, end = trim_bounds(len(dacs), int(params['trim_start']), int(params['trim_end']))
+            try:
+                current = (dacs[start:end] + read['offset']) * read['range'] / read['digitisation']
+                standardized = ((current - params['shift']) / params['scale']).astype(np.float32)
+                signal = torch.as_tensor(standardized[:, None, None]).to(device)
+                transweights = model(signal)[:, 0, :]
+            except Exception:
+                results[i] = (None, RemapResult.NETWORK_ERROR)
+                continue
+            can_read_ref = alphabet_info.collapse_sequence(read_ref)
+            todo.append((i, transweights, can_read_ref, start, params))
+        if todo:
+            aligned = flipflop_remap.flipflop_remap_batch(
+                [t[1] for t in todo], [t[2] for t in todo], alphabet=alphabet_info.can_bases,
+                localpen=localpen)
+            for (i, _, _, start, params), (_, path) in zip(todo, aligned):
+                read = reads[i]
+                int_ref = SignalMapping.get_integer_reference(read['ref'], alphabet_info.alphabet)
+                sig_mapping = SignalMapping.from_remapping_path(
+                    path, int_ref, model_stride, np.asarray(read['dacs']), start,
+                    read_id=read['read_id'], shift_frompA=params['shift'],
+                    scale_frompA=params['scale'], range=read['range'], offset=read['offset'],
+                    digitisation=read['digitisation'])
+                results[i] = (sig_mapping.get_read_dictionary(), RemapResult.SUCCESS)
+    return results

@@ -87,6 +87,55 @@ class SignalMapping:
     def reflen(self):
         return len(self.Reference)
 
+    @staticmethod
+    def get_integer_reference(string_reference, alphabet):
+        """Reference string -> int16 labels (signal_mapping.py:191-208)."""
+        return np.array([alphabet.index(i) for i in string_reference], dtype=np.int16)
+
+    @staticmethod
+    def get_reftosignal(signalpos_to_refpos, reflen, siglen):
+        """Reference position -> first signal sample, from a per-sample vector of reference
+        positions with -1 for unmapped samples (signal_mapping.py:211-263): length reflen + 1;
+        leading -1s for an unmapped start, trailing siglen + 1 for an unmapped end."""
+        rts_dt = np.int32
+        signalpos_to_refpos = np.asarray(signalpos_to_refpos)
+        valid_idxs = np.where(signalpos_to_refpos != -1)[0].astype(rts_dt)
+        if len(valid_idxs) == 0:
+            return -1 * np.ones(reflen + 1, dtype=rts_dt)
+        valid_refpos = signalpos_to_refpos[valid_idxs]
+        move_pos = np.concatenate([[1, ], np.diff(valid_refpos)])
+        ref_to_sig = np.repeat(valid_idxs, move_pos)
+        ref_to_sig = np.concatenate([ref_to_sig, np.array([valid_idxs[-1] + 1, ], dtype=rts_dt)])
+        if valid_refpos[0] > 0:
+            ref_to_sig = np.concatenate([-1 * np.ones(valid_refpos[0], dtype=rts_dt), ref_to_sig])
+        if reflen + 1 > len(ref_to_sig):
+            ref_to_sig = np.append(ref_to_sig, (siglen + 1) * np.ones(
+                reflen + 1 - len(ref_to_sig), dtype=rts_dt))
+        return ref_to_sig
+
+    @classmethod
+    def from_remapping_path(cls, sigtoref_downsampled, reference, stride, untrimmed_dacs,
+                            signalstart=0, **read_attrs):
+        """Mapping from a remapping path over network blocks (signal_mapping.py:265-320):
+        path element n belongs to sample stride * n - 1 + signalstart of the untrimmed
+        signal.  The reference passes a `Signal` object; here its two fields used
+        (`untrimmed_dacs`, `signalstart`) and the scaling attributes are passed directly."""
+        rts_dt = np.int32
+        sigtoref_downsampled = np.asarray(sigtoref_downsampled)
+        fullsigtoref = np.full(len(untrimmed_dacs), -1, dtype=rts_dt)
+        siglocs = np.arange(len(sigtoref_downsampled), dtype=rts_dt) * stride - 1 + signalstart
+        f = np.logical_and(np.greater_equal(siglocs, 0), np.less(siglocs, len(fullsigtoref)))
+        fullsigtoref[siglocs[f]] = sigtoref_downsampled[f]
+        ref_to_sig = cls.get_reftosignal(fullsigtoref, reference.shape[0], len(untrimmed_dacs))
+        return cls(untrimmed_dacs, ref_to_sig, reference, **read_attrs)
+
+    def get_read_dictionary(self):
+        """Fields as the mapped-signal writers take them (signal_mapping.py:322-345)."""
+        return {'Dacs': self.Dacs, 'Ref_to_signal': self.Ref_to_signal, 'Reference': self.Reference,
+                'read_id': self.read_id, 'shift_frompA': self.shift_frompA,
+                'scale_frompA': self.scale_frompA, 'range': self.range, 'offset': self.offset,
+                'digitisation': self.digitisation}
+
     def get_mapped_dacs_region(self):
         """(first, last) mapped sample (signal_mapping.py:208-225); cached: the arrays of a
         read do not change while it is being sampled from."""

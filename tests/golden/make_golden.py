@@ -460,6 +460,18 @@ def make_remap():
         out[tag + '_localpen'] = np.float64(pen)
         out[tag + '_score'] = np.float64(score)
         out[tag + '_path'] = path.astype(np.int32)
+        # block path -> Ref_to_signal: the arithmetic of SignalMapping.from_remapping_path
+        # (signal_mapping.py:303-318) with the reference's own get_reftosignal; stride 5, a
+        # signal trimmed by 7 samples at the start, 13 spare samples at the end
+        from taiyaki.signal_mapping import SignalMapping as RefSM
+        stride, signalstart = 5, 7
+        nd = T * stride + signalstart + 13
+        full = np.full(nd, -1, dtype=np.int32)
+        siglocs = np.arange(len(path), dtype=np.int32) * stride - 1 + signalstart
+        f = np.logical_and(siglocs >= 0, siglocs < nd)
+        full[siglocs[f]] = path[f]
+        out[tag + '_reftosig'] = RefSM.get_reftosignal(full, len(seq), nd)
+        out[tag + '_reftosig_cfg'] = np.array([stride, signalstart, nd])
     # unit-test tables: alphabet AB, 12 transitions; expected values are the test's own
     lt = np.zeros((6, 12), dtype='f4')
     for t, k in enumerate((8, 10, 6, 5, 1, 0)):

@@ -47,6 +47,30 @@ def test_remap_indices_mirror(g):
     assert list(step) == [8, 6, 1] and list(stay) == [0, 10, 5, 0]
 
 
+def test_path_to_ref_to_signal_matches_reference(g):
+    """Block path -> Ref_to_signal (from_remapping_path / get_reftosignal) against the
+    reference's get_reftosignal on the golden paths: global, clipped at either end."""
+    from taiyaki_b200.signal_mapping import SignalMapping
+    from taiyaki_b200.mapped_signal_files import check_read
+    nclipped = 0
+    for tag in CASES:
+        stride, signalstart, nd = (int(x) for x in g[tag + '_reftosig_cfg'])
+        seq = str(g[tag + '_seq'])
+        ref = SignalMapping.get_integer_reference(seq, 'ACGT')
+        sm = SignalMapping.from_remapping_path(g[tag + '_path'], ref, stride,
+                                               np.zeros(nd, dtype=np.int16), signalstart, read_id=tag)
+        assert sm.Ref_to_signal.dtype == np.int32
+        np.testing.assert_array_equal(sm.Ref_to_signal, g[tag + '_reftosig'])
+        assert check_read(sm) == 'pass'
+        nclipped += int((g[tag + '_path'] == -1).any())
+        d = sm.get_read_dictionary()
+        assert sorted(d) == sorted(['Dacs', 'Ref_to_signal', 'Reference', 'read_id', 'shift_frompA',
+                                    'scale_frompA', 'range', 'offset', 'digitisation'])
+    assert nclipped >= 3
+    # a fully clipped read maps nothing (signal_mapping.py:241-243)
+    np.testing.assert_array_equal(SignalMapping.get_reftosignal(np.full(10, -1), 3, 10), [-1] * 4)
+
+
 # ------------------------------------------------------------------ GPU
 
 @pytest.fixture(scope='module')
@@ -134,3 +158,59 @@ def test_remap_full_size(dev, T, L, pen):
     else:
         gscore, _ = flipflop_remap.flipflop_remap(scores, seq, localpen=1e30)
         assert score >= gscore
+
+
+@pytest.mark.gpu
+def test_remap_reads_driver(dev):
+    """prepare_mapping_funcs.remap_reads on a random-weight network: per read the result
+    equals the composition network -> oracle alignment -> from_remapping_path on the same
+    transition scores; the reference's failure categories are reported."""
+    from oracle import oracle
+    from taiyaki_b200 import helpers, prepare_mapping_funcs
+    from taiyaki_b200.alphabet import AlphabetInfo
+    from taiyaki_b200.mapped_signal_files import check_read
+    from taiyaki_b200.prepare_mapping_funcs import RemapResult
+    from taiyaki_b200.signal_mapping import SignalMapping
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    torch.manual_seed(4)
+    ai = AlphabetInfo('ACGTZ', 'ACGTC', ['5mC'])
+    model = helpers.load_model(os.path.join(root, 'models', 'mLstm_flipflop.py'),
+                               model_metadata={'reverse': False, 'standardize': True}, stride=5,
+                               winlen=19, insize=1, size=64,
+                               alphabet_info=AlphabetInfo('ACGT', 'ACGT')).to(dev)
+    rng = np.random.RandomState(9)
+    reads, params = [], {}
+    for i, (n, L) in enumerate(((6000, 500), (3011, 200), (4500, 60))):
+        rid = 'read%d' % i
+        ref = ''.join('ACGTZ'[b] for b in rng.choice(5, size=L, p=[.25, .15, .25, .25, .1]))
+        reads.append({'read_id': rid, 'dacs': rng.randint(300, 700, size=n).astype(np.int16),
+                      'offset': 10.0, 'range': 1400.0, 'digitisation': 8192.0, 'ref': ref})
+        params[rid] = {'trim_start': 50 * i, 'trim_end': 20, 'shift': 85.0, 'scale': 14.0}
+    reads.append({'read_id': 'noref', 'dacs': reads[0]['dacs'], 'offset': 0.0, 'range': 1.0,
+                  'digitisation': 1.0, 'ref': None})
+    reads.append(dict(reads[0], read_id='noparams'))
+    reads.append(dict(reads[0], read_id='long', ref='ACGT' * 300))
+    params['long'] = params['read0']
+    res = prepare_mapping_funcs.remap_reads(reads, model, params, ai, max_read_length=1000, localpen=0.0)
+    assert [r[1] for r in res] == [RemapResult.SUCCESS] * 3 + [
+        RemapResult.NO_REF_FOUND, RemapResult.NO_PARAMS, RemapResult.REF_TOO_LONG]
+    assert all(r[0] is None for r in res[3:])
+    for read, (d, _) in zip(reads[:3], res[:3]):
+        p = params[read['read_id']]
+        dacs = read['dacs']
+        start, end = p['trim_start'], len(dacs) - p['trim_end']
+        current = (dacs[start:end] + read['offset']) * read['range'] / read['digitisation']
+        sig = ((current - p['shift']) / p['scale']).astype(np.float32)
+        with torch.no_grad():
+            trans = model(torch.tensor(sig[:, None, None], device=dev))[:, 0].cpu().numpy()
+        can = ai.collapse_sequence(read['ref'])
+        step, stay = oracle.remap_indices(np.array(['ACGT'.find(b) for b in can]), 4)
+        _, opath = oracle.map_to_crf_viterbi(trans, step, stay, 0.0)
+        want = SignalMapping.from_remapping_path(
+            opath, SignalMapping.get_integer_reference(read['ref'], ai.alphabet), 5, dacs, start)
+        np.testing.assert_array_equal(d['Ref_to_signal'], want.Ref_to_signal)
+        np.testing.assert_array_equal(d['Reference'], want.Reference)
+        assert d['Reference'].max() == 4 and d['read_id'] == read['read_id']
+        np.testing.assert_array_equal(d['Dacs'], dacs)
+        sm = SignalMapping(**d)
+        assert check_read(sm) == 'pass' and sm.scale_frompA == 14.0
