@@ -2,7 +2,7 @@
 """Short workload for ncu: each hot kernel a few times at BASELINE config A
 (nblk=800, N=64, S=40, H=256).  Usage under gpurun:
   ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 2 \
-      -o gpurun_out/prof python tools/profile_target.py [crf|logz|rnn]"""
+      -o gpurun_out/prof python tools/profile_target.py [crf|logz|rnn|gru|aux|remap]"""
 import os
 import sys
 
@@ -39,6 +39,12 @@ for _ in range(reps):
                              layers.Convolution(16, 256, 19, stride=5, fun=swish)]).to(dev)
         xin = torch.randn(4000, N, 1, device=dev, requires_grad=True)
         net(xin).sum().backward()
+    if 'remap' in which:    # remapping DP: 148 reads of 8000 blocks x 3500 positions, one launch
+        from taiyaki_b200 import flipflop_remap
+        rng = np.random.RandomState(1)
+        rseqs = [''.join('ACGT'[b] for b in rng.randint(0, 4, size=3500)) for _ in range(148)]
+        rscores = [torch.randn(8000, 40, device=dev) for _ in range(148)]
+        flipflop_remap.flipflop_remap_batch(rscores, rseqs)
     if 'gru' in which:
         torch.manual_seed(0)
         np.random.seed(0)
