@@ -109,6 +109,32 @@ def test_flow_from_golden_paths_cpu(g, tag):
         assert max(abs(ord(a) - ord(b)) for a, b in zip(q, ref_q)) <= 1
 
 
+def _normalisation_cases():
+    rng = np.random.RandomState(0)
+    for n in (62001, 62000, 5, 2, 1001):
+        x = 90 + 12 * rng.standard_normal(n)
+        x[::7] = np.round(x[::7])               # ties around the median
+        yield x
+
+
+@pytest.mark.parametrize('device', ['cpu', pytest.param('cuda:0', marks=pytest.mark.gpu)])
+def test_normalisation_on_device_is_numpy_s(device):
+    """Median / MAD normalisation by sorting on the device against the numpy code of
+    bin/basecall.py:74-87 on float64 signals: bit-identical, odd and even lengths, reversed,
+    and with per-read shift / scale."""
+    from taiyaki_b200 import basecall
+    for x in _normalisation_cases():
+        for rev in (False, True):
+            want = basecall.normalise_signal(x, rev, None)
+            got = basecall.normalise_signal_device(x, device, rev, None)
+            assert got.dtype == torch.float32 and want.dtype == np.float32
+            np.testing.assert_array_equal(got.cpu().numpy(), want)
+        p = {'shift': 83.7, 'scale': 15.28}
+        np.testing.assert_array_equal(
+            basecall.normalise_signal_device(x, device, True, p).cpu().numpy(),
+            basecall.normalise_signal(x, True, p))
+
+
 # ------------------------------------------------------------------ GPU
 
 @pytest.fixture(scope='module')
