@@ -27,10 +27,31 @@ def flipflop_viterbi(scores, _never_use_cupy=False):
     return fwd, traceback, path
 
 
+@torch.no_grad()
 def flipflop_make_trans(scores, _never_use_cupy=False):
     """Posterior transition probabilities (not logs) of [T, N, S] scores: the
     derivative of the log-partition function with respect to the scores, which
-    is what the partition-function posterior kernel writes."""
+    is what the partition-function posterior kernel writes.  Called directly (no
+    autograd graph), so it behaves the same inside `torch.no_grad()` blocks."""
+    _lib.require_cuda(scores, 'scores')
+    lib = _lib.lib()
+    T, N, S = scores.shape
+    nbase = flipflopfings.nbase_flipflop(S)
+    x = scores.detach().float().contiguous()
+    dev = x.device
+    logz = torch.empty(N, dtype=torch.float32, device=dev)
+    trans = torch.empty(T, N, S, dtype=torch.float32, device=dev)
+    ws = _lib.workspace(lib.ty_flipflop_logz_workspace_bytes(nbase, T, N), dev)
+    rc = lib.ty_flipflop_logz(_lib.ptr(x), S, T, N, nbase, 1.0, _lib.ptr(logz), 1.0,
+                              _lib.ptr(trans), S, 0, _lib.ptr(ws), ws.numel(),
+                              _lib.stream_ptr(dev))
+    _lib.check(rc, 'ty_flipflop_logz')
+    _lib.count_launches(2)
+    return trans
+
+
+def _flipflop_make_trans_autograd(scores):
+    """The same through autograd of `layers.flipflop_logpartition` (kept for the tests)."""
     x = scores.detach().float().requires_grad_()
     with torch.enable_grad():
         logz = layers.flipflop_logpartition(x).sum()
