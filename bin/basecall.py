@@ -26,6 +26,7 @@ if ROOT not in sys.path:
 
 from taiyaki_b200 import basecall, basecall_helpers, helpers  # noqa: E402
 from taiyaki_b200.flipflopfings import nstate_flipflop  # noqa: E402
+from taiyaki_b200.prepare_mapping_funcs import get_per_read_params_dict_from_tsv  # noqa: E402
 
 
 def auto_bool(v):
@@ -68,24 +69,6 @@ def get_parser():
     p.add_argument('input_folder', help='Directory of <read_id>.npy signals, or one .npz')
     p.add_argument('model', help='Model checkpoint file to use for basecalling')
     return p
-
-
-def get_per_read_params_dict_from_tsv(input_file):
-    """UUID -> {trim_start, trim_end, shift, scale}
-    (taiyaki/prepare_mapping_funcs.py:148-177)."""
-    out = {}
-    with open(input_file) as fh:
-        header = fh.readline().rstrip('\n').split('\t')
-        col = {name: header.index(name) for name in ('UUID', 'trim_start', 'trim_end', 'shift', 'scale')}
-        for line in fh:
-            f = line.rstrip('\n').split('\t')
-            try:
-                out[f[col['UUID']]] = {'trim_start': int(f[col['trim_start']]),
-                                       'trim_end': int(f[col['trim_end']]),
-                                       'shift': float(f[col['shift']]), 'scale': float(f[col['scale']])}
-            except Exception:
-                sys.stderr.write('Warning: ignoring incorrect line {} in {}\n'.format(f, input_file))
-    return out
 
 
 def iterate_signals(input_folder, limit=None, strand_list=None):

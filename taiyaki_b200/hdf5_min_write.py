@@ -1,17 +1,21 @@
-"""Test-only writer of the HDF5 subset the batched mapped-signal format uses
+"""Minimal writer of the HDF5 subset the batched mapped-signal format uses
 (taiyaki/mapped_signal_files.py:562-679 through h5py's default settings): superblock 0,
-version-1 object headers, old-style groups (B-tree + SNOD + local heap), chunked datasets
-with shuffle + deflate, variable-length strings in a global heap collection, scalar
-attributes.  Written from the HDF5 file-format specification, independently of
-taiyaki_b200/hdf5_min.py's parsing code, to exercise the reader on layouts the reference's
-per-read fixture files do not contain."""
+version-1 object headers, old-style groups (B-tree + SNOD + local heap), chunked 1-D
+datasets with shuffle + deflate, variable-length strings in a global heap collection,
+scalar attributes.  Written from the HDF5 file-format specification, independently of
+hdf5_min.py's parsing code.  It serves `mapped_signal_files.BatchHDF5Writer` and the tests
+of the reader on layouts the reference's per-read fixture files do not contain.
+
+Status: files are read back by hdf5_min.py; this image has no libhdf5 / h5py, so they have
+NOT been opened with the HDF5 library itself.  Limits: one global heap collection of 1 MiB
+for all strings (read ids), groups of up to a few thousand links in a single B-tree level."""
 import struct
 import zlib
 
 import numpy as np
 
 UNDEF = 0xFFFFFFFFFFFFFFFF
-GCOL_BYTES = 1 << 16
+GCOL_BYTES = 1 << 20
 
 
 def _pad8(b):
@@ -140,7 +144,7 @@ class Writer:
             coll += struct.pack('<HHIQ', i + 1, 1, 0, len(raw)) + _pad8(raw)
         head = b'GCOL' + struct.pack('<B3xQ', 1, GCOL_BYTES)
         free = GCOL_BYTES - len(head) - len(coll)
-        assert free >= 16, 'global heap collection of the test writer is full'
+        assert free >= 16, 'global heap collection of the minimal writer is full'
         coll += struct.pack('<HHIQ', 0, 0, 0, free)
         self.buf[self.gcol:self.gcol + len(head) + len(coll)] = head + coll
         sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
@@ -151,23 +155,29 @@ class Writer:
             fh.write(bytes(self.buf))
 
 
-def write_batched_mapped_signal_file(filename, reads, batch_size=3, chunk=1000):
-    """The layout BatchHDF5Writer produces: /Batches/Batch_n/<field>[, <field>_lengths]."""
+def write_batched_mapped_signal_file(filename, reads, batch_size=3, chunk=1000,
+                                     alphabet=('ACGT', 'ACGT', '')):
+    """The layout BatchHDF5Writer produces: /Batches/Batch_n/<field>[, <field>_lengths].
+    `reads`: SignalMapping objects or read dictionaries; `alphabet`: (alphabet,
+    collapse_alphabet, newline-joined modified-base long names)."""
+    def field(r, k):
+        return r[k] if isinstance(r, dict) else getattr(r, k)
     w = Writer()
     batches = {}
     for b, first in enumerate(range(0, len(reads), batch_size)):
         part = reads[first:first + batch_size]
         links = {}
         for k, dt in (('Dacs', np.int16), ('Ref_to_signal', np.int32), ('Reference', np.int16)):
-            links[k] = w.dataset(np.concatenate([getattr(r, k) for r in part]).astype(dt), chunk)
+            links[k] = w.dataset(np.concatenate([field(r, k) for r in part]).astype(dt), chunk)
             links[k + '_lengths'] = w.dataset(
-                np.array([len(getattr(r, k)) for r in part], dtype=np.int32), chunk)
+                np.array([len(field(r, k)) for r in part], dtype=np.int32), chunk)
         for k in ('shift_frompA', 'scale_frompA', 'range', 'offset', 'digitisation'):
-            links[k] = w.dataset(np.array([getattr(r, k) for r in part], dtype=np.float64), chunk)
-        links['read_id'] = w.dataset([r.read_id for r in part], chunk)
+            links[k] = w.dataset(np.array([field(r, k) for r in part], dtype=np.float64), chunk)
+        links['read_id'] = w.dataset([field(r, 'read_id') for r in part], chunk)
         batches['Batch_%d' % b] = w.group(links, per_node=5)[0]
-    top = {'Batches': w.group(batches)[0],
-           'read_ids': w.dataset([r.read_id for r in reads], chunk)}
-    root = w.group(top, attrs=[('version', np.int64(8)), ('alphabet', 'ACGT'),
-                               ('collapse_alphabet', 'ACGT'), ('mod_long_names', '')])
+    top = {'Batches': w.group(batches, per_node=max(8, len(batches)))[0]}
+    if len(reads) > 0:
+        top['read_ids'] = w.dataset([field(r, 'read_id') for r in reads], chunk)
+    root = w.group(top, attrs=[('version', np.int64(8)), ('alphabet', alphabet[0]),
+                               ('collapse_alphabet', alphabet[1]), ('mod_long_names', alphabet[2])])
     w.close(*root, filename)

@@ -9,7 +9,7 @@ the same file layouts (docs/FILE_FORMATS.md:40-88):
   both     : root attributes version, alphabet, collapse_alphabet, mod_long_names
 
 Reads come back as `signal_mapping.SignalMapping`, what `chunk_selection` and the device
-read store consume.  Writing (prepare_mapped_reads.py) is not on this path."""
+read store consume.  `BatchHDF5Writer` writes the batched layout through hdf5_min_write.py."""
 import inspect
 
 import numpy as np
@@ -199,5 +199,46 @@ def HDF5Reader(filename, load_in_mem=False):
     return PerReadHDF5Reader(filename, load_in_mem)
 
 
-# module-level swap point, as in the reference (mapped_signal_files.py:729-731)
+class BatchHDF5Writer:
+    """Batched mapped-signal file writer with the reference's interface
+    (mapped_signal_files.py:562-679): `write_read(readdict)` with the dictionaries of
+    `SignalMapping.get_read_dictionary`, `close()`, context manager.  Reads are collected
+    and laid out by hdf5_min_write.py when the file is closed (see its status note)."""
+
+    def __init__(self, filename, alphabet_info, batch_size=25000):
+        self.filename = filename
+        self.alphabet_info = alphabet_info
+        self.batch_size = batch_size
+        self.read_ids = []
+        self._reads = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *args):
+        self.close()
+
+    def write_read(self, readdict):
+        self.read_ids.append(readdict['read_id'])
+        self._reads.append(readdict)
+
+    def close(self):
+        from .hdf5_min_write import write_batched_mapped_signal_file
+        ai = self.alphabet_info
+        longest = max([len(r['Dacs']) for r in self._reads] + [1])
+        write_batched_mapped_signal_file(
+            self.filename, self._reads, batch_size=self.batch_size,
+            chunk=int(min(max(longest, 1 << 16), 1 << 20)),
+            alphabet=(ai.alphabet, ai.collapse_alphabet, '\n'.join(ai.mod_long_names or [])))
+
+
+def HDF5Writer(filename, alphabet_info, batch_format=True):
+    """mapped_signal_files.py:708-726; only the batched format is written here."""
+    if not batch_format:
+        raise NotImplementedError('the per-read format (libver v108 headers) is not written here')
+    return BatchHDF5Writer(filename, alphabet_info)
+
+
+# module-level swap points, as in the reference (mapped_signal_files.py:729-731)
 MappedSignalReader = HDF5Reader
+MappedSignalWriter = HDF5Writer

@@ -7,6 +7,7 @@ transition scores (csrc/remap.cu), turn the block path into Ref_to_signal.
 `remap_reads` does this for a list of reads with ONE remapping launch for all of them (one
 CTA per read) instead of one worker process per read."""
 import enum
+import sys
 
 import numpy as np
 import torch
@@ -23,6 +24,62 @@ class RemapResult(enum.Enum):
     NO_PARAMS = 'No per-read params provided.'
     NETWORK_ERROR = 'Failure applying basecall network to remap read.'
     REF_TOO_LONG = 'Reference exceeded maximum allowed read length.'
+
+
+def get_per_read_params_dict_from_tsv(input_file):
+    """UUID -> {trim_start, trim_end, shift, scale} from a per-read parameter .tsv
+    (prepare_mapping_funcs.py:148-177)."""
+    out = {}
+    with open(input_file) as fh:
+        header = fh.readline().rstrip('\n').split('\t')
+        col = {name: header.index(name) for name in ('UUID', 'trim_start', 'trim_end', 'shift', 'scale')}
+        for line in fh:
+            f = line.rstrip('\n').split('\t')
+            try:
+                out[f[col['UUID']]] = {'trim_start': int(f[col['trim_start']]),
+                                       'trim_end': int(f[col['trim_end']]),
+                                       'shift': float(f[col['shift']]), 'scale': float(f[col['scale']])}
+            except Exception:
+                sys.stderr.write('Warning: ignoring incorrect line {} in {}\n'.format(f, input_file))
+    return out
+
+
+def fasta_file_to_dict(fasta_file_name):
+    """Record id (up to the first blank) -> sequence (taiyaki/bio.py fasta_file_to_dict)."""
+    references, name, parts = {}, None, []
+    with open(fasta_file_name) as fh:
+        for line in fh:
+            line = line.strip()
+            if line.startswith('>'):
+                if name is not None:
+                    references[name] = ''.join(parts)
+                name, parts = line[1:].split()[0], []
+            elif line:
+                parts.append(line)
+    if name is not None:
+        references[name] = ''.join(parts)
+    return references
+
+
+def generate_output_from_results(results, output, alphabet_info, verbose=True, batch_format=True):
+    """Write the successful remappings to a mapped-signal file and report the failures by
+    category (prepare_mapping_funcs.py:112-145)."""
+    from collections import defaultdict
+    from .mapped_signal_files import MappedSignalWriter
+    err_types = defaultdict(int)
+    count = 0
+    with MappedSignalWriter(output, alphabet_info, batch_format) as msw:
+        for resultdict, mesg in results:
+            if resultdict is None:
+                err_types[mesg] += 1
+            else:
+                count += 1
+                msw.write_read(resultdict)
+    sys.stderr.write('* {} reads mapped successfully\n'.format(count))
+    for result, n_errs in err_types.items():
+        sys.stderr.write('* {} reads failed to produce remapping results due to: {}\n'.format(
+            n_errs, getattr(result, 'value', result)))
+    return count, dict(err_types)
 
 
 def trim_bounds(nsample, trim_start, trim_end):

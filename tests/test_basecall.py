@@ -266,7 +266,8 @@ def test_driver_end_to_end(dev, tmp_path):
     bc.main(['--chunk_size', '400', '--overlap', '40', '--max_concurrent_chunks', '4', '--fastq',
              '--output', str(outfile), '--reads_per_batch', '3', str(folder), ckpt])
     lines = outfile.read_text().splitlines()
-    assert len(lines) == 4 * 5
+    assert len(lines) == 4 * sum(1 for r in pooled[:-1] if len(r[1]) > 0)   # empty calls are not written
     called = {lines[i][1:]: (lines[i + 1], lines[i + 3]) for i in range(0, len(lines), 4)}
     for rid, call, q, _ in pooled[:-1]:
-        assert _close(called[rid][0], call, 0.97) and len(called[rid][1]) == len(called[rid][0])
+        if rid in called:
+            assert _close(called[rid][0], call, 0.97) and len(called[rid][1]) == len(called[rid][0])

@@ -95,10 +95,10 @@ def test_train_entry_point_loads_hdf5(tmp_path):
 
 def test_batched_mapped_signal_file(g, tmp_path):
     """The batched layout (the reference writer's default: concatenated arrays per batch,
-    chunked + shuffle + deflate, variable-length read ids) written by the test-only writer
+    chunked + shuffle + deflate, variable-length read ids) written by the minimal writer
     from the real reads and read back through BatchHDF5Reader."""
     from taiyaki_b200 import mapped_signal_files
-    from .hdf5_write_min import write_batched_mapped_signal_file
+    from taiyaki_b200.hdf5_min_write import write_batched_mapped_signal_file
     reads = golden_reads(g)
     fn = str(tmp_path / 'batched.hdf5')
     write_batched_mapped_signal_file(fn, reads, batch_size=3, chunk=7000)
@@ -118,6 +118,32 @@ def test_batched_mapped_signal_file(g, tmp_path):
         pick = [reads[5].read_id, reads[0].read_id]
         assert sorted(r.read_id for r in msr.reads(pick)) == sorted(pick)
         np.testing.assert_array_equal(msr.get_read(reads[4].read_id).Dacs, reads[4].Dacs)
+
+
+def test_mapped_signal_writer_round_trip(g, tmp_path):
+    """MappedSignalWriter (read dictionaries in, batched file out) -> MappedSignalReader,
+    with a modified-base alphabet and one batch per two reads."""
+    from taiyaki_b200 import mapped_signal_files
+    from taiyaki_b200.alphabet import AlphabetInfo
+    reads = golden_reads(g)
+    fn = str(tmp_path / 'written.hdf5')
+    ai = AlphabetInfo('ACGTZY', 'ACGTCA', ['5mC', '6mA'])
+    with mapped_signal_files.MappedSignalWriter(fn, ai) as msw:
+        msw.batch_size = 2
+        for r in reads:
+            msw.write_read(r.get_read_dictionary())
+    with mapped_signal_files.MappedSignalReader(fn) as msr:
+        back = msr.get_alphabet_information()
+        assert (back.alphabet, back.collapse_alphabet, back.mod_long_names) == (
+            'ACGTZY', 'ACGTCA', ['5mC', '6mA'])
+        assert len(msr.batch_names) == 4 and msr.get_read_ids() == [r.read_id for r in reads]
+        for a, b in zip(msr.reads(), reads):
+            np.testing.assert_array_equal(a.Dacs, b.Dacs)
+            np.testing.assert_array_equal(a.Ref_to_signal, b.Ref_to_signal)
+            np.testing.assert_array_equal(a.Reference, b.Reference)
+            assert a.get_read_dictionary().keys() == b.get_read_dictionary().keys()
+    with pytest.raises(NotImplementedError):
+        mapped_signal_files.HDF5Writer(fn, ai, batch_format=False)
 
 
 def test_hdf5_errors(tmp_path):

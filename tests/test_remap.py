@@ -71,6 +71,63 @@ def test_path_to_ref_to_signal_matches_reference(g):
     np.testing.assert_array_equal(SignalMapping.get_reftosignal(np.full(10, -1), 3, 10), [-1] * 4)
 
 
+def _write_remap_inputs(tmp_path, with_mods=True):
+    """Three raw reads (.npz), their per-read parameters, references and a strand list."""
+    rng = np.random.RandomState(9)
+    folder = tmp_path / 'raw'
+    folder.mkdir()
+    tsv = ['UUID\ttrim_start\ttrim_end\tshift\tscale']
+    fasta, reads = [], {}
+    for i, (n, L) in enumerate(((6000, 500), (3011, 200), (4500, 60))):
+        rid = 'read%d' % i
+        letters = 'ACGTZ' if with_mods else 'ACGT'
+        ref = ''.join(letters[b] for b in rng.randint(0, len(letters), size=L))
+        dacs = rng.randint(300, 700, size=n).astype(np.int16)
+        np.savez(str(folder / (rid + '.npz')), dacs=dacs, offset=10.0, range=1400.0, digitisation=8192.0)
+        tsv.append('%s\t%d\t20\t85.0\t14.0' % (rid, 50 * i))
+        fasta += ['>%s some description' % rid, ref[:70], ref[70:]]
+        reads[rid] = (dacs, ref)
+    np.savez(str(folder / 'orphan.npz'), dacs=reads['read0'][0], offset=0.0, range=1.0, digitisation=1.0)
+    (tmp_path / 'params.tsv').write_text('\n'.join(tsv + ['broken\tline']) + '\n')
+    (tmp_path / 'refs.fa').write_text('\n'.join(fasta) + '\n')
+    return folder, tmp_path / 'params.tsv', tmp_path / 'refs.fa', reads
+
+
+def _load_cli(name):
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bin'))
+    return importlib.import_module(name)
+
+
+def test_prepare_mapped_reads_host_pieces(tmp_path):
+    """Inputs of bin/prepare_mapped_reads.py: per-read parameter table, fasta references,
+    raw read iteration, the alphabet built from --mod (sorted like the reference's
+    do_reorder=True) and the trimming rule of taiyaki/signal.py:77-95."""
+    from taiyaki_b200 import prepare_mapping_funcs as pmf
+    cli = _load_cli('prepare_mapped_reads')
+    folder, tsv, fa, reads = _write_remap_inputs(tmp_path)
+    params = pmf.get_per_read_params_dict_from_tsv(str(tsv))
+    assert sorted(params) == ['read0', 'read1', 'read2']
+    assert params['read2'] == {'trim_start': 100, 'trim_end': 20, 'shift': 85.0, 'scale': 14.0}
+    refs = pmf.fasta_file_to_dict(str(fa))
+    assert {k: v for k, v in refs.items()} == {k: v[1] for k, v in reads.items()}
+    raw = list(cli.iterate_raw_reads(str(folder)))
+    assert [r['read_id'] for r in raw] == ['orphan', 'read0', 'read1', 'read2']
+    assert raw[1]['digitisation'] == 8192.0 and raw[1]['dacs'].dtype == np.int16
+    assert [r['read_id'] for r in cli.iterate_raw_reads(str(folder), limit=2)] == ['orphan', 'read0']
+    ai = cli.make_alphabet_info('ACGT', [['Z', 'C', '5mC'], ['Y', 'A', '6mA']])
+    assert (ai.alphabet, ai.collapse_alphabet, ai.mod_long_names) == ('AYCZGT', 'AACCGT', ['6mA', '5mC'])
+    assert ai.collapse_sequence('AZYT') == 'ACAT'
+    with pytest.raises(AssertionError):
+        cli.make_alphabet_info('ACGT', [['C', 'C', 'x']])
+    assert pmf.trim_bounds(1000, 100, 20) == (100, 980)
+    assert pmf.trim_bounds(100, 80, 30) == (0, 100)          # nothing would be left: no trim
+    args = cli.get_parser().parse_args(['--localpen', '1.5', '--max_read_length', 'None', '--mod', 'Z', 'C',
+                                        '5mC', 'in', 'p.tsv', 'out.hdf5', 'm.checkpoint', 'r.fa'])
+    assert args.localpen == 1.5 and args.max_read_length is None and args.mod == [['Z', 'C', '5mC']]
+
+
 # ------------------------------------------------------------------ GPU
 
 @pytest.fixture(scope='module')
@@ -214,3 +271,36 @@ def test_remap_reads_driver(dev):
         np.testing.assert_array_equal(d['Dacs'], dacs)
         sm = SignalMapping(**d)
         assert check_read(sm) == 'pass' and sm.scale_frompA == 14.0
+
+
+@pytest.mark.gpu
+def test_prepare_mapped_reads_cli(dev, tmp_path):
+    """bin/prepare_mapped_reads.py end to end: raw reads + parameters + references + a
+    checkpoint -> a batched mapped-signal file that the reader (and so train_flipflop.py)
+    loads; reads without parameters or reference are reported, not written."""
+    from taiyaki_b200 import helpers, mapped_signal_files
+    from taiyaki_b200.alphabet import AlphabetInfo
+    cli = _load_cli('prepare_mapped_reads')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    folder, tsv, fa, reads = _write_remap_inputs(tmp_path)
+    torch.manual_seed(4)
+    model = helpers.load_model(os.path.join(root, 'models', 'mLstm_flipflop.py'),
+                               model_metadata={'reverse': False, 'standardize': True}, stride=5,
+                               winlen=19, insize=1, size=64,
+                               alphabet_info=AlphabetInfo('ACGT', 'ACGT')).to(dev)
+    ckpt, _ = helpers.save_model(model, str(tmp_path))
+    out = str(tmp_path / 'mapped.hdf5')
+    count, errs = cli.main(['--mod', 'Z', 'C', '5mC', '--reads_per_batch', '2', str(folder), str(tsv),
+                            out, ckpt, str(fa)])
+    assert count == 3 and sum(errs.values()) == 1
+    with mapped_signal_files.MappedSignalReader(out) as msr:
+        ai = msr.get_alphabet_information()
+        assert (ai.alphabet, ai.collapse_alphabet, ai.mod_long_names) == ('ACZGT', 'ACCGT', ['5mC'])
+        assert sorted(msr.get_read_ids()) == ['read0', 'read1', 'read2'] and msr.check() == 'pass'
+        for read in msr.reads():
+            dacs, ref = reads[read.read_id]
+            np.testing.assert_array_equal(read.Dacs, dacs)
+            assert ''.join('ACZGT'[b] for b in read.Reference) == ref
+            assert read.scale_frompA == 14.0 and read.digitisation == 8192.0
+    with pytest.raises(SystemExit):          # refuses to overwrite
+        cli.main([str(folder), str(tsv), out, ckpt, str(fa)])
