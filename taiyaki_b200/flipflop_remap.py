@@ -26,7 +26,41 @@ def remap_indices(sequence, alphabet=DEFAULT_ALPHABET):
     return step_index, stay_index
 
 
+#: cap on the decision table (one byte per block x position) of one launch
+MAX_TABLE_BYTES = 8 << 30
+
+
+def launch_groups(table_bytes, cap=None):
+    """Split reads (by their T x M decision-table sizes, in order) into consecutive groups
+    whose tables fit `cap` bytes together; a read larger than the cap gets its own group."""
+    cap = MAX_TABLE_BYTES if cap is None else cap
+    groups, current, used = [], [], 0
+    for r, nbytes in enumerate(table_bytes):
+        if current and used + nbytes > cap:
+            groups.append(current)
+            current, used = [], 0
+        current.append(r)
+        used += nbytes
+    if current:
+        groups.append(current)
+    return groups
+
+
 def map_to_crf_viterbi_batch(scores_list, step_list, stay_list, localpen=LARGE_VAL):
+    """Align several reads, one launch per group of reads whose decision tables fit
+    MAX_TABLE_BYTES together (normally a single launch)."""
+    sizes = [int(s.shape[0]) * len(st) for s, st in zip(scores_list, stay_list)]
+    groups = launch_groups(sizes)
+    if len(groups) <= 1:
+        return _map_to_crf_viterbi_launch(scores_list, step_list, stay_list, localpen)
+    out = []
+    for grp in groups:
+        out += _map_to_crf_viterbi_launch([scores_list[r] for r in grp], [step_list[r] for r in grp],
+                                          [stay_list[r] for r in grp], localpen)
+    return out
+
+
+def _map_to_crf_viterbi_launch(scores_list, step_list, stay_list, localpen=LARGE_VAL):
     """Align several reads in one launch.  scores_list: [T_r, S] float arrays or tensors
     (host or device); step_list / stay_list: their index vectors.  Returns a list of
     (score, path[T_r + 1] int numpy array)."""

@@ -71,6 +71,14 @@ def test_path_to_ref_to_signal_matches_reference(g):
     np.testing.assert_array_equal(SignalMapping.get_reftosignal(np.full(10, -1), 3, 10), [-1] * 4)
 
 
+def test_launch_groups():
+    from taiyaki_b200.flipflop_remap import launch_groups
+    assert launch_groups([3, 3, 3], cap=10) == [[0, 1, 2]]
+    assert launch_groups([6, 6, 3, 20, 1, 1], cap=10) == [[0], [1, 2], [3], [4, 5]]
+    assert launch_groups([], cap=10) == []
+    assert launch_groups([8000 * 3500] * 148) == [list(range(148))]       # the benchmark batch: one launch
+
+
 def _write_remap_inputs(tmp_path, with_mods=True):
     """Three raw reads (.npz), their per-read parameters, references and a strand list."""
     rng = np.random.RandomState(9)
