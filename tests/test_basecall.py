@@ -109,6 +109,34 @@ def test_flow_from_golden_paths_cpu(g, tag):
         assert max(abs(ord(a) - ord(b)) for a, b in zip(q, ref_q)) <= 1
 
 
+def test_basecall_cli_host_pieces(tmp_path):
+    """bin/basecall.py: the reference's flags and defaults (bin/basecall.py:23-72), signal
+    iteration from a folder of .npy files or one .npz, --limit and a strand list."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bin'))
+    cli = importlib.import_module('basecall')
+    a = cli.get_parser().parse_args(['reads', 'model.checkpoint'])
+    assert (a.chunk_size, a.overlap, a.max_concurrent_chunks, a.posterior, a.fastq, a.temperature,
+            a.qscore_scale, a.qscore_offset, a.reverse, a.alphabet) == (
+                1000, 100, 128, True, False, 1.0, 1.0, 0.0, False, 'ACGT')
+    a = cli.get_parser().parse_args(['--fastq', '--posterior', 'false', '--chunk_size', '500', 'r', 'm'])
+    assert a.fastq is True and a.posterior is False and a.chunk_size == 500
+    folder = tmp_path / 'sig'
+    folder.mkdir()
+    for i in range(3):
+        np.save(str(folder / ('r%d.npy' % i)), np.arange(10 + i, dtype='f4'))
+    (folder / 'notes.txt').write_text('x')
+    got = list(cli.iterate_signals(str(folder)))
+    assert [g[0] for g in got] == ['r0', 'r1', 'r2'] and len(got[2][1]) == 12
+    assert [g[0] for g in cli.iterate_signals(str(folder), limit=2)] == ['r0', 'r1']
+    strands = tmp_path / 's.tsv'
+    strands.write_text('filename\tread_id\na\tr2\n')
+    assert [g[0] for g in cli.iterate_signals(str(folder), strand_list=str(strands))] == ['r2']
+    np.savez(str(tmp_path / 'all.npz'), x=np.zeros(4), y=np.ones(5))
+    assert [(k, len(v)) for k, v in cli.iterate_signals(str(tmp_path / 'all.npz'))] == [('x', 4), ('y', 5)]
+
+
 def _normalisation_cases():
     rng = np.random.RandomState(0)
     for n in (62001, 62000, 5, 2, 1001):
