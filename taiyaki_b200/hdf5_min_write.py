@@ -7,8 +7,10 @@ hdf5_min.py's parsing code.  It serves `mapped_signal_files.BatchHDF5Writer` and
 of the reader on layouts the reference's per-read fixture files do not contain.
 
 Status: files are read back by hdf5_min.py; this image has no libhdf5 / h5py, so they have
-NOT been opened with the HDF5 library itself.  Limits: one global heap collection of 1 MiB
-for all strings (read ids), groups of up to a few thousand links in a single B-tree level."""
+NOT been opened with the HDF5 library itself.  Node sizes and fan-outs follow the library's
+rules (symbol-table nodes of 2 x leaf-K entries, B-tree nodes padded to full size, chunk
+trees of at most 64 entries per node with as many levels as needed).  Limits: one global
+heap collection of 1 MiB for all strings (read ids), at most 256 links per group."""
 import struct
 import zlib
 
@@ -16,6 +18,8 @@ import numpy as np
 
 UNDEF = 0xFFFFFFFFFFFFFFFF
 GCOL_BYTES = 1 << 20
+CHUNK_K = 32          # chunk B-tree K (library default; superblock 0 does not store it)
+GROUP_LEAF_K, GROUP_INTERNAL_K = 4, 16      # written into the superblock
 
 
 def _pad8(b):
@@ -97,11 +101,7 @@ class Writer:
                 piece = np.frombuffer(piece, dtype='u1').reshape(-1, esize).T.tobytes()
             piece = zlib.compress(piece, 4)
             entries.append((len(piece), start, self.alloc(piece)))
-        node = b'TREE' + struct.pack('<BBHQQ', 1, 0, len(entries), UNDEF, UNDEF)
-        for size, start, addr in entries:
-            node += struct.pack('<IIQQ', size, 0, start, 0) + struct.pack('<Q', addr)
-        node += struct.pack('<IIQQ', 0, 0, ((n + chunk - 1) // chunk) * chunk, 0)
-        btree = self.alloc(node)
+        btree = self._chunk_btree(entries, ((n + chunk - 1) // chunk) * chunk)
         layout = struct.pack('<BBB', 3, 2, 2) + struct.pack('<Q', btree) + struct.pack('<II', chunk, esize)
         filters = b''
         nfilt = 0
@@ -114,6 +114,28 @@ class Writer:
         return self.header([(0x01, self.dataspace((n,))), (0x03, dt_msg), (0x0B, pipeline),
                             (0x08, layout)])
 
+    def _chunk_btree(self, entries, end_offset):
+        """Version-1 B-tree (node type 1) over (stored size, first element, address) chunk
+        records: at most 2K = 64 entries per node (the library's default K for chunk trees,
+        implied by superblock 0), nodes padded to their full size, as many levels as needed."""
+        def key(size, start):
+            return struct.pack('<IIQQ', size, 0, start, 0)
+        level, items = 0, [(size, start, addr) for size, start, addr in entries]
+        while True:
+            nodes = []
+            for i in range(0, len(items), 2 * CHUNK_K):
+                part = items[i:i + 2 * CHUNK_K]
+                nxt = items[i + 2 * CHUNK_K][1] if i + 2 * CHUNK_K < len(items) else end_offset
+                node = b'TREE' + struct.pack('<BBHQQ', 1, level, len(part), UNDEF, UNDEF)
+                for size, start, addr in part:
+                    node += key(size, start) + struct.pack('<Q', addr)
+                node += key(0, nxt)
+                node += bytes(24 + 2 * CHUNK_K * 32 + 24 - len(node))
+                nodes.append((part[0][0], part[0][1], self.alloc(node)))
+            if len(nodes) == 1:
+                return nodes[0][2]
+            level, items = level + 1, nodes
+
     def group(self, links, attrs=(), per_node=8):
         """Old-style group; `links` name -> object header address."""
         names = sorted(links)
@@ -124,16 +146,21 @@ class Writer:
             heap_data += _pad8(nm.encode() + b'\0')
         data_addr = self.alloc(bytes(heap_data))
         heap = self.alloc(b'HEAP' + struct.pack('<B3xQQQ', 0, len(heap_data), UNDEF, data_addr))
+        per_node = min(per_node, 2 * GROUP_LEAF_K)
         children = []
         for i in range(0, len(names), per_node):
             part = names[i:i + per_node]
             snod = b'SNOD' + struct.pack('<BxH', 1, len(part))
             for nm in part:
                 snod += struct.pack('<QQII16x', offsets[nm], links[nm], 0, 0)
+            snod += bytes(8 + 2 * GROUP_LEAF_K * 40 - len(snod))          # full-size node
             children.append((self.alloc(snod), offsets[part[-1]]))
+        assert len(children) <= 2 * GROUP_INTERNAL_K, 'more than %d links in one group' % (
+            4 * GROUP_LEAF_K * GROUP_INTERNAL_K)
         node = b'TREE' + struct.pack('<BBHQQ', 0, 0, len(children), UNDEF, UNDEF) + struct.pack('<Q', 0)
         for addr, last in children:
             node += struct.pack('<QQ', addr, last)
+        node += bytes(24 + 2 * GROUP_INTERNAL_K * 16 + 8 - len(node))     # full-size node
         btree = self.alloc(node)
         msgs = [(0x11, struct.pack('<QQ', btree, heap))] + [self.attribute(k, v) for k, v in attrs]
         return self.header(msgs), btree, heap
@@ -147,7 +174,7 @@ class Writer:
         assert free >= 16, 'global heap collection of the minimal writer is full'
         coll += struct.pack('<HHIQ', 0, 0, 0, free)
         self.buf[self.gcol:self.gcol + len(head) + len(coll)] = head + coll
-        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
+        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, GROUP_LEAF_K, GROUP_INTERNAL_K, 0)
         sb += struct.pack('<QQQQ', 0, UNDEF, len(self.buf), UNDEF)
         sb += struct.pack('<QQII', 0, root_header, 1, 0) + struct.pack('<QQ', root_btree, root_heap)
         self.buf[:96] = sb
@@ -175,7 +202,7 @@ def write_batched_mapped_signal_file(filename, reads, batch_size=3, chunk=1000,
             links[k] = w.dataset(np.array([field(r, k) for r in part], dtype=np.float64), chunk)
         links['read_id'] = w.dataset([field(r, 'read_id') for r in part], chunk)
         batches['Batch_%d' % b] = w.group(links, per_node=5)[0]
-    top = {'Batches': w.group(batches, per_node=max(8, len(batches)))[0]}
+    top = {'Batches': w.group(batches)[0]}
     if len(reads) > 0:
         top['read_ids'] = w.dataset([field(r, 'read_id') for r in reads], chunk)
     root = w.group(top, attrs=[('version', np.int64(8)), ('alphabet', alphabet[0]),

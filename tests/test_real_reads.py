@@ -102,6 +102,14 @@ def test_batched_mapped_signal_file(g, tmp_path):
     reads = golden_reads(g)
     fn = str(tmp_path / 'batched.hdf5')
     write_batched_mapped_signal_file(fn, reads, batch_size=3, chunk=7000)
+    # the same with 500-element chunks: several hundred chunks per dataset, i.e. chunk B-trees of
+    # two levels (64 entries per node)
+    fn_small = str(tmp_path / 'batched_small_chunks.hdf5')
+    write_batched_mapped_signal_file(fn_small, reads, batch_size=4, chunk=500)
+    with mapped_signal_files.MappedSignalReader(fn_small) as msr:
+        for a, b in zip(msr.reads(), reads):
+            np.testing.assert_array_equal(a.Dacs, b.Dacs)
+            np.testing.assert_array_equal(a.Ref_to_signal, b.Ref_to_signal)
     with mapped_signal_files.MappedSignalReader(fn) as msr:
         assert isinstance(msr, mapped_signal_files.BatchHDF5Reader)
         assert msr.batch_names == ['Batch_0', 'Batch_1', 'Batch_2']
