@@ -154,6 +154,31 @@ def test_mapped_signal_writer_round_trip(g, tmp_path):
         mapped_signal_files.HDF5Writer(fn, ai, batch_format=False)
 
 
+def test_train_entry_point_loads_written_file(g, tmp_path):
+    """The file MappedSignalWriter writes (what bin/prepare_mapped_reads.py produces) is what
+    bin/train_flipflop.py's load_data reads: same reads, chunk sampling works on them."""
+    import argparse
+    import importlib
+    import sys
+    from taiyaki_b200 import chunk_selection, mapped_signal_files
+    from taiyaki_b200.alphabet import AlphabetInfo
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'bin'))
+    tf = importlib.import_module('train_flipflop')
+    reads = golden_reads(g)
+    fn = str(tmp_path / 'mapped.hdf5')
+    with mapped_signal_files.MappedSignalWriter(fn, AlphabetInfo('ACGT', 'ACGT')) as msw:
+        for r in reads:
+            msw.write_read(r.get_read_dictionary())
+    log = type('L', (), {'write': lambda self, m: None})()
+    args = argparse.Namespace(input=fn, limit=5, input_strand_list=None, mod_factor=[8.0, 1.0, 50000])
+    loaded, ai, _ = tf.load_data(args, log, None)
+    assert [r.read_id for r in loaded] == [r.read_id for r in reads[:5]] and ai.nbase == 4
+    np.random.seed(17)
+    fp = chunk_selection.sample_filter_parameters(loaded, 30, 1000, 10.0, 10.0, 0.1, 5, 1.1)
+    chunks, rej = chunk_selection.sample_chunks(loaded, 10, 1000, fp)
+    assert len(chunks) == 10 and all(c.sig_len == 1000 for c in chunks)
+
+
 def test_hdf5_errors(tmp_path):
     from taiyaki_b200 import hdf5_min
     p = tmp_path / 'x.hdf5'
