@@ -364,15 +364,32 @@ def train_model(train_params, net_info, optim_info, res_info, read_data, alphabe
                               mod_info=mod_info)
     # reads resident in HBM: batches are assembled by three kernel launches instead of
     # ~7 ms of single-threaded numpy per batch (the step itself takes ~6.5 ms)
-    store = None
+    prefetcher = None
     device = next(net_info.net.parameters()).device
     if device.type == 'cuda' and not train_params.host_batching:
         store = device_batching.DeviceReadStore(read_data, device)
+        prefetcher = device_batching.BatchPrefetcher(store, alphabet_info, filter_params,
+                                                     net_info, logs.main)
     score_smoothed = helpers.WindowedExpSmoother()
     total_bases = total_samples = 0
     rejection_dict = defaultdict(int)
     time_last = time.time()
     logs.main.write('* Training\n')
+
+    def draw_batch_shape():
+        """Chunk length and sub-batch size of one iteration (train_flipflop.py:554-562);
+        with device batching the iteration's batches are enqueued right away."""
+        batch_chunk_len = (np.random.randint(train_params.chunk_len_min,
+                                             train_params.chunk_len_max + 1) //
+                           net_info.stride) * net_info.stride
+        sub_batch_size = int(train_params.min_sub_batch_size * train_params.chunk_len_max /
+                             batch_chunk_len + 0.5)
+        if prefetcher is not None:
+            for _ in range(train_params.sub_batches):
+                prefetcher.request(batch_chunk_len, sub_batch_size)
+        return batch_chunk_len, sub_batch_size
+
+    next_shape = draw_batch_shape() if train_params.niteration > 0 else None
     for curr_iter in range(train_params.niteration):
         sharpen = float(train_params.sharpen.min + (
             train_params.sharpen.max - train_params.sharpen.min) *
@@ -380,15 +397,13 @@ def train_model(train_params, net_info, optim_info, res_info, read_data, alphabe
         mod_factor = float(mod_info.mod_factor.start + (
             mod_info.mod_factor.final - mod_info.mod_factor.start) *
             min(1.0, curr_iter / mod_info.mod_factor.niter))
-        batch_chunk_len = (np.random.randint(train_params.chunk_len_min,
-                                             train_params.chunk_len_max + 1) //
-                           net_info.stride) * net_info.stride
-        sub_batch_size = int(train_params.min_sub_batch_size * train_params.chunk_len_max /
-                             batch_chunk_len + 0.5)
-        if store is not None:
-            main_batch_gen = device_batching.prepare_random_batches(
-                store, batch_chunk_len, sub_batch_size, train_params.sub_batches, alphabet_info,
-                filter_params, net_info, logs.main)
+        batch_chunk_len, sub_batch_size = next_shape
+        if prefetcher is not None:
+            # batches of iteration k+1 go onto the batching stream BEFORE the step of
+            # iteration k is enqueued: assembly and its read-back run under the step
+            if curr_iter + 1 < train_params.niteration:
+                next_shape = draw_batch_shape()
+            main_batch_gen = prefetcher.batches(train_params.sub_batches)
         else:
             main_batch_gen = training.prepare_random_batches(
                 read_data, batch_chunk_len, sub_batch_size, train_params.sub_batches,
@@ -424,6 +439,8 @@ def train_model(train_params, net_info, optim_info, res_info, read_data, alphabe
                                curr_iter, logs)
             time_last = time.time()
         optim_info.lr_scheduler.step()
+        if prefetcher is None and curr_iter + 1 < train_params.niteration:
+            next_shape = draw_batch_shape()
     if res_info.is_lead_process:
         helpers.save_model(net_info.net, train_params.outdir)
 

@@ -714,8 +714,10 @@ int ty::crf_pick_p(int max_seqlen, bool mod) {
     // SM sub-partition); longer chunks widen the thread block first.  The cat-mod
     // chain (three gathers per position) measures 7 % faster with 8 positions
     // per thread and two DP warps (profiles/r1_microbench_v4.jsonl, tag B).
-    const char *e = getenv("TY_CRF_P");   // tuning override, read per call
-    const int forced = e ? atoi(e) : 0;
+    static const int forced = [] {          // tuning override, read once per process
+        const char *e = getenv("TY_CRF_P");
+        return e ? atoi(e) : 0;
+    }();
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) {
         const int cap = forced >= 8 ? 512 : 992;
         if ((max_seqlen + forced - 1) / forced <= cap) return forced;

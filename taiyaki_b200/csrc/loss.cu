@@ -81,8 +81,8 @@ extern "C" int ty_flipflop_train_loss(const float *scores, int ntrans, int nblk,
     char *ws = static_cast<char *>(workspace);
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     // TY_LOSS_SERIAL=1: partition-function chains on the caller's stream (A/B timing)
-    const char *serial = getenv("TY_LOSS_SERIAL");
-    SideStream *side = (serial && serial[0] == '1') ? nullptr : side_for_current_device();
+    static const bool serial = [] { const char *e = getenv("TY_LOSS_SERIAL"); return e && e[0] == '1'; }();
+    SideStream *side = serial ? nullptr : side_for_current_device();
     const float inv = 1.0f / (float)nblk;
     int rc;
     // ---- fork: partition-function chains on the side stream ----
@@ -92,8 +92,9 @@ extern "C" int ty_flipflop_train_loss(const float *scores, int ntrans, int nblk,
         cudaStreamWaitEvent(side->stream, side->fork, 0);
         zs = side->stream;
     }
-    const char *pack = getenv("TY_LOGZ_PACK");     // "0": one chain per CTA next to the CRF chains (A/B timing)
-    const int own_sms = side && !(pack && pack[0] == '0') ? 4 : 0;
+    // TY_LOGZ_PACK=0: one chain per CTA next to the CRF chains (A/B timing)
+    static const bool unpacked = [] { const char *e = getenv("TY_LOGZ_PACK"); return e && e[0] == '0'; }();
+    const int own_sms = side && !unpacked ? 4 : 0;
     rc = ty_flipflop_logz_phase(scores, ntrans, nblk, nbatch, 4, inv, logz_out, inv, grad_out,
                                 ntrans, 1, ws + crf_bytes, z_bytes, 1 | own_sms, zs);
     if (side) cudaEventRecord(side->join, side->stream);

@@ -41,21 +41,21 @@ def _as_device_i64(x, device):
     return x.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
 
 
-_LENGTH_HINTS = {}
-
-
 def hint_lengths(seqlen, max_len, total):
     """Tell the ops the (max, sum) of a DEVICE-resident seqlen tensor so they
-    need not synchronise to read it back."""
-    _LENGTH_HINTS[id(seqlen)] = (seqlen, int(max_len), int(total))
+    need not synchronise to read it back.  The hint rides on the tensor object
+    itself, so it is released with the batch (a module-level table keyed by id()
+    kept every batch's tensor alive for the whole run)."""
+    seqlen._ty_len_hint = (int(max_len), int(total))
+    return seqlen
 
 
 def _max_len(seqlen):
     """Longest sequence; free when seqlen lives on the host (the reference's
     batching hands over CPU tensors, train_flipflop.py:133-135)."""
-    hint = _LENGTH_HINTS.get(id(seqlen))
-    if hint is not None and hint[0] is seqlen:
-        return hint[1], hint[2]
+    hint = getattr(seqlen, '_ty_len_hint', None)
+    if hint is not None:
+        return hint
     if not torch.is_tensor(seqlen):
         seqlen = torch.as_tensor(np.asarray(seqlen))
     return int(seqlen.max()) if seqlen.numel() else 0, int(seqlen.sum())

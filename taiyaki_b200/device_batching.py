@@ -76,11 +76,24 @@ class DeviceReadStore:
         start = np.where(spare > 0, start, -1)
         return reads.astype(np.int32), start.astype(np.int32)
 
-    def sample(self, number_to_sample, chunk_len, filter_params, metadata, nbase,
-               select_strands_randomly=True, first_strand_index=0, candidates=None):
-        """One batch.  Returns (indata [T, N, 1] fp32, seqs int64, seqlens int64 [N],
-        mod_cats int64 or None, number accepted, rejection counts) -- device
-        tensors, one small device -> host copy (the counters and lengths)."""
+    def _staging(self, nbytes_cand, nbytes_small):
+        """Pinned host buffers from a free list, returned by `finish` (allocating
+        pinned memory per batch -- cudaHostAlloc -- cost milliseconds on some hosts)."""
+        free = self.__dict__.setdefault('_stage_free', [])
+        for i, (c, m) in enumerate(free):
+            if c.numel() >= nbytes_cand and m.numel() >= nbytes_small:
+                return free.pop(i)
+        pin = self.device.type == 'cuda'
+        return (torch.empty(max(nbytes_cand, 1 << 12), dtype=torch.uint8, pin_memory=pin),
+                torch.empty(max(nbytes_small, 1 << 12), dtype=torch.uint8, pin_memory=pin))
+
+    def launch(self, number_to_sample, chunk_len, filter_params, metadata, nbase,
+               select_strands_randomly=True, first_strand_index=0, candidates=None,
+               stream=None):
+        """Enqueue the three batching kernels and the small device -> host copy of
+        one batch on `stream` (default: the current stream) WITHOUT waiting;
+        `finish(pending)` completes it.  Issuing batch k+1 before the train step of
+        batch k is enqueued hides both the kernels and the read-back."""
         lib = _lib.lib()
         dev = self.device
         N, T = int(number_to_sample), int(chunk_len)
@@ -90,8 +103,12 @@ class DeviceReadStore:
                                               first_strand_index)
         cand_read, cand_start = candidates
         M = len(cand_read)
-        cand = torch.from_numpy(np.stack([cand_read, cand_start]).astype(np.int32))
-        cand = (cand.pin_memory() if dev.type == 'cuda' else cand).to(dev, non_blocking=True)
+        ncount = lib.ty_batch_counts_len()
+        nsmall = (2 * N + 1) * 8 + ncount * 4
+        cand_host, small_host = self._staging(2 * M * 4, nsmall)
+        ch = cand_host[:2 * M * 4].view(torch.int32).view(2, M)
+        ch[0] = torch.from_numpy(np.ascontiguousarray(cand_read, dtype=np.int32))
+        ch[1] = torch.from_numpy(np.ascontiguousarray(cand_start, dtype=np.int32))
         use_filters = None not in (filter_params.median_meandwell, filter_params.mad_meandwell,
                                    filter_params.model_stride, filter_params.path_buffer)
         filt = None
@@ -102,30 +119,58 @@ class DeviceReadStore:
                                         filter_params.median_meandwell,
                                         filter_params.mad_meandwell, filter_params.path_buffer)
         can_t, mod_t = self._label_tables(metadata)
-        indata = torch.empty(T, N, 1, dtype=torch.float32, device=dev)
-        max_seq = T          # a window of T samples spans at most T + 1 mapped positions
-        seqs = torch.empty(N * (max_seq + 1), dtype=torch.int64, device=dev)
-        mod_cats = torch.empty_like(seqs) if metadata.is_cat_mod else None
-        ncount = lib.ty_batch_counts_len()
-        small = torch.zeros(2 * N + 1 + ncount, dtype=torch.int64, device=dev)
-        seqlen, seqoff = small[:N], small[N:2 * N + 1]
-        counts = torch.zeros(ncount, dtype=torch.int32, device=dev)
-        scratch = torch.empty(3 * M + N, dtype=torch.int32, device=dev)
-        rc = lib.ty_sample_chunks(
-            _lib.ptr(self.dacs), _lib.ptr(self.dacs_off), _lib.ptr(self.r2s),
-            _lib.ptr(self.r2s_off), _lib.ptr(self.ref), _lib.ptr(self.ref_off),
-            _lib.ptr(self.lin[bool(metadata.standardize)]), _lib.ptr(cand[0]), _lib.ptr(cand[1]),
-            M, N, T, filt, int(filter_params.model_stride or 0), int(bool(metadata.reverse)),
-            int(nbase), _lib.ptr(can_t), _lib.ptr(mod_t), _lib.ptr(indata), _lib.ptr(seqs),
-            _lib.ptr(mod_cats), _lib.ptr(seqlen), _lib.ptr(seqoff), _lib.ptr(counts),
-            _lib.ptr(scratch), _lib.stream_ptr(dev))
-        _lib.check(rc, 'ty_sample_chunks')
-        _lib.count_launches(3)
-        host = torch.cat([counts.to(torch.int64), seqlen]).cpu().numpy()     # the one sync
-        cnt, lens = host[:ncount], host[ncount:]
+        ctx = torch.cuda.stream(stream) if stream is not None else _null_context()
+        with ctx:
+            cur = torch.cuda.current_stream(dev)
+            cand = ch.to(dev, non_blocking=True)
+            indata = torch.empty(T, N, 1, dtype=torch.float32, device=dev)
+            max_seq = T          # a window of T samples spans at most T + 1 mapped positions
+            seqs = torch.empty(N * (max_seq + 1), dtype=torch.int64, device=dev)
+            mod_cats = torch.empty_like(seqs) if metadata.is_cat_mod else None
+            # seqlen [N] | seqoff [N+1] (int64) | counters [ncount] (int32): one zero fill,
+            # one device -> host copy
+            small = torch.zeros(nsmall, dtype=torch.uint8, device=dev)
+            small64 = small[:(2 * N + 1) * 8].view(torch.int64)
+            seqlen, seqoff = small64[:N], small64[N:2 * N + 1]
+            counts = small[(2 * N + 1) * 8:].view(torch.int32)
+            scratch = torch.empty(3 * M + N, dtype=torch.int32, device=dev)
+            rc = lib.ty_sample_chunks(
+                _lib.ptr(self.dacs), _lib.ptr(self.dacs_off), _lib.ptr(self.r2s),
+                _lib.ptr(self.r2s_off), _lib.ptr(self.ref), _lib.ptr(self.ref_off),
+                _lib.ptr(self.lin[bool(metadata.standardize)]), _lib.ptr(cand[0]),
+                _lib.ptr(cand[1]), M, N, T, filt, int(filter_params.model_stride or 0),
+                int(bool(metadata.reverse)), int(nbase), _lib.ptr(can_t), _lib.ptr(mod_t),
+                _lib.ptr(indata), _lib.ptr(seqs), _lib.ptr(mod_cats), _lib.ptr(seqlen),
+                _lib.ptr(seqoff), _lib.ptr(counts), _lib.ptr(scratch), c_stream(cur))
+            _lib.check(rc, 'ty_sample_chunks')
+            _lib.count_launches(3)
+            small_host[:nsmall].copy_(small, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+        return dict(N=N, ncount=ncount, indata=indata, seqs=seqs, mod_cats=mod_cats,
+                    seqlen=seqlen, small_host=small_host[:nsmall], done=done,
+                    stream=stream, keep=(cand, scratch, small), stage=(cand_host, small_host))
+
+    def finish(self, pending):
+        """Wait for a launched batch and hand it over on the CURRENT stream."""
+        dev = self.device
+        N, ncount = pending['N'], pending['ncount']
+        pending['done'].synchronize()                       # the one host wait per batch
+        host = pending['small_host'].numpy().copy()
+        self._stage_free.append(pending['stage'])
+        lens = host[:N * 8].view(np.int64)
+        cnt = host[(2 * N + 1) * 8:].view(np.int32)
         n_acc, total = int(cnt[len(REJECT_NAMES)]), int(lens.sum())
         rejections = {name: int(c) for name, c in zip(REJECT_NAMES, cnt) if c}
-        seqlens = seqlen.clone()
+        indata, seqs, mod_cats = pending['indata'], pending['seqs'], pending['mod_cats']
+        if pending['stream'] is not None:
+            # produced on the batching stream, consumed on the caller's
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(pending['done'])
+            for t in (indata, seqs, mod_cats) + pending['keep']:
+                if t is not None:
+                    t.record_stream(cur)
+        seqlens = pending['seqlen'].clone()
         if n_acc < N:       # rare: not enough chunks passed the filters
             indata = indata[:, :n_acc].contiguous()
             seqlens = seqlens[:n_acc].clone()
@@ -134,23 +179,87 @@ class DeviceReadStore:
         if mod_cats is not None:
             mod_cats = mod_cats[:total]
         ctc.hint_lengths(seqlens, int(lens.max()) if n_acc else 0, total)
+        seqlens._ty_len_min = int(lens.min()) if n_acc else 0      # host copy, no sync to check
         return indata, seqs, seqlens, mod_cats, n_acc, rejections
+
+    def sample(self, number_to_sample, chunk_len, filter_params, metadata, nbase,
+               select_strands_randomly=True, first_strand_index=0, candidates=None):
+        """One batch.  Returns (indata [T, N, 1] fp32, seqs int64, seqlens int64 [N],
+        mod_cats int64 or None, number accepted, rejection counts) -- device
+        tensors, one small device -> host copy (the counters and lengths)."""
+        return self.finish(self.launch(number_to_sample, chunk_len, filter_params, metadata,
+                                       nbase, select_strands_randomly, first_strand_index,
+                                       candidates))
+
+
+class _null_context:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+def c_stream(stream):
+    import ctypes
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
+class BatchPrefetcher:
+    """FIFO of batches in flight: `request` enqueues the kernels and the small
+    read-back of a batch on a side stream, `next` hands the oldest one over.
+    Requesting the batches of iteration k+1 before the train step of iteration k
+    is enqueued puts batch assembly under the step (train_flipflop.py:78-142 is
+    serial with the step in the reference).  Candidates are drawn at `request`
+    time, in request order, so the numpy random stream is consumed exactly as by
+    the unpipelined loop (chunk length, then candidates, per iteration)."""
+
+    def __init__(self, store, alphabet_info, filter_params, net_info, log, use_side_stream=True):
+        self.store, self.alphabet_info, self.filter_params = store, alphabet_info, filter_params
+        self.net_info, self.log = net_info, log
+        self.queue = []
+        self.side = None
+        if use_side_stream and store.device.type == 'cuda':
+            self.side = torch.cuda.Stream(store.device)
+            self.side.wait_stream(torch.cuda.current_stream(store.device))   # store uploads
+
+    def request(self, chunk_len, sub_batch_size):
+        self.queue.append((sub_batch_size, self.store.launch(
+            sub_batch_size, chunk_len, self.filter_params, self.net_info.metadata,
+            self.alphabet_info.ncan_base, stream=self.side)))
+
+    def next(self):
+        sub_batch_size, pending = self.queue.pop(0)
+        out = self.store.finish(pending)
+        _check_batch(out, sub_batch_size, self.log)
+        return out
+
+    def batches(self, n):
+        for _ in range(n):
+            yield self.next()
+
+
+def _check_batch(batch, sub_batch_size, log):
+    _, _, seqlens, _, n_acc, _ = batch
+    if n_acc < sub_batch_size and log is not None:
+        log.write(('* Warning: only {} chunks passed filters (asked for {}).\n').format(
+            n_acc, sub_batch_size))
+    if n_acc == 0 or seqlens._ty_len_min <= 0:
+        raise Exception('Error: zero length sequence')
 
 
 def prepare_random_batches(store, batch_chunk_len, sub_batch_size, target_sub_batches,
                            alphabet_info, filter_params, net_info, log,
                            select_strands_randomly=True, first_strand_index=0):
-    """Device twin of training.prepare_random_batches: same tuples, tensors on the device."""
+    """Device twin of training.prepare_random_batches: same tuples, tensors on the
+    device, one batch at a time on the current stream (`BatchPrefetcher` is the
+    pipelined form the training loop uses)."""
     total_sub_batches = 0
     while total_sub_batches < target_sub_batches:
-        indata, seqs, seqlens, mod_cats, n_acc, rejections = store.sample(
-            sub_batch_size, batch_chunk_len, filter_params, net_info.metadata,
-            alphabet_info.ncan_base, select_strands_randomly, first_strand_index)
-        first_strand_index += sum(rejections.values())
-        if n_acc < sub_batch_size and log is not None:
-            log.write(('* Warning: only {} chunks passed filters (asked for {}).\n').format(
-                n_acc, sub_batch_size))
-        if n_acc == 0 or bool((seqlens <= 0).any()):
-            raise Exception('Error: zero length sequence')
+        batch = store.sample(sub_batch_size, batch_chunk_len, filter_params, net_info.metadata,
+                             alphabet_info.ncan_base, select_strands_randomly,
+                             first_strand_index)
+        first_strand_index += sum(batch[5].values())
+        _check_batch(batch, sub_batch_size, log)
         total_sub_batches += 1
-        yield indata, seqs, seqlens, mod_cats, n_acc, rejections
+        yield batch

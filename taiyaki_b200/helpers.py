@@ -19,12 +19,43 @@ def _load_python_model(model_file, **model_kwargs):
     return netmodule.network(**model_kwargs)
 
 
+class _legacy_rnn_pickles:
+    """Whole-module pickles written by torch 1.x (the reference pins 1.5.1,
+    requirements.txt:23; its shipped models/*.checkpoint are such files) hold
+    nn.LSTM / nn.GRU objects without `_flat_weights`, which current torch's
+    RNNBase.__setstate__ dereferences.  While a checkpoint is being loaded the
+    missing list is rebuilt from the pickled parameter names."""
+
+    def __enter__(self):
+        base = torch.nn.RNNBase
+        self.orig = orig = base.__setstate__
+
+        def setstate(module, d):
+            names = d.get('_all_weights')
+            if '_flat_weights' not in d and names and isinstance(names[0][0], str):
+                d = dict(d)
+                flat = [n for layer in names for n in layer]
+                d['_flat_weights_names'] = flat
+                d['_flat_weights'] = [d['_parameters'].get(n) for n in flat]
+            orig(module, d)
+        base.__setstate__ = setstate
+
+    def __exit__(self, *exc):
+        torch.nn.RNNBase.__setstate__ = self.orig
+
+
 def load_model(model_file, params_file=None, model_metadata=None, **model_kwargs):
-    """Load a model from a .py definition or a .checkpoint pickle (helpers.py:82-136)."""
+    """Load a model from a .py definition or a .checkpoint pickle (helpers.py:82-136).
+    Checkpoints pickled by the reference name their classes `taiyaki.layers.*`; they
+    resolve through the `taiyaki` alias package of this repository."""
     if os.path.splitext(model_file)[1] == '.py':
         network = _load_python_model(model_file, **model_kwargs)
     else:
-        network = torch.load(model_file, map_location='cpu', weights_only=False)
+        import warnings
+        import taiyaki  # noqa: F401  (registers taiyaki.layers -> taiyaki_b200.layers)
+        with _legacy_rnn_pickles(), warnings.catch_warnings():
+            warnings.simplefilter('ignore')       # SourceChangeWarning of every pickled class
+            network = torch.load(model_file, map_location='cpu', weights_only=False)
     if params_file is not None:
         network.load_state_dict(torch.load(params_file, map_location='cpu'))
     if model_metadata is not None:
@@ -59,7 +90,7 @@ def guess_model_stride(net):
     runs on the model's device."""
     device = get_model_device(net)
     with torch.no_grad():
-        out = net(torch.zeros((720, 8, 1), dtype=torch.float32, device=device))
+        out = net(torch.zeros((720, 1, 1), dtype=torch.float32, device=device))
     return int(round(720 / out.size()[0]))
 
 

@@ -423,6 +423,56 @@ def make_real():
           '; median/mad mean dwell', fp.median_meandwell, fp.mad_meandwell, '; L', seqlen)
 
 
+def make_trained():
+    """The reference's SHIPPED trained model on REAL signal -> tests/golden/trained_r941.npz.
+
+    models/mLstm_flipflop_model_r941_DNA.checkpoint (mLstm_flipflop, size 256, stride 5: the
+    architecture of BASELINE configs[1]) is unpickled into the REFERENCE's own taiyaki.layers
+    classes (stock nn.LSTM / nn.Conv1d / nn.Linear; the one shim is the `_flat_weights` list
+    torch >= 1.8 expects and a torch-1.5 pickle lacks) and run on the CPU in fp32 over the real
+    r9.4.1 chunks of real_reads.npz.  Every parameter is rounded to bf16 first -- on BOTH sides:
+    the rounded values are what is stored (uint16, half the bytes) and what the reference
+    network computes with -- so the comparison isolates the arithmetic of the layers from the
+    storage format of the fixture.  Stored: the parameters, the reference's scores
+    [200, 16, 40], and the reference loss (its C via oracle/_ref + its TorchScript partition
+    function) of each chunk against its real label sequence."""
+    import warnings
+    from taiyaki_b200.helpers import _legacy_rnn_pickles
+    real = np.load(os.path.join(HERE, 'real_reads.npz'))
+    with _legacy_rnn_pickles(), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        net = torch.load(os.path.join(REF, 'models/mLstm_flipflop_model_r941_DNA.checkpoint'),
+                         map_location='cpu', weights_only=False)
+    assert type(net).__module__ == 'taiyaki.layers' and ref_layers.Serial is type(net)
+    out = {}
+    with torch.no_grad():
+        for name, p in net.state_dict().items():
+            r = p.detach().to(torch.bfloat16)
+            p.copy_(r.float())
+            out['param_' + name] = r.view(torch.int16).numpy().view(np.uint16)
+    nb = 16
+    x = torch.tensor(real['chunk_current'][:nb].T.astype(np.float32)).unsqueeze(2)   # [1000, 16, 1]
+    net.eval()
+    with torch.no_grad():
+        scores = net(x)
+    assert scores.shape == (200, nb, 40)
+    out['signal'] = x.numpy()
+    out['scores'] = scores.numpy()
+    seqlen = real['chunk_seqlen'][:nb].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(real['chunk_seqlen'])])
+    seqs = np.concatenate([ref_fff.flipflop_code(real['chunk_seq'][off[i]:off[i + 1]].astype(np.int64), 4)
+                           for i in range(nb)]).astype(np.int64)
+    mv, st = ref_indices(seqs, seqlen, 4)
+    sc, gr = oracle.c_crf_flipflop_grad(scores.numpy(), mv, st, seqlen, 'ref')
+    logz = ref_layers.log_partition_flipflop(scores).squeeze(1).numpy()
+    nblk = scores.shape[0]
+    out['seqs'], out['seqlen'] = seqs, seqlen
+    out['loss'] = (-sc / nblk + logz / nblk).astype(np.float32)     # train_flipflop.py:163-176
+    np.savez_compressed(os.path.join(HERE, 'trained_r941.npz'), **out)
+    print('trained_r941.npz', os.path.getsize(os.path.join(HERE, 'trained_r941.npz')), 'bytes; loss per chunk',
+          np.round(out['loss'], 4), '; score range', float(scores.min()), float(scores.max()))
+
+
 def make_remap():
     """Alignments of the reference's taiyaki/flipflop_remap.py on seeded random scores and
     on the two tables of its unit test (test/unit/test_flipflop_remap.py:8-90)
@@ -498,6 +548,8 @@ if __name__ == '__main__':
         make_real()
     elif sys.argv[1:] == ['remap']:
         make_remap()
+    elif sys.argv[1:] == ['trained']:
+        make_trained()
     else:
         if sys.argv[1:] != ['decode']:
             main()
