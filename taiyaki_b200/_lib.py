@@ -89,18 +89,36 @@ def sources():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into taiyaki_b200/libtaiyaki_b200.so."""
+    """Compile csrc/*.cu for sm_100a into taiyaki_b200/libtaiyaki_b200.so: one object
+    per source (in parallel, rebuilt only when the source or a header changed),
+    then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = sources()
-    deps = srcs + glob.glob(os.path.join(_CSRC, '*.cuh')) + [
+    headers = glob.glob(os.path.join(_CSRC, '*.cuh')) + [
         os.path.join(os.path.dirname(_HERE), 'include', 'taiyaki_b200.h')]
-    if not force and os.path.exists(LIB_PATH):
-        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
-            return LIB_PATH
+    hdr_time = max(os.path.getmtime(h) for h in headers)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + srcs
-    if verbose:
-        print(' '.join(cmd))
-    subprocess.run(cmd, check=True)
+    objdir = os.path.join(_HERE, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != '-shared']
+    jobs, objs = [], []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        if force or not os.path.exists(obj) or \
+                os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            jobs.append([nvcc] + compile_flags + ['-c', '-o', obj, src])
+
+    def run(cmd):
+        if verbose:
+            print(' '.join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            list(pool.map(run, jobs))
+    if jobs or not os.path.exists(LIB_PATH) or \
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        run([nvcc] + NVCC_FLAGS[:2] + ['-shared', '-o', LIB_PATH] + objs)
     return LIB_PATH
 
 
