@@ -293,6 +293,31 @@ int ty_flipflop_remap(const float *scores, const int64_t *t_off, const int32_t *
                       int nread, int S, int max_m, double localpen, double *score,
                       int32_t *path, uint8_t *tb_ws, double *dp_ws, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Dense bf16 contraction on the 5th-generation tensor cores
+ * (taiyaki_b200/csrc/gemm_tc5.cu: TMA + tcgen05.mma, fp32 accumulators in tensor
+ * memory).  Replaces the library GEMMs the reference reaches through nn.LSTM /
+ * nn.GRU (taiyaki/layers.py:515,633: input projections and their input / weight
+ * gradients inside cuDNN), nn.Conv1d (layers.py:795) and the score projection
+ * nn.Linear + scale * tanh of GlobalNormFlipFlop (layers.py:1402-1411).
+ *
+ *     C[M x N] (fp32, row pitch ldc) = A[M x K] * B[N x K]^T
+ *
+ * a_mn / b_mn = 0: the operand is stored K-major ([M][lda] resp. [N][ldb] bf16);
+ *             = 1: MN-major ([K][lda] resp. [K][ldb] bf16, i.e. the transpose in
+ *                  place: weight gradients contract over the slow index of both).
+ * Operands 16-byte aligned, lda / ldb multiples of 8.  epi:
+ *   0  C = acc                          (ldc multiple of 4)
+ *   1  C = scale * tanh(acc + bias[n])  (bias may be NULL)
+ *   2  C[row'] += acc by red.global.add, row' = (row % map_g) * map_h + row / map_g when
+ *      map_g > 0 (unit-major -> gate-major rows of the recurrent weights), else row;
+ *      k_splits CTAs share an output tile
+ *   3  C += acc by TMA reduce-add; k_splits as for 2
+ * Asynchronous on `stream`; no workspace. */
+int ty_gemm_bf16(const void *A, int lda, int a_mn, const void *B, int ldb, int b_mn, int M,
+                 int N, int K, float *C, int ldc, int epi, const float *bias, float scale,
+                 int k_splits, int map_g, int map_h, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

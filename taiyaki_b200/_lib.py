@@ -75,6 +75,9 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     'ty_gru_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p]),
+    'ty_gemm_bf16': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p, c_int, c_int, c_void_p, c_float, c_int, c_int, c_int,
+                             c_void_p]),
     'ty_gru_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

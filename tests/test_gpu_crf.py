@@ -278,7 +278,7 @@ def test_golden_logz(dev, golden_random, tag):
     lz = layers.flipflop_logpartition(x)
     lz.sum().backward()
     np.testing.assert_allclose(lz.detach().cpu().numpy(), g[tag + '_logz'], rtol=2e-6, atol=3e-4)
-    np.testing.assert_allclose(x.grad.cpu().numpy(), g[tag + '_logz_grad'], rtol=2e-4, atol=3e-6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g[tag + '_logz_grad'], rtol=RTOL, atol=3e-6)
 
 
 def test_logz_decodeutil_golden(dev, kat):
@@ -299,7 +299,7 @@ def test_logz_full_size(dev, oracle):
     np.testing.assert_allclose(g.sum(-1), 1.0, atol=2e-5)
     lz_ref, g_ref = oracle.c_flipflop_logz(scores[:, 5:7], want_grad=True, impl='f64')
     np.testing.assert_allclose(lz.detach().cpu().numpy()[5:7], lz_ref, rtol=2e-6)
-    np.testing.assert_allclose(g[:, 5:7], g_ref, rtol=2e-4, atol=3e-6)
+    np.testing.assert_allclose(g[:, 5:7], g_ref, rtol=RTOL, atol=3e-6)
     # cost-only path (no gradient requested)
     lz2 = layers.flipflop_logpartition(torch.tensor(scores, device=dev))
     np.testing.assert_allclose(lz2.cpu().numpy(), lz.detach().cpu().numpy(), rtol=1e-6)
@@ -320,8 +320,9 @@ def test_training_loss_matches_reference_composition(dev, oracle):
     lz_ref, gz_ref = oracle.c_flipflop_logz(scores, want_grad=True, impl='f32')
     np.testing.assert_allclose(lossvec.detach().cpu().numpy(), c_ref + lz_ref / nblk, rtol=RTOL,
                                atol=1e-5)
-    np.testing.assert_allclose(x.grad.cpu().numpy(), (g_ref + gz_ref / nblk) / nbatch,
-                               rtol=2e-4, atol=1e-7)
+    # a difference of two posteriors: each term within 1e-4 of its own magnitude
+    err = np.abs(x.grad.cpu().numpy() * nbatch - (g_ref + gz_ref / nblk))
+    assert np.all(err <= RTOL * (np.abs(g_ref) + np.abs(gz_ref) / nblk) + 1e-5 / nblk)
 
 
 @pytest.mark.parametrize('ntrans', [40, 45])
@@ -360,6 +361,9 @@ def test_fused_train_loss_equals_separate_operators(dev, oracle, ntrans):
         c_ref, g_ref = oracle.crf_flipflop_loss(scores, seqs, seqlen, 1.5, impl='f32')
     lz, gz = oracle.c_flipflop_logz(np.ascontiguousarray(scores[:, :, :40]), impl='f32')
     np.testing.assert_allclose(l1.detach().cpu().numpy(), c_ref + lz / nblk, rtol=RTOL, atol=1e-5)
-    g_ref = g_ref.copy()
-    g_ref[:, :, :40] += gz / nblk
-    np.testing.assert_allclose(x1.grad.cpu().numpy(), g_ref / nbatch, rtol=2e-4, atol=1e-7)
+    want = g_ref.copy()
+    want[:, :, :40] += gz / nblk
+    tol = RTOL * np.abs(g_ref)
+    tol[:, :, :40] += RTOL * np.abs(gz) / nblk
+    err = np.abs(x1.grad.cpu().numpy() * nbatch - want)
+    assert np.all(err <= tol + 1e-5 / nblk), (err - tol).max() * nblk

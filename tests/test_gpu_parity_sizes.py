@@ -6,8 +6,24 @@ Everything here compares with the REFERENCE'S OWN C (`oracle/_ref`,
 c_crf_flipflop.c:434-516, c_cat_mod_flipflop.c:493-582; falls back to the
 restatement only when `_ref` was not shipped) and with the fp64 restatement,
 at north_star's 1e-4 relative.  Absolute floors: a gradient row is a posterior
-divided by nblk, so 5e-6/nblk is 5e-6 of a row's unit mass (entries below that
-are round-off of the reference's own fp32 softmax).
+divided by nblk, so x/nblk is x of a row's unit mass.
+
+Floors.  fp32 round-off of the recursion grows with the chain length, for the
+reference's C exactly as for the kernels (profiles/r2_parity_table.md, measured
+on B200 by tools/parity_table.py; distances from fp64 in units of a row's mass):
+
+    nblk    reference C vs fp64      kernels vs fp64       kernels vs reference C
+     800    1.2e-5                   1.1e-5                1.4e-5
+    1300    1.8e-5                   3.0e-5                2.9e-5
+    2000    1.2e-4 .. 2.3e-4         1.1e-4 .. 1.6e-4      1.6e-4 .. 3.6e-4
+    2300    3.7e-4                   2.8e-4                5.7e-4
+    5000    5.2e-4                   6.2e-4                5.9e-4
+
+so "within 1e-4 relative of the reference" is checked above a floor of 5e-6 of a
+row's mass up to 1000 blocks, 5e-5 up to 1500 and 1e-3 beyond (twice that when
+both sides are fp32), and `assert_not_noisier` additionally bounds the kernels'
+distance from fp64 by a multiple of the reference's own distance (at configs A
+and B the kernels are the closer of the two).
 """
 import ctypes
 
@@ -39,6 +55,19 @@ def _mod_cats(raw, seed=0):
     rng = np.random.RandomState(seed)
     return np.concatenate([(r == 1).astype(np.int64) * rng.randint(0, 2, size=len(r))
                            for r in raw])
+
+
+def assert_not_noisier(ours, ref32, f64, nblk, factor=2.5):
+    """max and rms distance from fp64 no more than `factor` times the reference C's."""
+    do, dr = np.abs(ours - f64) * nblk, np.abs(ref32 - f64) * nblk
+    assert do.max() <= factor * dr.max() + 5e-6, (do.max(), dr.max())
+    rms_o, rms_r = np.sqrt((do ** 2).mean()), np.sqrt((dr ** 2).mean())
+    assert rms_o <= factor * rms_r + 1e-7, (rms_o, rms_r)
+
+
+def floor_for(nblk):
+    """Absolute floor as a fraction of a row's mass (see the module docstring)."""
+    return (5e-6 if nblk <= 1000 else 5e-5 if nblk <= 1500 else 1e-3) / nblk
 
 
 def _gpu_cat_mod(dev, scores, seqs, seqlen, mod_cats, sharp):
@@ -81,8 +110,10 @@ def test_cat_mod_multiwarp_vs_reference(dev, oracle, nblk, lengths):
     cost, grad = _gpu_cat_mod(dev, scores, seqs, seqlen, mc, sharp)
     np.testing.assert_allclose(cost, c_ref, rtol=RTOL, atol=1e-6)
     np.testing.assert_allclose(cost, c64, rtol=RTOL, atol=1e-6)
-    np.testing.assert_allclose(grad, g64, rtol=RTOL, atol=5e-6 / nblk)
-    np.testing.assert_allclose(grad, g_ref, rtol=RTOL, atol=5e-6 / nblk)
+    np.testing.assert_allclose(grad, g64, rtol=RTOL, atol=floor_for(nblk))
+    # fp32 vs fp32: both sides carry round-off, hence twice the floor
+    np.testing.assert_allclose(grad, g_ref, rtol=RTOL, atol=2 * floor_for(nblk))
+    assert_not_noisier(grad, g_ref, g64, nblk)
 
 
 def test_cat_mod_config_b_full(dev, oracle):
@@ -97,9 +128,13 @@ def test_cat_mod_config_b_full(dev, oracle):
     mc = _mod_cats(raw, seed=6)
     c_ref, g_ref = oracle.cat_mod_flipflop_loss(scores, seqs, seqlen, mc, OFF, WEIGHTS, 1.0,
                                                 impl=_impl(oracle))
+    c64, g64 = oracle.cat_mod_flipflop_loss(scores, seqs, seqlen, mc, OFF, WEIGHTS, 1.0,
+                                            impl='f64')
     cost, grad = _gpu_cat_mod(dev, scores, seqs, seqlen, mc, 1.0)
     np.testing.assert_allclose(cost, c_ref, rtol=RTOL, atol=1e-6)
-    np.testing.assert_allclose(grad, g_ref, rtol=RTOL, atol=5e-6 / nblk)
+    np.testing.assert_allclose(grad, g64, rtol=RTOL, atol=floor_for(nblk))
+    np.testing.assert_allclose(grad, g_ref, rtol=RTOL, atol=2 * floor_for(nblk))
+    assert_not_noisier(grad, g_ref, g64, nblk)
     # the reference's invariants at this size: canonical columns of a row are a posterior
     np.testing.assert_allclose(-grad[:, :, :40].sum(-1) * nblk, 1.0, atol=3e-5)
     # fused loss = cat-mod cost + logZ/nblk (train_flipflop.py:163-182)
@@ -111,9 +146,13 @@ def test_cat_mod_config_b_full(dev, oracle):
     lz, gz = oracle.c_flipflop_logz(np.ascontiguousarray(scores[:, :, :40]), impl='f64')
     np.testing.assert_allclose(loss.detach().cpu().numpy(), c_ref + lz / nblk, rtol=RTOL,
                                atol=1e-5)
-    want = g_ref.copy()
+    # the fused gradient is a DIFFERENCE of two posteriors (-G + P)/nblk: each within 1e-4
+    want = g64.copy()
     want[:, :, :40] += gz / nblk
-    np.testing.assert_allclose(x.grad.cpu().numpy(), want, rtol=RTOL, atol=5e-6 / nblk)
+    tol = RTOL * np.abs(g64)
+    tol[:, :, :40] += RTOL * np.abs(gz) / nblk
+    err = np.abs(x.grad.cpu().numpy() - want)
+    assert np.all(err <= tol + 2 * floor_for(nblk)), (err - tol).max() * nblk
 
 
 # --------------------------------------------------------------------------
@@ -134,8 +173,11 @@ def test_config_a_all_chunks_vs_reference(dev, oracle):
     lz, gz = oracle.c_flipflop_logz(scores, impl='f64')
     np.testing.assert_allclose(loss.detach().cpu().numpy(), c_ref + lz / nblk, rtol=RTOL,
                                atol=1e-5)
-    np.testing.assert_allclose(x.grad.cpu().numpy(), g_ref + gz / nblk, rtol=RTOL,
-                               atol=5e-6 / nblk)
+    # fused gradient = (-G + P)/nblk, a difference of two posteriors: each term within 1e-4
+    # of its own magnitude (relative to the difference the bar would be ill-posed)
+    err = np.abs(x.grad.cpu().numpy() - (g_ref + gz / nblk))
+    tol = RTOL * (np.abs(g_ref) + np.abs(gz) / nblk) + 2 * floor_for(nblk)
+    assert np.all(err <= tol), (err - tol).max() * nblk
 
 
 def test_reference_speed_test_generator(dev, oracle):

@@ -61,34 +61,97 @@ def test_alias_package_resolves_reference_names():
         import taiyaki.squiggle_match  # noqa: F401
 
 
+def swish(x):
+    return x * torch.sigmoid(x)
+
+
+def bf16_operand_emulation(sd, x):
+    """The reference network in plain torch fp32 with exactly the roundings
+    north_star sanctions for the dense contractions: the operands of the strided
+    convolution's GEMM, of each input projection, of each recurrent product (h_{t-1})
+    and of the score projection are rounded to bf16; accumulation, gates, cell
+    state and everything else stay fp32.  (The weights are bf16-exact already.)"""
+    def bf(t):
+        return t.to(torch.bfloat16).float()
+
+    def conv(x, w, b, stride, rounded):
+        k = w.shape[2]
+        xi = x.permute(1, 2, 0)
+        xi = bf(xi) if rounded else xi
+        y = torch.nn.functional.conv1d(torch.nn.functional.pad(xi, (k // 2, (k - 1) // 2)), w, b,
+                                       stride=stride)
+        return swish(y).permute(2, 0, 1)
+
+    def lstm(x, wih, whh, bih, reverse):
+        xs = torch.flip(x, (0,)) if reverse else x
+        xp = bf(xs) @ wih.t() + bih
+        h = torch.zeros(x.shape[1], whh.shape[1])
+        c = torch.zeros_like(h)
+        ys = []
+        for t in range(x.shape[0]):
+            i, f, g, o = (xp[t] + bf(h) @ whh.t()).chunk(4, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            ys.append(h)
+        y = torch.stack(ys)
+        return torch.flip(y, (0,)) if reverse else y
+
+    with torch.no_grad():
+        y = conv(x, sd['sublayers.0.conv.weight'], sd['sublayers.0.conv.bias'], 1, False)
+        y = conv(y, sd['sublayers.1.conv.weight'], sd['sublayers.1.conv.bias'], 1, False)
+        y = conv(y, sd['sublayers.2.conv.weight'], sd['sublayers.2.conv.bias'], 5, True)
+        for i, rev in zip(range(3, 8), (True, False, True, False, True)):
+            pre = 'sublayers.%d.%slstm.' % (i, 'layer.' if rev else '')
+            y = lstm(y, sd[pre + 'weight_ih_l0'], sd[pre + 'weight_hh_l0'], sd[pre + 'bias_ih_l0'], rev)
+        return 5 * torch.tanh(bf(y) @ sd['sublayers.8.linear.weight'].t() + sd['sublayers.8.linear.bias'])
+
+
+def test_bf16_operand_rounding_alone_explains_the_score_deviation(trained):
+    """CPU: the deviation of a bf16-operand network from the fp32 reference on the
+    trained model is a property of the operand type, not of a kernel."""
+    s16 = bf16_operand_emulation(state_dict(trained), torch.from_numpy(trained['signal'])).numpy()
+    err = np.abs(s16 - trained['scores'])
+    assert 1e-3 < err.mean() < 1.2e-2 and err.max() < 1.0, (err.mean(), err.max())
+
+
 @pytest.mark.gpu
 def test_trained_reference_model_scores_and_loss(trained):
-    """Our layers, the reference's trained weights, real r9.4.1 signal.  The
-    recurrent products use bf16 operands (north_star), so scores differ from the
-    fp32 CPU run by bf16 rounding of the hidden state through five layers:
-    bounds measured on B200 and written here, not 1e-4."""
+    """Our layers, the reference's trained weights, real r9.4.1 signal.  The dense
+    contractions use bf16 operands (north_star), so scores differ from the fp32
+    CPU run by bf16 rounding of the hidden state through five layers -- sharp
+    transitions of a trained model shift by a block here and there: mean |d|
+    0.0074, max 0.63 on scores in [-5, 5] measured on B200, and 0.0076 / 0.59 for
+    the plain-torch emulation of the same roundings on the CPU; kernel vs emulation
+    0.0072 / 0.59 -- two bf16-operand evaluations differ from each other as much as
+    from fp32 (a rounding that flips moves a transition), so neither is a tighter
+    pin than the other.  What IS tight: the training loss of the real labels, 6e-4
+    absolute / 1 % relative from the reference's, and the loss operator alone on
+    the reference's scores at 1e-4.  Bounds below: the measured ones with headroom."""
     from taiyaki_b200 import ctc, helpers
     dev = torch.device('cuda:0')
     net = helpers.load_model(os.path.join(ROOT, 'models', 'mLstm_flipflop.py'),
                              size=256, stride=5, winlen=19, insize=1, alphabet_info=None)
-    missing = net.load_state_dict(state_dict(trained), strict=True)
+    sd = state_dict(trained)
+    missing = net.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     net = net.to(dev).eval()
     x = torch.from_numpy(trained['signal']).to(dev)
+    seqs, seqlen = torch.from_numpy(trained['seqs']), torch.from_numpy(trained['seqlen'])
     with torch.no_grad():
         scores = net(x)
-        loss = ctc.flipflop_train_loss(scores, torch.from_numpy(trained['seqs']),
-                                       torch.from_numpy(trained['seqlen']), 1.0)
+        loss = ctc.flipflop_train_loss(scores, seqs, seqlen, 1.0)
+        # the loss operator alone on the REFERENCE's scores: fp32 parity at 1e-4
+        l2 = ctc.flipflop_train_loss(torch.from_numpy(trained['scores']).to(dev), seqs, seqlen, 1.0)
     s, ref = scores.cpu().numpy(), trained['scores']
-    err = np.abs(s - ref)
-    print('trained model: max |dscore| %.4f  mean %.5f  (scores in [-5, 5])' % (err.max(), err.mean()))
-    assert err.mean() < 5e-3 and err.max() < 0.25
-    # the per-chunk training loss of real labels under the trained model
+    s16 = bf16_operand_emulation(sd, torch.from_numpy(trained['signal'])).numpy()
+    err, err16 = np.abs(s - ref), np.abs(s - s16)
     l, lref = loss.cpu().numpy(), trained['loss']
-    print('trained model: loss ours', np.round(l, 4), 'reference', np.round(lref, 4))
-    np.testing.assert_allclose(l, lref, rtol=2e-2, atol=2e-3)
-    # and the loss operator alone on the REFERENCE's scores: fp32 parity at 1e-4
-    with torch.no_grad():
-        l2 = ctc.flipflop_train_loss(torch.from_numpy(ref).to(dev), torch.from_numpy(trained['seqs']),
-                                     torch.from_numpy(trained['seqlen']), 1.0)
+    print('trained model vs fp32 reference : max |dscore| %.4f  mean %.5f' % (err.max(), err.mean()))
+    print('trained model vs bf16 emulation : max |dscore| %.4f  mean %.5f' % (err16.max(), err16.mean()))
+    print('loss per chunk ours     ', np.round(l, 4))
+    print('loss per chunk reference', np.round(lref, 4))
+    print('max |dloss| %.5f  max rel %.4f' % (np.abs(l - lref).max(), np.abs(l / lref - 1).max()))
     np.testing.assert_allclose(l2.cpu().numpy(), lref, rtol=1e-4, atol=1e-6)
+    assert err.mean() < 1.2e-2 and err.max() < 1.0
+    assert err16.mean() < 1.2e-2
+    np.testing.assert_allclose(l, lref, rtol=2e-2, atol=2e-3)
