@@ -92,6 +92,76 @@ def _operand(t):
     return t.to(torch.bfloat16) if PROJECTION_DTYPE == 'bf16' else t
 
 
+#: bf16 contractions go to csrc/gemm_tc5.cu (TMA + tcgen05); False sends them to the
+#: library GEMM instead (A/B timing only -- `TY_GEMM=lib` in the environment)
+import os as _os
+TC5_GEMM = _os.environ.get('TY_GEMM', 'tc5') != 'lib'
+_EPI_STORE, _EPI_BIAS_TANH, _EPI_ATOMIC, _EPI_REDUCE = 0, 1, 2, 3
+
+
+def _tc5_ok(*operands):
+    """bf16, unit inner stride, 16-byte aligned base and row pitch."""
+    return TC5_GEMM and all(
+        t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and
+        t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in operands)
+
+
+def _gemm(a, a_mn, b, b_mn, M, N, K, out=None, epi=_EPI_STORE, bias=None, scale=1.0,
+          k_splits=1, map_g=0, map_h=0):
+    """out[M, N] (fp32) = A[M, K] B[N, K]^T on the tensor cores (ty_gemm_bf16).
+    a_mn / b_mn: the operand tensor is the stored TRANSPOSE ([K, M] / [K, N])."""
+    if out is None:
+        # row pitch a multiple of 16 bytes (TMA store); a [:, :N] view when N % 4 != 0
+        out = torch.empty(M, (N + 3) // 4 * 4, dtype=torch.float32, device=a.device)[:, :N]
+    rc = _lib.lib().ty_gemm_bf16(
+        _lib.ptr(a), a.stride(0), int(a_mn), _lib.ptr(b), b.stride(0), int(b_mn), M, N, K,
+        _lib.ptr(out), out.stride(0), epi, _lib.ptr(bias), float(scale), int(k_splits),
+        int(map_g), int(map_h), _lib.stream_ptr(a.device))
+    _lib.check(rc, 'ty_gemm_bf16')
+    _lib.count_launches(1)
+    return out
+
+
+def _k_splits(M, N, K, ctas=296):
+    """CTAs sharing an output tile of a weight-gradient product (contraction over
+    time x batch): enough of them to fill the chip twice over."""
+    tiles = -(-M // 128) * -(-N // (64 if N <= 64 else 128))
+    return max(1, min(-(-K // 64), ctas // tiles))
+
+
+def _mm_nt(x, w):
+    """x[M, K] w[N, K]^T -> fp32 [M, N]"""
+    if _tc5_ok(x, w):
+        return _gemm(x, 0, w, 0, x.shape[0], w.shape[0], x.shape[1])
+    return _mm(x, w.t())
+
+
+def _mm_nn(d, w):
+    """d[M, K] w[K, N] -> fp32 [M, N] (input gradient: w read in place, MN-major)"""
+    if _tc5_ok(d, w):
+        return _gemm(d, 0, w, 1, d.shape[0], w.shape[1], d.shape[1])
+    return _mm(d, w)
+
+
+def _mm_tn(d, x, out=None, map_g=0, map_h=0):
+    """d[K, M]^T x[K, N] -> fp32 [M, N] (weight gradient: both operands read in
+    place, MN-major; split-K, accumulated into `out` (zeros when None), rows
+    optionally sent from unit-major to gate-major order)."""
+    K, M = d.shape
+    N = x.shape[1]
+    if _tc5_ok(d, x):
+        if out is None:
+            out = torch.zeros(M, N, dtype=torch.float32, device=d.device)
+        return _gemm(d, 1, x, 1, M, N, K, out=out, epi=_EPI_ATOMIC, k_splits=_k_splits(M, N, K),
+                     map_g=map_g, map_h=map_h)
+    res = _mm(d.t(), x)
+    if map_g:
+        res = _gate_major(res, map_g)
+    if out is not None:
+        return out.add_(res)
+    return res
+
+
 # ---------------------------------------------------------------------------
 # recurrence
 def _unit_major(w, G):
@@ -131,14 +201,6 @@ def flush_weight_grads():
     _pending = []
 
 
-def _accumulate_unit_major(param, dw_um, G):
-    """param.grad (gate-major) += dw (unit-major rows), in place."""
-    GH, K = dw_um.shape
-    if param.grad is None:
-        param.grad = torch.zeros_like(param)
-    param.grad.view(G, GH // G, K).transpose(0, 1).add_(dw_um.view(GH // G, G, K))
-
-
 #: 'ws' = warp-specialised kernels behind the unit-major ABI (csrc/rnn_ws.cu, bf16
 #: projections only); 'legacy' = one-role kernels behind the gate-major ABI (csrc/rnn.cu)
 RNN_IMPL = 'ws'
@@ -175,7 +237,7 @@ class _Recurrence(torch.autograd.Function):
             wo.view(H, G, I).copy_(w_ih.detach().view(G, H, I).transpose(0, 1))
         else:
             wo = _operand(w_ih.detach())
-        xproj = _mm(xo, wo.t())
+        xproj = _mm_nt(xo, wo)
         bias = b_ih.detach().contiguous().float() if b_ih is not None else None
         dev = x.device
         y = torch.empty(T, N, H, dtype=torch.float32, device=dev)
@@ -231,27 +293,32 @@ class _Recurrence(torch.autograd.Function):
             d2 = do.view(T * N, G * H)
             dh_side = do if cell == _CELL_LSTM else dhid
             w_ih, w_hh = ctx.weights
+            dh2 = dh_side[sl_cur].reshape(-1, G * H)
             if DEFER_WEIGHT_GRADS and w_ih.is_leaf and w_hh.is_leaf:
+                # straight into param.grad (a view of the flat gradient buffer): split-K
+                # partial products are added with red.global.add, rows permuted back to the
+                # parameters' gate-major order on the way out
+                for w in (w_ih, w_hh):
+                    if w.grad is None:
+                        w.grad = torch.zeros_like(w)
                 main = torch.cuda.current_stream(dev)
                 side = _side_stream(dev)
                 ready = torch.cuda.Event()
                 ready.record(main)
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
-                    dw_ih = _mm(d2.t(), xo)
-                    dw_hh = _mm(dh_side[sl_cur].reshape(-1, G * H).t(), hp2)
                     if ctx.needs_input_grad[1]:
-                        _accumulate_unit_major(w_ih, dw_ih, G)
+                        _mm_tn(d2, xo, out=w_ih.grad, map_g=G, map_h=H)
                     if ctx.needs_input_grad[2]:
-                        _accumulate_unit_major(w_hh, dw_hh, G)
+                        _mm_tn(dh2, hp2, out=w_hh.grad, map_g=G, map_h=H)
                     done = torch.cuda.Event()
                     done.record(side)
-                _pending.append((done, (do, dhid, xo, yo, dw_ih, dw_hh)))
-                dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
+                _pending.append((done, (do, dhid, xo, yo)))
+                dx = _mm_nn(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
                 return dx, None, None, db, None, None, None
-            dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
-            dw_ih = _gate_major(_mm(d2.t(), xo), G)
-            dw_hh = _gate_major(_mm(dh_side[sl_cur].reshape(-1, G * H).t(), hp2), G)
+            dx = _mm_nn(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
+            dw_ih = _mm_tn(d2, xo, map_g=G, map_h=H)
+            dw_hh = _mm_tn(dh2, hp2, map_g=G, map_h=H)
             return dx, dw_ih, dw_hh, db, None, None, None
         dhn = torch.empty(T, N, H, dtype=gdt, device=dev) if cell == _CELL_GRU else None
         with _lib.timed('rnn_bwd', dev):
@@ -458,7 +525,7 @@ class _ConvTimeMajor(torch.autograd.Function):
             wo[:, :C * k] = weight.detach().reshape(Cout, C * k)
             if bias is not None:
                 wo[:, C * k] = bias.detach()
-            out = _mm(co, wo.t())
+            out = _mm_nt(co, wo)
         else:
             ld = C * k
             xp = torch.nn.functional.pad(x, (0, 0, 0, 0, padding[0], padding[1]))
@@ -477,7 +544,7 @@ class _ConvTimeMajor(torch.autograd.Function):
         T, N, C, Cout, k, stride, padding, Tp, Tout, wide, has_bias, ld = ctx.cfg
         d2 = dout.reshape(Tout * N, Cout)
         do = _operand(d2) if wide else d2
-        dwf = _mm(do.t(), co)                                        # [Cout, ld]
+        dwf = _mm_tn(do, co) if wide else _mm(do.t(), co)            # [Cout, ld]
         if wide:
             dw = dwf[:, :C * k].reshape(Cout, C, k)
             db = dwf[:, C * k] if has_bias else None
@@ -486,7 +553,7 @@ class _ConvTimeMajor(torch.autograd.Function):
             db = d2.sum(0) if has_bias else None
         dx = None
         if ctx.needs_input_grad[0]:
-            dcols = _mm(do, wo)                                     # [T_out*N, ld]
+            dcols = _mm_nn(do, wo) if wide else _mm(do, wo)         # [T_out*N, ld]
             if dcols.is_cuda:
                 dx = torch.empty(T, N, C, dtype=torch.float32, device=dcols.device)
                 rc = _lib.lib().ty_col2im_time_major_ld(
@@ -609,7 +676,7 @@ class _ProjLinear(torch.autograd.Function):
         T, N, I = x.shape
         xo = x16.view(T * N, I) if x16 is not None else _operand(x.reshape(T * N, I))
         wo = _operand(weight.detach())
-        out = _mm(xo, wo.t())
+        out = _mm_nt(xo, wo)
         if bias is not None:
             out += bias.detach()
         ctx.save_for_backward(xo, wo)
@@ -622,10 +689,42 @@ class _ProjLinear(torch.autograd.Function):
         T, N, O = dy.shape
         d2 = dy.reshape(T * N, O)
         do = _operand(d2)
-        dx = _mm(do, wo).view(T, N, -1) if ctx.needs_input_grad[0] else None
-        dw = _mm(do.t(), xo)
+        dx = _mm_nn(do, wo).view(T, N, -1) if ctx.needs_input_grad[0] else None
+        dw = _mm_tn(do, xo)
         db = d2.sum(0) if ctx.has_bias else None
         return dx, dw, db, None
+
+
+class _ScoreProjection(torch.autograd.Function):
+    """scores = scale * tanh(x W^T + b) as ONE kernel: the bf16 contraction on the
+    tensor cores with bias, tanh and the scale applied to the fp32 accumulators
+    before they leave the SM (layers.py:1402-1411 is a cuBLAS GEMM followed by
+    three elementwise passes over [T, N, S])."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, x16, scale):
+        T, N, I = x.shape
+        O = weight.shape[0]
+        xo = x16.view(T * N, I) if x16 is not None else _operand(x.reshape(T * N, I))
+        wo = _operand(weight.detach())
+        b = bias.detach().float().contiguous() if bias is not None else None
+        out = _gemm(xo, 0, wo, 0, T * N, O, I, epi=_EPI_BIAS_TANH, bias=b, scale=scale)
+        ctx.save_for_backward(xo, wo, out)
+        ctx.cfg = (bias is not None, float(scale))
+        return out.view(T, N, O)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xo, wo, out = ctx.saved_tensors
+        has_bias, scale = ctx.cfg
+        T, N, O = dy.shape
+        # d/dz scale tanh(z) = scale - s^2 / scale with s the saved output
+        dz = dy.reshape(T * N, O) * (scale - out * out * (1.0 / scale))
+        do = dz.to(torch.bfloat16)
+        dx = _mm_nn(do, wo).view(T, N, -1) if ctx.needs_input_grad[0] else None
+        dw = _mm_tn(do, xo)
+        db = dz.sum(0) if has_bias else None
+        return dx, dw, db, None, None
 
 
 def _proj_linear(linear, x):
@@ -667,6 +766,13 @@ class GlobalNormFlipFlop(nn.Module):
             init_(self.linear.bias, truncated_normal(list(self.linear.bias.shape), sd=0.5))
 
     def forward(self, x):
+        if (self.activation is activation.tanh and x.is_cuda and x.dim() == 3 and
+                PROJECTION_DTYPE == 'bf16' and TC5_GEMM and self.insize % 8 == 0):
+            x16 = getattr(x, '_ty_bf16', None)
+            if x16 is not None and (x16.shape != x.shape or x16.device != x.device):
+                x16 = None
+            return _ScoreProjection.apply(x, self.linear.weight, self.linear.bias, x16,
+                                          self.scale)
         return self.scale * self.activation(_proj_linear(self.linear, x))
 
 
