@@ -357,90 +357,117 @@ def log_validation(net_info, reporting_batch_list, train_params, mod_info, curr_
     logs.validation.write(VAL_TMPLT.format(curr_iter + 1, rloss))
 
 
-def train_model(train_params, net_info, optim_info, res_info, read_data, alphabet_info,
-                filter_params, mod_info, reporting_batch_list, logs):
-    """The hot loop, train_flipflop.py:532-627."""
-    step = training.TrainStep(net_info, optim_info.optimiser, optim_info.rolling_mads,
-                              mod_info=mod_info)
-    # reads resident in HBM: batches are assembled by three kernel launches instead of
-    # ~7 ms of single-threaded numpy per batch (the step itself takes ~6.5 ms)
-    prefetcher = None
-    device = next(net_info.net.parameters()).device
-    if device.type == 'cuda' and not train_params.host_batching:
-        store = device_batching.DeviceReadStore(read_data, device)
-        prefetcher = device_batching.BatchPrefetcher(store, alphabet_info, filter_params,
-                                                     net_info, logs.main)
-    score_smoothed = helpers.WindowedExpSmoother()
-    total_bases = total_samples = 0
-    rejection_dict = defaultdict(int)
-    time_last = time.time()
-    logs.main.write('* Training\n')
+class TrainLoop:
+    """The hot loop, train_flipflop.py:532-627, as an object so that it can be run in
+    pieces (`run(n)` continues where the previous call stopped; bench.py times the
+    entry point's own loop this way, warm-up excluded).  `train_model` runs it whole."""
 
-    def draw_batch_shape():
+    def __init__(self, train_params, net_info, optim_info, res_info, read_data, alphabet_info,
+                 filter_params, mod_info, reporting_batch_list, logs):
+        self.train_params, self.net_info, self.optim_info = train_params, net_info, optim_info
+        self.res_info, self.read_data, self.alphabet_info = res_info, read_data, alphabet_info
+        self.filter_params, self.mod_info, self.logs = filter_params, mod_info, logs
+        self.reporting_batch_list = reporting_batch_list
+        self.step = training.TrainStep(net_info, optim_info.optimiser, optim_info.rolling_mads,
+                                       mod_info=mod_info, sub_batches=train_params.sub_batches)
+        # reads resident in HBM: batches are assembled by three kernel launches, enqueued one
+        # iteration ahead on a side stream (device_batching.BatchPrefetcher), instead of ~5 ms
+        # of single-threaded numpy per batch (the step itself takes ~6.5 ms)
+        self.prefetcher = None
+        device = next(net_info.net.parameters()).device
+        if device.type == 'cuda' and not train_params.host_batching:
+            store = device_batching.DeviceReadStore(read_data, device)
+            self.prefetcher = device_batching.BatchPrefetcher(store, alphabet_info, filter_params,
+                                                              net_info, logs.main)
+        self.score_smoothed = helpers.WindowedExpSmoother()
+        self.total_bases = self.total_samples = 0
+        self.samples_seen = 0
+        self.rejection_dict = defaultdict(int)
+        self.curr_iter = 0
+        self.next_shape = None
+        self.time_last = time.time()
+
+    def draw_batch_shape(self):
         """Chunk length and sub-batch size of one iteration (train_flipflop.py:554-562);
         with device batching the iteration's batches are enqueued right away."""
-        batch_chunk_len = (np.random.randint(train_params.chunk_len_min,
-                                             train_params.chunk_len_max + 1) //
-                           net_info.stride) * net_info.stride
-        sub_batch_size = int(train_params.min_sub_batch_size * train_params.chunk_len_max /
-                             batch_chunk_len + 0.5)
-        if prefetcher is not None:
-            for _ in range(train_params.sub_batches):
-                prefetcher.request(batch_chunk_len, sub_batch_size)
+        tp = self.train_params
+        batch_chunk_len = (np.random.randint(tp.chunk_len_min, tp.chunk_len_max + 1) //
+                           self.net_info.stride) * self.net_info.stride
+        sub_batch_size = int(tp.min_sub_batch_size * tp.chunk_len_max / batch_chunk_len + 0.5)
+        if self.prefetcher is not None:
+            for _ in range(tp.sub_batches):
+                self.prefetcher.request(batch_chunk_len, sub_batch_size)
         return batch_chunk_len, sub_batch_size
 
-    next_shape = draw_batch_shape() if train_params.niteration > 0 else None
-    for curr_iter in range(train_params.niteration):
-        sharpen = float(train_params.sharpen.min + (
-            train_params.sharpen.max - train_params.sharpen.min) *
-            min(1.0, curr_iter / train_params.sharpen.niter))
-        mod_factor = float(mod_info.mod_factor.start + (
-            mod_info.mod_factor.final - mod_info.mod_factor.start) *
-            min(1.0, curr_iter / mod_info.mod_factor.niter))
-        batch_chunk_len, sub_batch_size = next_shape
-        if prefetcher is not None:
-            # batches of iteration k+1 go onto the batching stream BEFORE the step of
-            # iteration k is enqueued: assembly and its read-back run under the step
-            if curr_iter + 1 < train_params.niteration:
-                next_shape = draw_batch_shape()
-            main_batch_gen = prefetcher.batches(train_params.sub_batches)
-        else:
-            main_batch_gen = training.prepare_random_batches(
-                read_data, batch_chunk_len, sub_batch_size, train_params.sub_batches,
-                alphabet_info, filter_params, net_info, logs.main)
-        (chunk_count, _, chunk_samples, chunk_bases, batch_rejections), fval, grad_maxs = step(
-            main_batch_gen, sharpen, mod_factor, read_back=True)
-        assert np.isfinite(fval), (
-            "Error: all costs must be finite, got {}.\n"
-            "Try restarting from a checkpoint with a lower learning rate.").format(fval)
-        if res_info.is_lead_process:
-            thr = step.grad_max_threshs
-            thr_str = 'NaN' if thr is None else ','.join(str(float(t)) for t in thr)
-            logs.batch.write(BATCH_TMPLT.format(
-                curr_iter + 1, fval, ','.join(map(str, grad_maxs)), thr_str,
-                optim_info.lr_scheduler.get_last_lr()[0], batch_chunk_len))
-        total_samples += chunk_samples
-        total_bases += chunk_bases
-        score_smoothed.update(fval)
-        for k, v in batch_rejections.items():
-            rejection_dict[k] += v
-        logs.main.write('.')
-        if (curr_iter + 1) % DOTROWLENGTH == 0:
-            log_polka(net_info, train_params, optim_info, time_last, score_smoothed, curr_iter,
-                      total_samples, total_bases, rejection_dict, logs.main)
-            time_last = time.time()
-            total_bases = total_samples = 0
-        if (curr_iter + 1) % train_params.save_every == 0:
-            if res_info.is_lead_process:
-                saved = helpers.save_model(net_info.net, train_params.outdir,
-                                           (curr_iter + 1) // train_params.save_every)
-                logs.main.write("Model saved to {}.\n".format(saved))
-                log_validation(net_info, reporting_batch_list, train_params, mod_info,
-                               curr_iter, logs)
-            time_last = time.time()
-        optim_info.lr_scheduler.step()
-        if prefetcher is None and curr_iter + 1 < train_params.niteration:
-            next_shape = draw_batch_shape()
+    def run(self, niter):
+        """`niter` more optimiser steps (never beyond train_params.niteration)."""
+        tp, net_info, optim_info, mod_info = (self.train_params, self.net_info, self.optim_info,
+                                              self.mod_info)
+        logs, res_info = self.logs, self.res_info
+        last = min(tp.niteration, self.curr_iter + niter)
+        if self.next_shape is None and self.curr_iter < tp.niteration:
+            self.next_shape = self.draw_batch_shape()
+        while self.curr_iter < last:
+            curr_iter = self.curr_iter
+            sharpen = float(tp.sharpen.min + (tp.sharpen.max - tp.sharpen.min) *
+                            min(1.0, curr_iter / tp.sharpen.niter))
+            mod_factor = float(mod_info.mod_factor.start + (
+                mod_info.mod_factor.final - mod_info.mod_factor.start) *
+                min(1.0, curr_iter / mod_info.mod_factor.niter))
+            batch_chunk_len, sub_batch_size = self.next_shape
+            if self.prefetcher is not None:
+                # batches of iteration k+1 go onto the batching stream BEFORE the step of
+                # iteration k is enqueued: assembly and its read-back run under the step
+                if curr_iter + 1 < tp.niteration:
+                    self.next_shape = self.draw_batch_shape()
+                main_batch_gen = self.prefetcher.batches(tp.sub_batches)
+            else:
+                main_batch_gen = training.prepare_random_batches(
+                    self.read_data, batch_chunk_len, sub_batch_size, tp.sub_batches,
+                    self.alphabet_info, self.filter_params, net_info, logs.main)
+            (chunk_count, _, chunk_samples, chunk_bases, batch_rejections), fval, grad_maxs = \
+                self.step(main_batch_gen, sharpen, mod_factor, read_back=True)
+            assert np.isfinite(fval), (
+                "Error: all costs must be finite, got {}.\n"
+                "Try restarting from a checkpoint with a lower learning rate.").format(fval)
+            if res_info.is_lead_process and logs.batch is not None:
+                thr = self.step.grad_max_threshs
+                thr_str = 'NaN' if thr is None else ','.join(str(float(t)) for t in thr)
+                logs.batch.write(BATCH_TMPLT.format(
+                    curr_iter + 1, fval, ','.join(map(str, grad_maxs)), thr_str,
+                    optim_info.lr_scheduler.get_last_lr()[0], batch_chunk_len))
+            self.total_samples += chunk_samples
+            self.samples_seen += chunk_samples
+            self.total_bases += chunk_bases
+            self.score_smoothed.update(fval)
+            for k, v in batch_rejections.items():
+                self.rejection_dict[k] += v
+            logs.main.write('.')
+            if (curr_iter + 1) % DOTROWLENGTH == 0:
+                log_polka(net_info, tp, optim_info, self.time_last, self.score_smoothed, curr_iter,
+                          self.total_samples, self.total_bases, self.rejection_dict, logs.main)
+                self.time_last = time.time()
+                self.total_bases = self.total_samples = 0
+            if (curr_iter + 1) % tp.save_every == 0:
+                if res_info.is_lead_process:
+                    saved = helpers.save_model(net_info.net, tp.outdir,
+                                               (curr_iter + 1) // tp.save_every)
+                    logs.main.write("Model saved to {}.\n".format(saved))
+                    log_validation(net_info, self.reporting_batch_list, tp, mod_info,
+                                   curr_iter, logs)
+                self.time_last = time.time()
+            optim_info.lr_scheduler.step()
+            if self.prefetcher is None and curr_iter + 1 < tp.niteration:
+                self.next_shape = self.draw_batch_shape()
+            self.curr_iter += 1
+        return self.score_smoothed.value
+
+
+def train_model(train_params, net_info, optim_info, res_info, read_data, alphabet_info,
+                filter_params, mod_info, reporting_batch_list, logs):
+    loop = TrainLoop(train_params, net_info, optim_info, res_info, read_data, alphabet_info,
+                     filter_params, mod_info, reporting_batch_list, logs)
+    loop.run(train_params.niteration)
     if res_info.is_lead_process:
         helpers.save_model(net_info.net, train_params.outdir)
 

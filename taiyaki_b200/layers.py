@@ -184,6 +184,11 @@ def _gate_major(w, G):
 DEFER_WEIGHT_GRADS = False
 _pending = []          # (event, tensors kept alive until the join)
 _side_streams = {}
+#: called as hook(last_parameter_of_the_layer, side_stream) at the start of a recurrent
+#: layer's backward, when every gradient of the layers ABOVE it is final (their weight-
+#: gradient GEMMs are on the side stream, everything else was accumulated on the current
+#: stream): training.FlatGradients uses it to start the all-reduce of those slices early
+GRADS_FINAL_ABOVE_HOOK = None
 
 
 def _side_stream(device):
@@ -254,6 +259,7 @@ class _Recurrence(torch.autograd.Function):
         ctx.save_for_backward(xo, wo, w_hh_c, y, reserve, y16)
         ctx.cfg = (cell, bool(reverse), b_ih is not None, G, H, I, um)
         ctx.weights = (w_ih, w_hh)
+        ctx.last_param = b_ih if b_ih is not None else w_hh
         if y16 is None:
             y16 = y.new_empty(0)
         ctx.mark_non_differentiable(y16)
@@ -267,6 +273,8 @@ class _Recurrence(torch.autograd.Function):
         cell, reverse, has_bias, G, H, I, um = ctx.cfg
         T, N, _ = y.shape
         dev = y.device
+        if GRADS_FINAL_ABOVE_HOOK is not None:
+            GRADS_FINAL_ABOVE_HOOK(ctx.last_param, _side_stream(dev))
         use16 = y16 is not None
         gdt = torch.bfloat16 if use16 else torch.float32
         if dy is None:

@@ -181,8 +181,54 @@ class FlatGradients:
                    base <= p.grad.data_ptr() < base + self.flat.numel() * 4
                    for p in self.params)
 
+    # ---- overlapped reduction (one sub-batch per step, NCCL) ----------------------
+    # Backward runs from the last layer to the first, so the gradients of the upper layers
+    # are final long before backward() returns.  `begin_overlap` arms a hook that the
+    # recurrent layers call at the start of their backward (layers.GRADS_FINAL_ABOVE_HOOK):
+    # the slice of the flat buffer belonging to the layers above is then all-reduced on the
+    # side stream (behind the weight-gradient GEMMs that write into it), under the backward
+    # recurrences of the layers below.  `all_reduce` reduces what is left and joins.
+    def begin_overlap(self):
+        if self.world <= 1 or not self.flat.is_cuda or dist.get_backend(self.group) != 'nccl':
+            return False
+        if not hasattr(self, '_end_offset'):
+            self._end_offset, off = {}, 0
+            for p in self.params:
+                off += p.numel()
+                self._end_offset[id(p)] = off
+        self._reduced_from = self.flat.numel()
+        self._works = []
+        layers.GRADS_FINAL_ABOVE_HOOK = self._grads_final_above
+        return True
+
+    def _grads_final_above(self, last_param, side):
+        start = self._end_offset.get(id(last_param))
+        if start is None or start >= self._reduced_from:
+            return
+        main = torch.cuda.current_stream(self.flat.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self._works.append(dist.all_reduce(self.flat[start:self._reduced_from],
+                                               op=dist.ReduceOp.AVG, group=self.group,
+                                               async_op=True))
+        self._reduced_from = start
+
     def all_reduce(self):
-        if self.world > 1:
+        if self.world <= 1:
+            return
+        if layers.GRADS_FINAL_ABOVE_HOOK is not None:       # overlapped mode: reduce the rest, join
+            layers.GRADS_FINAL_ABOVE_HOOK = None
+            if self._reduced_from > 0:
+                dist.all_reduce(self.flat[:self._reduced_from], op=dist.ReduceOp.AVG, group=self.group)
+            for w in self._works:
+                w.wait()                                    # current stream waits for the NCCL stream
+            self._works = []
+            return
+        if self.flat.is_cuda and dist.get_backend(self.group) == 'nccl':
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
 
@@ -212,7 +258,8 @@ class TrainStep:
     AdamW step (train_flipflop.py:570-578) as one callable."""
 
     def __init__(self, net_info, optimiser, rolling_mads=None, lr_scheduler=None,
-                 mod_info=None):
+                 mod_info=None, sub_batches=1):
+        self.sub_batches = sub_batches      # > 1: gradients accumulate over sub-batches, reduce at the end
         self.net_info = net_info
         self.optimiser = optimiser
         self.rolling_mads = rolling_mads
@@ -224,8 +271,14 @@ class TrainStep:
     def __call__(self, batch_gen, sharpen=1.0, mod_factor=1.0, read_back=True):
         self.flat.zero()
         mcw = None if self.mod_info is None else self.mod_info.mod_cat_weights
-        res = calculate_loss(self.net_info, batch_gen, sharpen, mcw, mod_factor,
-                             calc_grads=True)
+        if self.sub_batches == 1 and DEFER_WEIGHT_GRADS:
+            self.flat.begin_overlap()
+        try:
+            res = calculate_loss(self.net_info, batch_gen, sharpen, mcw, mod_factor,
+                                 calc_grads=True)
+        finally:
+            if layers.GRADS_FINAL_ABOVE_HOOK is not None and self.flat.world <= 1:
+                layers.GRADS_FINAL_ABOVE_HOOK = None
         self.flat.all_reduce()
         grad_maxs = apply_clipping(self.net_info, self.grad_max_threshs, self.flat)
         self.optimiser.step()
