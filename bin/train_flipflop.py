@@ -385,6 +385,7 @@ class TrainLoop:
         self.rejection_dict = defaultdict(int)
         self.curr_iter = 0
         self.next_shape = None
+        self.deferred_log = None
         self.time_last = time.time()
 
     def draw_batch_shape(self):
@@ -416,39 +417,32 @@ class TrainLoop:
                 min(1.0, curr_iter / mod_info.mod_factor.niter))
             batch_chunk_len, sub_batch_size = self.next_shape
             if self.prefetcher is not None:
-                # batches of iteration k+1 go onto the batching stream BEFORE the step of
-                # iteration k is enqueued: assembly and its read-back run under the step
-                if curr_iter + 1 < tp.niteration:
-                    self.next_shape = self.draw_batch_shape()
                 main_batch_gen = self.prefetcher.batches(tp.sub_batches)
             else:
                 main_batch_gen = training.prepare_random_batches(
                     self.read_data, batch_chunk_len, sub_batch_size, tp.sub_batches,
                     self.alphabet_info, self.filter_params, net_info, logs.main)
+            pending = self.step.enqueue(main_batch_gen, sharpen, mod_factor)
+            # With the step on the stream: the batches of iteration k+1 go onto the batching
+            # stream (assembly and its read-back run under this step), and the log lines of
+            # iteration k-1 are written -- the device never waits for host bookkeeping.
+            if self.prefetcher is not None and curr_iter + 1 < tp.niteration:
+                self.next_shape = self.draw_batch_shape()
+            self.flush_log()
             (chunk_count, _, chunk_samples, chunk_bases, batch_rejections), fval, grad_maxs = \
-                self.step(main_batch_gen, sharpen, mod_factor, read_back=True)
+                self.step.finish(pending)
             assert np.isfinite(fval), (
                 "Error: all costs must be finite, got {}.\n"
                 "Try restarting from a checkpoint with a lower learning rate.").format(fval)
-            if res_info.is_lead_process and logs.batch is not None:
-                thr = self.step.grad_max_threshs
-                thr_str = 'NaN' if thr is None else ','.join(str(float(t)) for t in thr)
-                logs.batch.write(BATCH_TMPLT.format(
-                    curr_iter + 1, fval, ','.join(map(str, grad_maxs)), thr_str,
-                    optim_info.lr_scheduler.get_last_lr()[0], batch_chunk_len))
-            self.total_samples += chunk_samples
+            assert np.all(np.isfinite(grad_maxs)), (
+                "Error: Gradients not finite.\n"
+                "Try restarting from a checkpoint with a lower learning rate.")
             self.samples_seen += chunk_samples
-            self.total_bases += chunk_bases
-            self.score_smoothed.update(fval)
-            for k, v in batch_rejections.items():
-                self.rejection_dict[k] += v
-            logs.main.write('.')
-            if (curr_iter + 1) % DOTROWLENGTH == 0:
-                log_polka(net_info, tp, optim_info, self.time_last, self.score_smoothed, curr_iter,
-                          self.total_samples, self.total_bases, self.rejection_dict, logs.main)
-                self.time_last = time.time()
-                self.total_bases = self.total_samples = 0
+            self.deferred_log = (curr_iter, fval, grad_maxs, self.step.grad_max_threshs,
+                                 optim_info.lr_scheduler.get_last_lr()[0], batch_chunk_len,
+                                 chunk_samples, chunk_bases, batch_rejections)
             if (curr_iter + 1) % tp.save_every == 0:
+                self.flush_log()
                 if res_info.is_lead_process:
                     saved = helpers.save_model(net_info.net, tp.outdir,
                                                (curr_iter + 1) // tp.save_every)
@@ -460,7 +454,34 @@ class TrainLoop:
             if self.prefetcher is None and curr_iter + 1 < tp.niteration:
                 self.next_shape = self.draw_batch_shape()
             self.curr_iter += 1
+        self.flush_log()
         return self.score_smoothed.value
+
+    def flush_log(self):
+        """batch.log line, progress dot and the 50-iteration summary of the last finished
+        iteration (train_flipflop.py:580-606)."""
+        if self.deferred_log is None:
+            return
+        (curr_iter, fval, grad_maxs, thr, lr, batch_chunk_len, chunk_samples, chunk_bases,
+         batch_rejections) = self.deferred_log
+        self.deferred_log = None
+        logs = self.logs
+        if self.res_info.is_lead_process and logs.batch is not None:
+            thr_str = 'NaN' if thr is None else ','.join(str(float(t)) for t in thr)
+            logs.batch.write(BATCH_TMPLT.format(
+                curr_iter + 1, fval, ','.join(map(str, grad_maxs)), thr_str, lr, batch_chunk_len))
+        self.total_samples += chunk_samples
+        self.total_bases += chunk_bases
+        self.score_smoothed.update(fval)
+        for k, v in batch_rejections.items():
+            self.rejection_dict[k] += v
+        logs.main.write('.')
+        if (curr_iter + 1) % DOTROWLENGTH == 0:
+            log_polka(self.net_info, self.train_params, self.optim_info, self.time_last,
+                      self.score_smoothed, curr_iter, self.total_samples, self.total_bases,
+                      self.rejection_dict, logs.main)
+            self.time_last = time.time()
+            self.total_bases = self.total_samples = 0
 
 
 def train_model(train_params, net_info, optim_info, res_info, read_data, alphabet_info,

@@ -107,6 +107,18 @@ int ty_flipflop_indices(const int64_t *seqs, const int64_t *seqlen, int nbatch,
                         int32_t *moveidx, int32_t *stayidx, int32_t *seqlen32,
                         int32_t *modmoveidx, float *modmovefact, void *stream);
 
+/* As ty_flipflop_indices; additionally ORs 1 into *bad_flag (device int32, may be
+ * NULL) when a label lies outside [0, 2 nbase) or a modification category outside its
+ * base's range -- the host assertions of ctc.pyx:133-134 as a flag the caller reads
+ * back whenever it next copies something to the host.  Bad values are clamped, so the
+ * index arrays are always safe to use. */
+int ty_flipflop_indices_checked(const int64_t *seqs, const int64_t *seqlen, int nbatch,
+                                int64_t total, int nbase, const int64_t *mod_cats,
+                                const int32_t *can_mods_offsets, const float *mod_cat_weights,
+                                int32_t *moveidx, int32_t *stayidx, int32_t *seqlen32,
+                                int32_t *modmoveidx, float *modmovefact, int32_t *bad_flag,
+                                void *stream);
+
 /* Partition function over the 2*nbase-state lattice.
  * scores: [nblk][nbatch] rows of `ld` floats of which the first
  * S = 2*nbase*(nbase+1) are transition scores (ld >= S lets the cat-mod

@@ -31,6 +31,9 @@ _SIGNATURES = {
     'ty_flipflop_indices': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
+    'ty_flipflop_indices_checked': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p]),
     'ty_flipflop_logz_workspace_bytes': (c_size_t, [c_int] * 3),
     'ty_flipflop_logz': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                  c_float, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),

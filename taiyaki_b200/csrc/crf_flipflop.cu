@@ -615,7 +615,7 @@ __global__ void indices_kernel(const int64_t *seqs, const int64_t *seqlen, int n
                                int64_t total, int nbase, const int64_t *mod_cats,
                                const int32_t *can_mods_offsets, const float *mod_cat_weights,
                                int32_t *moveidx, int32_t *stayidx, int32_t *seqlen32,
-                               int32_t *modmoveidx, float *modmovefact) {
+                               int32_t *modmoveidx, float *modmovefact, int32_t *bad_flag) {
     // s_off[b]: first label of chunk b; s_ne[b]: non-empty chunks before b.
     // Move entries are packed as the reference's Python packs them (one per
     // non-final position, ctc.pyx:127-129), i.e. at i - s_ne[b].
@@ -640,18 +640,29 @@ __global__ void indices_kernel(const int64_t *seqs, const int64_t *seqlen, int n
             if (s_off[mid] <= i) lo = mid; else hi = mid;
         }
         const int b = lo;
-        const int q = (int)seqs[i];
+        // labels outside [0, 2 nbase) are clamped so that no kernel gathers outside a score
+        // row; the operator layer raises the reference's assertion (ctc.pyx:133-134) from a
+        // device flag it reads back with the loss (ctc.check_pending)
+        const int64_t q_raw = seqs[i];
+        const int q = min(max((int)q_raw, 0), nstate - 1);
+        bool bad = q_raw != q;
         stayidx[i] = q + min(q, nbase) * nstate;
         if (i + 1 < s_off[b + 1]) {
-            const int qn = (int)seqs[i + 1];
+            const int qn = min(max((int)seqs[i + 1], 0), nstate - 1);
             const int64_t j = i - s_ne[b];
             moveidx[j] = q + min(qn, nbase) * nstate;
             if (modmoveidx) {
-                const int modseq = can_mods_offsets[qn % nbase] + (int)mod_cats[i + 1];
+                const int base = qn % nbase;
+                const int nmod = can_mods_offsets[base + 1] - can_mods_offsets[base];
+                const int64_t mc_raw = mod_cats[i + 1];
+                const int mc = min(max((int)mc_raw, 0), nmod - 1);
+                bad |= mc_raw != mc;
+                const int modseq = can_mods_offsets[base] + mc;
                 modmoveidx[j] = nstate * (nbase + 1) + modseq;
                 modmovefact[j] = mod_cat_weights[modseq];
             }
         }
+        if (bad && bad_flag) atomicOr(bad_flag, 1);
     }
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < nbatch; i += blockDim.x) seqlen32[i] = (int32_t)seqlen[i];
@@ -839,6 +850,17 @@ extern "C" int ty_flipflop_indices(const int64_t *seqs, const int64_t *seqlen, i
                                    const int32_t *can_mods_offsets, const float *mod_cat_weights,
                                    int32_t *moveidx, int32_t *stayidx, int32_t *seqlen32,
                                    int32_t *modmoveidx, float *modmovefact, void *stream) {
+    return ty_flipflop_indices_checked(seqs, seqlen, nbatch, total, nbase, mod_cats, can_mods_offsets,
+                                       mod_cat_weights, moveidx, stayidx, seqlen32, modmoveidx,
+                                       modmovefact, nullptr, stream);
+}
+
+extern "C" int ty_flipflop_indices_checked(const int64_t *seqs, const int64_t *seqlen, int nbatch,
+                                           int64_t total, int nbase, const int64_t *mod_cats,
+                                           const int32_t *can_mods_offsets,
+                                           const float *mod_cat_weights, int32_t *moveidx,
+                                           int32_t *stayidx, int32_t *seqlen32, int32_t *modmoveidx,
+                                           float *modmovefact, int32_t *bad_flag, void *stream) {
     if (!seqs || !seqlen || !moveidx || !stayidx || !seqlen32 || nbatch <= 0 || nbase <= 0) {
         set_error("ty_flipflop_indices: bad argument");
         return TY_EINVAL;
@@ -854,6 +876,6 @@ extern "C" int ty_flipflop_indices(const int64_t *seqs, const int64_t *seqlen, i
     const size_t smem = (size_t)(2 * nbatch + 1) * sizeof(int64_t);
     indices_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
         seqs, seqlen, nbatch, total, nbase, mod_cats, can_mods_offsets, mod_cat_weights,
-        moveidx, stayidx, seqlen32, modmoveidx, modmovefact);
+        moveidx, stayidx, seqlen32, modmoveidx, modmovefact, bad_flag);
     return check_launch("indices_kernel");
 }

@@ -35,6 +35,46 @@ def nstate_to_nbase(nstate):
     return int(nbase_f)
 
 
+#: Lazy input checks.  ctc.pyx:133-134 asserts label indices on the host, which here would
+#: cost a device synchronisation per call.  Instead the index kernel clamps bad labels (so
+#: nothing gathers out of bounds) and ORs into a per-device flag word
+#: (ty_flipflop_indices_checked); training.TrainStep copies the flag back with the loss of
+#: the step, `check_pending()` does it on demand; both raise the reference's AssertionError.
+_FLAGS = {}          # device index -> int32[1], ORed into by ty_flipflop_indices_checked
+
+
+def _flag_tensor(device):
+    t = _FLAGS.get(device.index)
+    if t is None:
+        t = _FLAGS[device.index] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
+
+
+def pending_flags(device=None):
+    """Snapshot of the label-range flag as a device tensor (None if no operator ran on
+    that device yet); the flag is cleared."""
+    if device is None:
+        if not _FLAGS:
+            return None
+        device = torch.device('cuda', next(iter(_FLAGS)))
+    t = _FLAGS.get(device.index)
+    if t is None:
+        return None
+    snap = t.clone()
+    t.zero_()
+    return snap
+
+
+def raise_if_flagged(flag_value):
+    assert not flag_value, 'Error: label indices out of range for the flip-flop model (ctc.pyx:133-134)'
+
+
+def check_pending():
+    for idx in list(_FLAGS):
+        flag = pending_flags(torch.device('cuda', idx))
+        raise_if_flagged(bool(flag.item()))
+
+
 def _as_device_i64(x, device):
     if not torch.is_tensor(x):
         x = torch.as_tensor(np.asarray(x))
@@ -83,10 +123,11 @@ def build_indices(seqs, seqlen, nbase, device, mod_cats=None, can_mods_offsets=N
             device=device, dtype=torch.float32).contiguous()
         modmove = torch.zeros(n, dtype=torch.int32, device=device)
         modfact = torch.zeros(n, dtype=torch.float32, device=device)
-    rc = lib.ty_flipflop_indices(
+    rc = lib.ty_flipflop_indices_checked(
         _lib.ptr(seqs_d), _lib.ptr(seqlen_d), nbatch, total, nbase, _lib.ptr(mod_d),
         _lib.ptr(off_d), _lib.ptr(w_d), _lib.ptr(move), _lib.ptr(stay), _lib.ptr(seqlen32),
-        _lib.ptr(modmove), _lib.ptr(modfact), _lib.stream_ptr(device))
+        _lib.ptr(modmove), _lib.ptr(modfact), _lib.ptr(_flag_tensor(device)),
+        _lib.stream_ptr(device))
     _lib.check(rc, 'ty_flipflop_indices')
     _lib.count_launches(1)
     return move, stay, seqlen32, modmove, modfact, max_len

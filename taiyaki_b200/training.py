@@ -267,8 +267,12 @@ class TrainStep:
         self.mod_info = mod_info
         self.flat = FlatGradients(net_info.net.parameters())
         self.grad_max_threshs = None
+        self._host_buf = None
 
-    def __call__(self, batch_gen, sharpen=1.0, mod_factor=1.0, read_back=True):
+    def enqueue(self, batch_gen, sharpen=1.0, mod_factor=1.0):
+        """Put one optimiser step on the stream without waiting for it; `finish` reads its
+        results back.  Splitting the two lets the caller enqueue the next batch's assembly
+        (and do its host bookkeeping) while the device is busy with this step."""
         self.flat.zero()
         mcw = None if self.mod_info is None else self.mod_info.mod_cat_weights
         if self.sub_batches == 1 and DEFER_WEIGHT_GRADS:
@@ -284,11 +288,37 @@ class TrainStep:
         self.optimiser.step()
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
-        loss_dev = res[1]
-        if not read_back:
-            return res, None, grad_maxs
         # one device->host copy per optimiser step: loss and gradient maxima together
-        host = torch.cat([loss_dev.reshape(1), grad_maxs]).cpu().numpy()
+        # label-range flag of the loss operators, read back with the loss (ctc.pyx:133-134)
+        flag = ctc.pending_flags(res[1].device) if res[1].is_cuda else None
+        packed = torch.cat([res[1].reshape(1), grad_maxs] +
+                           ([flag.to(torch.float32)] if flag is not None else []))
+        self._has_flag = flag is not None
+        if self._host_buf is None or self._host_buf.numel() != packed.numel():
+            self._host_buf = torch.empty(packed.numel(), dtype=torch.float32,
+                                         pin_memory=packed.is_cuda)
+        self._host_buf.copy_(packed, non_blocking=True)
+        done = None
+        if packed.is_cuda:
+            done = torch.cuda.Event()
+            done.record()
+        return res, grad_maxs, done
+
+    def finish(self, pending):
+        """Wait for an enqueued step; returns (calculate_loss tuple, loss, gradient maxima)."""
+        res, _, done = pending
+        if done is not None:
+            done.synchronize()
+        host = self._host_buf.numpy().copy()
+        if self._has_flag:
+            ctc.raise_if_flagged(host[-1] != 0)
+            host = host[:-1]
         if self.rolling_mads is not None:
             self.grad_max_threshs = self.rolling_mads.update(host[1:])
         return res, float(host[0]), host[1:]
+
+    def __call__(self, batch_gen, sharpen=1.0, mod_factor=1.0, read_back=True):
+        pending = self.enqueue(batch_gen, sharpen, mod_factor)
+        if not read_back:
+            return pending[0], None, pending[1]
+        return self.finish(pending)

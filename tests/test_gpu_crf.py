@@ -367,3 +367,18 @@ def test_fused_train_loss_equals_separate_operators(dev, oracle, ntrans):
     tol[:, :, :40] += RTOL * np.abs(gz) / nblk
     err = np.abs(x1.grad.cpu().numpy() * nbatch - want)
     assert np.all(err <= tol + 1e-5 / nblk), (err - tol).max() * nblk
+
+
+def test_bad_label_raises_reference_assertion_lazily(dev, oracle):
+    """ctc.pyx:133-134 asserts label indices on the host; here the kernels clamp and a
+    device flag is raised when somebody collects it (no synchronisation per call)."""
+    from taiyaki_b200 import ctc
+    ctc.check_pending()
+    scores = torch.tensor(oracle.synth_scores(30, 2, 40, seed=1), device=dev)
+    seqs = torch.tensor([0, 5, 1, 9, 2, 6])       # 9 is not a flip-flop label for 4 bases
+    cost = ctc.crf_flipflop_loss(scores, seqs, torch.tensor([3, 3]), 1.0)
+    assert torch.isfinite(cost).all()             # clamped, nothing read out of bounds
+    with pytest.raises(AssertionError, match='out of range'):
+        ctc.check_pending()
+    ctc.crf_flipflop_loss(scores, torch.tensor([0, 5, 1, 7, 2, 6]), torch.tensor([3, 3]), 1.0)
+    ctc.check_pending()                           # valid labels: no flag
