@@ -2,7 +2,7 @@
 taiyaki/layers.py (time-major [T, N, F] tensors, same class / attribute /
 parameter names so `state_dict`s and model-definition files carry over).
 
-  Lstm, GruMod              layers.py:491-725  recurrence in csrc/rnn.cu instead of cuDNN
+  Lstm, GruMod              layers.py:491-725  recurrence in csrc/rnn_ws.cu / rnn_fp32.cu instead of cuDNN
   Reverse                   layers.py:117-153  loop direction instead of two flips
   Serial, Convolution       layers.py:944-982, :744-850
   GlobalNormFlipFlop[CatMod] layers.py:1316-1640
@@ -65,27 +65,43 @@ def _reshape(x, shape):
 
 #: Operand type of the dense projection GEMMs around the recurrence
 #: (x W_ih^T, and the weight / input gradients): 'bf16' (tensor cores, fp32
-#: accumulate and fp32 result -- north_star's "dense bf16 contractions") or
-#: 'tf32' (what cuDNN does for the reference on Ampere and later).
+#: accumulate and fp32 result -- north_star's "dense bf16 contractions"),
+#: 'tf32' (what cuDNN does for the reference on Ampere and later) or 'fp32'
+#: (the parity mode: plain fp32 products, see `set_precision`).
 PROJECTION_DTYPE = 'bf16'
 
 
-class _tf32_matmul:
+class _matmul_tf32:
+    def __init__(self, allow):
+        self.allow = allow
+
     def __enter__(self):
         self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = self.allow
 
     def __exit__(self, *exc):
         torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
 def _mm(a, b):
-    """a @ b with fp32 result; bf16 operands go to the tensor cores with fp32
-    accumulation, fp32 operands use TF32."""
+    """a @ b with fp32 result through the library: bf16 operands with fp32
+    accumulation; fp32 operands as TF32 or, in the parity mode, true fp32."""
     if a.dtype == torch.bfloat16:
         return torch.mm(a, b, out_dtype=torch.float32)
-    with _tf32_matmul():
+    with _matmul_tf32(PROJECTION_DTYPE != 'fp32'):
         return torch.mm(a, b)
+
+
+def set_precision(mode):
+    """'bf16' (default): bf16 tensor-core products everywhere north_star allows them --
+    tcgen05 GEMMs for the projections, the bf16 recurrent product of csrc/rnn_ws.cu.
+    'fp32': the parity mode -- every product of the recurrent layers, the strided
+    convolution and the score projection in fp32 (csrc/rnn_fp32.cu for the recurrence),
+    which reproduces torch.nn.LSTM / nn.GRU fp32 to ~1e-5; ~10x slower."""
+    global PROJECTION_DTYPE, RNN_IMPL
+    assert mode in ('bf16', 'fp32')
+    PROJECTION_DTYPE = mode
+    RNN_IMPL = 'ws' if mode == 'bf16' else 'fp32'
 
 
 def _operand(t):
@@ -206,13 +222,16 @@ def flush_weight_grads():
     _pending = []
 
 
-#: 'ws' = warp-specialised kernels behind the unit-major ABI (csrc/rnn_ws.cu, bf16
-#: projections only); 'legacy' = one-role kernels behind the gate-major ABI (csrc/rnn.cu)
+#: 'ws' = warp-specialised bf16 tensor-core kernels behind the unit-major ABI
+#: (csrc/rnn_ws.cu; hidden sizes that are multiples of 64 up to 256); 'fp32' = the fp32
+#: recurrence behind the gate-major ABI (csrc/rnn_fp32.cu; any hidden size) -- selected
+#: by `set_precision('fp32')`, and automatically for sizes the cluster kernels lack
 RNN_IMPL = 'ws'
+CLUSTER_KERNEL_SIZES = (64, 128, 192, 256)
 
 
 class _Recurrence(torch.autograd.Function):
-    """y = RNN(x) with the sequential part in csrc/rnn_ws.cu (or csrc/rnn.cu).
+    """y = RNN(x) with the sequential part in csrc/rnn_ws.cu (or csrc/rnn_fp32.cu).
 
     forward:  xproj = x W_ih^T (one GEMM) -> ty_rnn_forward_* (adds b_ih)
     backward: ty_rnn_backward_* gives d xproj, the bias gradient (and the
@@ -231,7 +250,7 @@ class _Recurrence(torch.autograd.Function):
         G = 4 if cell == _CELL_LSTM else 3
         H = w_hh.shape[1]
         use16 = PROJECTION_DTYPE == 'bf16'
-        um = use16 and RNN_IMPL == 'ws'
+        um = use16 and RNN_IMPL == 'ws' and H in CLUSTER_KERNEL_SIZES
         w_hh_c = w_hh.detach().contiguous().float()
         if use16 and x16 is not None:
             xo = x16.view(T * N, I)            # bf16 copy written by the producing layer
@@ -338,14 +357,14 @@ class _Recurrence(torch.autograd.Function):
         _lib.count_launches(1)
         d2 = do.view(T * N, G * H)
         d_cur = do[sl_cur]
-        dx = _mm(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
-        dw_ih = _mm(d2.t(), xo)
+        dx = _mm_nn(d2, wo).view(T, N, I) if ctx.needs_input_grad[0] else None
+        dw_ih = _mm_tn(d2, xo)
         if cell == _CELL_LSTM:
-            dw_hh = _mm(d_cur.reshape(-1, G * H).t(), hp2)
+            dw_hh = _mm_tn(d_cur.reshape(-1, G * H), hp2)
         else:
             dw_hh = torch.cat([
-                _mm(d_cur[:, :, :2 * H].reshape(-1, 2 * H).t(), hp2),
-                _mm(dhn[sl_cur].reshape(-1, H).t(), hp2)], 0)
+                _mm_tn(d_cur[:, :, :2 * H].reshape(-1, 2 * H), hp2),
+                _mm_tn(dhn[sl_cur].reshape(-1, H), hp2)], 0)
         return dx, dw_ih, dw_hh, db, None, None, None
 
 

@@ -1,6 +1,8 @@
-"""GPU tests of the persistent LSTM / GRU kernels (csrc/rnn.cu).
+"""GPU tests of the recurrent kernels: the bf16 tensor-core cluster kernels
+(csrc/rnn_ws.cu, `um`) and the fp32 any-size recurrence (csrc/rnn_fp32.cu, `fp32`: the
+parity mode, pinned against torch.nn.LSTM / nn.GRU at 1e-4 over 800 steps).
 
-Two references, both plain PyTorch:
+References, all plain PyTorch:
   * `emulated`: the same recurrence with W_hh and h_{t-1} rounded to bf16 for
     the recurrent product (what the kernel computes) -- tight tolerance;
   * torch.nn.LSTM / nn.GRU in fp32 with bias_hh = 0 (what the reference's
@@ -66,10 +68,10 @@ def to_gate_major(t, G):
     return t.reshape(*lead, -1, G).transpose(-1, -2).reshape(*lead, -1).contiguous()
 
 
-IMPLS = ['legacy', 'um']
+IMPLS = ['fp32', 'um']
 
 
-def kernel_forward(cell, xproj, w_hh, reverse, impl='legacy'):
+def kernel_forward(cell, xproj, w_hh, reverse, impl='fp32'):
     """xproj is gate-major [T,N,G*H]; `um` permutes it to the unit-major ABI."""
     from taiyaki_b200 import _lib
     lib = _lib.lib()
@@ -91,7 +93,7 @@ def kernel_forward(cell, xproj, w_hh, reverse, impl='legacy'):
     return y, reserve
 
 
-def kernel_backward(cell, dy, w_hh, reverse, y, reserve, impl='legacy'):
+def kernel_backward(cell, dy, w_hh, reverse, y, reserve, impl='fp32'):
     """Returns the gradient of the gate-major xproj as fp32 (the `um` kernels
     write it unit-major in bf16)."""
     from taiyaki_b200 import _lib
@@ -137,10 +139,13 @@ def test_forward_vs_emulated(dev, cell, H, N, T, reverse, impl):
     y, _ = kernel_forward(cell, xproj, w_hh, reverse, impl)
     ref = ref_recurrence(cell, xproj, w_hh, reverse, emulate=True)
     torch.cuda.synchronize()
+    ref32 = ref_recurrence(cell, xproj, w_hh, reverse, emulate=False)
+    if impl == 'fp32':           # the parity mode computes the un-rounded recurrence
+        assert (y - ref32).abs().max().item() < 2e-5
+        return
     err = (y - ref).abs().max().item()
     assert err < 2e-3, err       # bf16 rounding of h can flip by one ulp between the two
     # against the un-rounded recurrence: the cost of the bf16 recurrent product
-    ref32 = ref_recurrence(cell, xproj, w_hh, reverse, emulate=False)
     assert (y - ref32).abs().max().item() < 5e-2
 
 
@@ -157,18 +162,21 @@ def test_backward_vs_autograd_of_emulated(dev, cell, H, N, T, reverse, impl):
     dy = torch.randn(T, N, H, device=dev)
     y, reserve = kernel_forward(cell, xproj.detach(), w_hh, reverse, impl)
     dx, dhn = kernel_backward(cell, dy, w_hh, reverse, y, reserve, impl)
-    ref = ref_recurrence(cell, xproj, w_hh, reverse, emulate=True)
+    ref = ref_recurrence(cell, xproj, w_hh, reverse, emulate=impl != 'fp32')
     ref.backward(dy)
     torch.cuda.synchronize()
     scale = xproj.grad.abs().max().item()
     err = (dx - xproj.grad).abs().max().item()
+    if impl == 'fp32':
+        assert err < 2e-5 * max(scale, 1.0), (err, scale)
+        return
     # the kernel also rounds the gate gradients to bf16 for the recurrent product
     assert err < 3e-2 * scale, (err, scale)
     rel = ((dx - xproj.grad).norm() / xproj.grad.norm()).item()
     assert rel < 1e-2, rel
 
 
-@pytest.mark.parametrize('impl', ['ws', 'legacy'])
+@pytest.mark.parametrize('impl', ['ws', 'fp32'])
 @pytest.mark.parametrize('cell', ['lstm', 'gru'])
 @pytest.mark.parametrize('reverse', [False, True])
 def test_module_vs_torch_nn(dev, cell, reverse, impl, monkeypatch):
@@ -176,6 +184,8 @@ def test_module_vs_torch_nn(dev, cell, reverse, impl, monkeypatch):
     torch.nn.LSTM / nn.GRU fp32 with the same weights."""
     from taiyaki_b200 import layers
     monkeypatch.setattr(layers, 'RNN_IMPL', impl)
+    monkeypatch.setattr(layers, 'PROJECTION_DTYPE', 'bf16' if impl == 'ws' else 'fp32')
+    tol = 3e-2 if impl == 'ws' else 1e-4
     torch.manual_seed(3)
     np.random.seed(3)
     T, N, I, H = 30, 8, 256, 256
@@ -195,15 +205,15 @@ def test_module_vs_torch_nn(dev, cell, reverse, impl, monkeypatch):
         y2 = nnmod(x2)[0]
     y2.backward(dy)
     torch.cuda.synchronize()
-    assert (y1 - y2).abs().max().item() < 3e-2
+    assert (y1 - y2).abs().max().item() < tol
     for (n1, p1), (n2, p2) in zip(src.named_parameters(), nnmod.named_parameters()):
         if 'bias_hh' in n1:
             assert p1.grad is None
             continue
         rel = ((p1.grad - p2.grad).norm() / p2.grad.norm()).item()
-        assert rel < 3e-2, (n1, rel)
+        assert rel < tol, (n1, rel)
     rel = ((x1.grad - x2.grad).norm() / x2.grad.norm()).item()
-    assert rel < 3e-2, rel
+    assert rel < tol, rel
 
 
 @pytest.mark.parametrize('impl', IMPLS)
@@ -217,5 +227,103 @@ def test_long_sequence_stability(dev, impl):
     ref = ref_recurrence('lstm', xproj, w_hh, False, emulate=False)
     torch.cuda.synchronize()
     assert torch.isfinite(y).all()
+    if impl == 'fp32':
+        assert (y - ref).abs().max().item() < 1e-4
+        return
     assert (y - ref).abs().max().item() < 8e-2
     assert (y - ref).abs().mean().item() < 5e-3
+
+
+@pytest.mark.parametrize('cell', ['lstm', 'gru'])
+def test_parity_mode_module_vs_torch_800_steps(dev, cell, monkeypatch):
+    """layers.set_precision('fp32'): Lstm / GruMod against torch.nn.LSTM / nn.GRU (cuDNN
+    with TF32 off, fp32 throughout) over 800 steps -- outputs and every gradient at 1e-4
+    (round-1 review: the bf16 kernels had no fp32-grade counterpart to be pinned against)."""
+    from taiyaki_b200 import layers
+    monkeypatch.setattr(layers, 'RNN_IMPL', 'fp32')
+    monkeypatch.setattr(layers, 'PROJECTION_DTYPE', 'fp32')
+    torch.manual_seed(11)
+    np.random.seed(11)
+    T, N, I, H = 800, 8, 256, 256
+    mod = (layers.Lstm(I, H) if cell == 'lstm' else layers.GruMod(I, H)).to(dev)
+    nnmod = (torch.nn.LSTM(I, H) if cell == 'lstm' else torch.nn.GRU(I, H)).to(dev)
+    src = mod.lstm if cell == 'lstm' else mod.cudnn_gru
+    nnmod.load_state_dict(src.state_dict())
+    x = torch.randn(T, N, I, device=dev)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    dy = torch.randn(T, N, H, device=dev) / np.sqrt(T)
+    y1 = mod(x1)
+    y1.backward(dy)
+    y2 = nnmod(x2)[0]
+    y2.backward(dy)
+    torch.cuda.synchronize()
+    assert (y1 - y2).abs().max().item() < 1e-4
+    for (n1, p1), (n2, p2) in zip(src.named_parameters(), nnmod.named_parameters()):
+        if 'bias_hh' in n1:
+            continue
+        rel = ((p1.grad - p2.grad).norm() / p2.grad.norm()).item()
+        assert rel < 1e-4, (n1, rel)
+    assert ((x1.grad - x2.grad).norm() / x2.grad.norm()).item() < 1e-4
+
+
+@pytest.mark.parametrize('cell', ['lstm', 'gru'])
+def test_bf16_kernels_vs_parity_mode_800_steps(dev, cell, monkeypatch):
+    """The production bf16 kernels against the fp32 parity mode on the same weights, 800
+    steps: what the bf16 recurrent product costs, measured (bounds with headroom)."""
+    from taiyaki_b200 import layers
+    torch.manual_seed(12)
+    np.random.seed(12)
+    T, N, I, H = 800, 16, 256, 256
+    mod = (layers.Lstm(I, H) if cell == 'lstm' else layers.GruMod(I, H)).to(dev)
+    x = torch.randn(T, N, I, device=dev)
+    dy = torch.randn(T, N, H, device=dev) / np.sqrt(T)
+    out = {}
+    for mode in ('bf16', 'fp32'):
+        monkeypatch.setattr(layers, 'RNN_IMPL', 'ws' if mode == 'bf16' else 'fp32')
+        monkeypatch.setattr(layers, 'PROJECTION_DTYPE', mode)
+        for p in mod.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        y = mod(xi)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        src = mod.lstm if cell == 'lstm' else mod.cudnn_gru
+        out[mode] = (y.detach(), xi.grad, [p.grad.clone() for n, p in src.named_parameters()
+                                           if 'bias_hh' not in n])
+    (y16, dx16, g16), (y32, dx32, g32) = out['bf16'], out['fp32']
+    print(cell, 'max |dy| %.4f mean %.5f; rel dx %.4f; rel dW %s' % (
+        (y16 - y32).abs().max().item(), (y16 - y32).abs().mean().item(),
+        ((dx16 - dx32).norm() / dx32.norm()).item(),
+        ['%.4f' % ((a - b).norm() / b.norm()).item() for a, b in zip(g16, g32)]))
+    assert (y16 - y32).abs().max().item() < 8e-2 and (y16 - y32).abs().mean().item() < 5e-3
+    assert ((dx16 - dx32).norm() / dx32.norm()).item() < 3e-2
+    for a, b in zip(g16, g32):
+        assert ((a - b).norm() / b.norm()).item() < 3e-2
+
+
+@pytest.mark.parametrize('H', [96, 384])
+@pytest.mark.parametrize('cell', ['lstm', 'gru'])
+def test_hidden_sizes_outside_the_cluster_kernels(dev, cell, H):
+    """size 96 (the reference's 'fast' models, README.md:354-359) and 384 (the default of
+    bin/_bin_argparse.py:16) run through the fp32 recurrence with bf16 projections and match
+    torch.nn at the tolerance of the bf16 projections."""
+    from taiyaki_b200 import layers
+    torch.manual_seed(H)
+    np.random.seed(H)
+    T, N, I = 40, 5, 64
+    mod = (layers.Lstm(I, H) if cell == 'lstm' else layers.GruMod(I, H)).to(dev)
+    nnmod = (torch.nn.LSTM(I, H) if cell == 'lstm' else torch.nn.GRU(I, H)).to(dev)
+    src = mod.lstm if cell == 'lstm' else mod.cudnn_gru
+    nnmod.load_state_dict(src.state_dict())
+    x = torch.randn(T, N, I, device=dev)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    dy = torch.randn(T, N, H, device=dev)
+    y1 = layers.Reverse(mod)(x1)
+    y1.backward(dy)
+    y2 = torch.flip(nnmod(torch.flip(x2, (0,)))[0], (0,))
+    y2.backward(dy)
+    assert (y1 - y2).abs().max().item() < 3e-2
+    assert ((x1.grad - x2.grad).norm() / x2.grad.norm()).item() < 3e-2
+    for (n1, p1), (n2, p2) in zip(src.named_parameters(), nnmod.named_parameters()):
+        if 'bias_hh' not in n1:
+            assert ((p1.grad - p2.grad).norm() / p2.grad.norm()).item() < 3e-2, n1
