@@ -5,8 +5,11 @@
 //       ([unit][8 chunks] rows of 16 bytes -- the layout h_t is exchanged in), and whether
 //       a zero stride (second 8-column group = the first) is honoured
 //   P3  thread <-> element map of tcgen05.ld.16x256b and a lane base of 32w + 16
-//   P4  latency of one recurrent product issued as tcgen05.mma (M = 128, N = 16, K = H,
-//       A in tensor memory): first issue -> commit observed -> accumulators in registers
+//   P4  latency of one recurrent product issued as tcgen05.mma (M = 128, N = 8..64, K = H):
+//       first issue -> commit observed -> accumulators in registers, with A in tensor memory
+//       (.ts form) and A in shared memory (.ss form, K-major un-swizzled core matrices); the
+//       issue loop is fully unrolled with compile-time operands (`latency` kernel below) --
+//       the loop of `probe` carries a run-time modulo and measures its own scalar code
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build_variants/tc5_probe tools/tc5_probe.cu
 #include <cuda_bf16.h>
 
@@ -129,6 +132,127 @@ __global__ void __launch_bounds__(160, 1) probe(const float *W, const float *h, 
     if (warp == 4) tmem_dealloc<256>(tmem);
 }
 
+
+// ---- P4: the product as the recurrence would issue it --------------------------------
+// A[128 gate rows][K = 256] bf16, B = h[K][NC chunks] bf16 (MN-major, rows of NC*2 bytes are
+// split in 16-byte pieces: piece p of row k at hs + p * (H*16) + k*16), D[128][NC] fp32.
+template <int NC, bool TS, int NMMA, int NACC>
+__global__ void __launch_bounds__(160, 1) latency(const float *W, const float *h, float *D, long long *clk,
+                                                  int reps, int swap_a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int NP = NC / 8;                        // 16-byte pieces per B row
+    unsigned char *hs = smem;                         // NP * H * 16 bytes
+    unsigned char *as = smem + 8 * H * 16;            // A, K-major core matrices: [k piece (8 el)][128 rows][16 B]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(as + 128 * H * 2);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(bar + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < H * NC; i += blockDim.x) {
+        const int k = i / NC, c = i % NC;
+        reinterpret_cast<__nv_bfloat16 *>(hs + (c / 8) * (H * 16) + k * 16)[c % 8] = __float2bfloat16(h[k * 8 + c % 8]);
+    }
+    for (int i = tid; i < 128 * H; i += blockDim.x) {
+        const int r = i / H, k = i % H;
+        reinterpret_cast<__nv_bfloat16 *>(as + (k / 8) * 2048 + r * 16)[k % 8] = __float2bfloat16(W[r * H + k]);
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(bar), 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<512>(smem_u32(tptr));
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tptr;
+    if (warp < 4) {
+        const float *src = W + (size_t)tid * H;
+        for (int kc = 0; kc < H / 16; kc++) {
+            uint32_t v[8];
+            for (int j = 0; j < 8; j++) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(src[kc * 16 + 2 * j], src[kc * 16 + 2 * j + 1]);
+                v[j] = *reinterpret_cast<uint32_t *>(&p);
+            }
+            tmem_st_32x8(tmem + ((uint32_t)(warp * 32) << 16) + kc * 8, v);
+        }
+        tmem_st_wait();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    constexpr uint32_t dcol = 128;
+    // B: LBO = K-direction stride of 8-row groups (128 B), SBO = N-direction stride (H*16)
+    const uint64_t bdesc = (uint64_t(1) << 46) | (uint64_t((H * 16) >> 4) << 32) | (uint64_t(128 >> 4) << 16) |
+                           uint64_t((smem_u32(hs) & 0x3FFFF) >> 4);
+    // A (.ss): core matrix = 8 rows x 16 B contiguous; next 8 rows +128 B; next k piece +2048 B
+    const uint32_t a_k = 2048, a_m = 128;
+    const uint32_t albo = swap_a ? a_m : a_k, asbo = swap_a ? a_k : a_m;
+    const uint64_t adesc = (uint64_t(1) << 46) | (uint64_t(asbo >> 4) << 32) | (uint64_t(albo >> 4) << 16) |
+                           uint64_t((smem_u32(as) & 0x3FFFF) >> 4);
+    const uint32_t idesc = idesc_bf16(128, NC, false, true);
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (int rep = 0; rep < reps; rep++) {
+        if (tid == 0) {
+            t0 = clock64();
+#pragma unroll
+            for (int k = 0; k < NMMA; k++) {
+                const uint32_t d = tmem + dcol + NC * (k % NACC);
+                if (TS)
+                    mma_ts(d, tmem + (k % 16) * 8, bdesc + (uint64_t)((256 * (k % 16)) >> 4), idesc, k >= NACC);
+                else
+                    mma_ss(d, adesc + (uint64_t)((4096 * (k % 16)) >> 4), bdesc + (uint64_t)((256 * (k % 16)) >> 4),
+                           idesc, k >= NACC);
+            }
+            t3 = clock64();
+            mma_commit(smem_u32(bar));
+        }
+        mbar_wait(smem_u32(bar), rep & 1);
+        fence_after_sync();
+        if (tid == 0) t1 = clock64();
+        if (warp < 4) {
+            uint32_t v[8];
+            tmem_ld_32x8(tmem + ((uint32_t)(warp * 32) << 16) + dcol, v);
+            tmem_ld_wait();
+            if (tid == 0) t2 = clock64();
+            if (rep == reps - 1)
+                for (int j = 0; j < 8; j++) D[tid * 8 + j] = __uint_as_float(v[j]);
+            fence_before_sync();
+        }
+        __syncthreads();
+        fence_after_sync();
+        if (tid == 0 && rep == reps - 1) {
+            clk[0] = t3 - t0;
+            clk[1] = t1 - t0;
+            clk[2] = t2 - t0;
+        }
+    }
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+template <int NC, bool TS, int NMMA, int NACC>
+static void run_latency(const float *dW, const float *dh, float *dD, long long *dclk, const std::vector<float> &ref,
+                        int swap_a) {
+    const int smem = 8 * H * 16 + 128 * H * 2 + 64;
+    cudaFuncSetAttribute(latency<NC, TS, NMMA, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaMemset(dD, 0, 128 * 8 * 4);
+    latency<NC, TS, NMMA, NACC><<<1, 160, smem>>>(dW, dh, dD, dclk, 20, swap_a);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("latency<%d,%d,%d,%d>: CUDA error %s\n", NC, (int)TS, NMMA, NACC, cudaGetErrorString(e)); exit(1); }
+    std::vector<float> o(128 * 8);
+    long long clk[3];
+    cudaMemcpy(o.data(), dD, o.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(clk, dclk, 24, cudaMemcpyDeviceToHost);
+    double err = 0;
+    if (NMMA == 16 && NACC == 1)
+        for (int r = 0; r < 128; r++)
+            for (int c = 0; c < 8; c++) err = fmax(err, fabs(o[r * 8 + c] - ref[r * NB + c]));
+    printf("N %2d  A in %s%s  %3d MMA over %2d acc: issue loop %4lld  issue->commit %4lld  issue->regs %4lld"
+           "  (%.1f cycles/MMA issued)", NC, TS ? "tmem" : "smem", TS ? "" : (swap_a ? " (lbo=m)" : " (lbo=k)"), NMMA, NACC,
+           clk[0], clk[1], clk[2], (double)clk[1] / NMMA);
+    if (NMMA == 16 && NACC == 1) printf("  max|D - ref| %.2e", err);
+    printf("\n");
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 int main() {
@@ -170,16 +294,22 @@ int main() {
                "16x256b map err %.3e  | cycles issue->commit %lld  issue->regs %lld\n",
                o.swap_half, o.swap_lbo, o.sbo_zero, e32, edup, e16, clk[0], clk[1]);
     }
-    printf("\nlatency of the product vs how it is issued (correct packing; cycles at the SM clock)\n");
-    const int cfg[][2] = {{1, 16}, {2, 16}, {4, 16}, {8, 16}, {16, 16}, {1, 1}, {1, 2}, {1, 4}, {1, 8}};
-    for (auto &c : cfg) {
-        Opt o{0, 0, 0, 20, c[0], c[1]};
-        probe<<<1, 160>>>(dW, dh, d32, d16, dclk, o);
-        cudaDeviceSynchronize();
-        long long clk[3];
-        cudaMemcpy(clk, dclk, 24, cudaMemcpyDeviceToHost);
-        printf("%2d MMA over %2d accumulator(s): issue loop %4lld  issue->commit %4lld  issue->regs %4lld\n", c[1], c[0],
-               clk[2], clk[0], clk[1]);
-    }
+    printf("\nlatency of one recurrent product (M 128, K 256; cycles at the SM clock; unrolled issue)\n");
+    float *dD;
+    cudaMalloc(&dD, 128 * 8 * 4);
+    // (M = 128 needs N % 16 == 0: 8 chunks are padded / duplicated to 16 columns)
+    run_latency<16, true, 16, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<16, true, 16, 4>(dW, dh, dD, dclk, ref, 0);
+    run_latency<16, false, 16, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<32, true, 16, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<64, true, 16, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<64, false, 16, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<16, true, 1, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<16, true, 4, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<16, true, 8, 1>(dW, dh, dD, dclk, ref, 0);
+    run_latency<16, true, 64, 4>(dW, dh, dD, dclk, ref, 0);
+    run_latency<16, false, 64, 4>(dW, dh, dD, dclk, ref, 0);
+    run_latency<64, true, 64, 4>(dW, dh, dD, dclk, ref, 0);
+    run_latency<64, false, 64, 4>(dW, dh, dD, dclk, ref, 0);
     return 0;
 }
