@@ -213,6 +213,11 @@ int ty_rnn_backward_ex(int cell, const float *dy, const float *w_hh, int T, int 
  * ty_rnn_reserve_bytes() bytes and is private to the forward / backward pair.
  * The weight gradients the caller forms from dxproj / dhid come out with the
  * same row permutation P. */
+/* 1 when the warp-specialised kernels cover this hidden size (multiples of 64 up to 448
+ * with clusters of 8; 32, 96, 160, 224 with clusters of 4 -- the reference's defaults are
+ * 256 / 384 and 96 for its "fast" models, bin/_bin_argparse.py:16, README.md:354-359);
+ * other sizes run through the gate-major fp32 entry points. */
+int ty_rnn_um_supported(int hidden);
 int ty_rnn_forward_um(int cell, const float *xproj, const float *bias,
                       const float *w_hh, int T, int N, int H, int reverse,
                       float *y, void *y_bf16, void *reserve, void *stream);

@@ -68,6 +68,7 @@ _SIGNATURES = {
     'ty_rnn_backward_ex': (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                    c_void_p]),
+    'ty_rnn_um_supported': (c_int, [c_int]),
     'ty_rnn_forward_um': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     'ty_rnn_backward_um': (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

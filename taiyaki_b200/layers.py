@@ -223,11 +223,23 @@ def flush_weight_grads():
 
 
 #: 'ws' = warp-specialised bf16 tensor-core kernels behind the unit-major ABI
-#: (csrc/rnn_ws.cu; hidden sizes that are multiples of 64 up to 256); 'fp32' = the fp32
+#: (csrc/rnn_ws.cuh; hidden sizes CLUSTER_KERNEL_SIZES, which include the reference's
+#: defaults 256 / 384 and the 96 of its "fast" models); 'fp32' = the fp32
 #: recurrence behind the gate-major ABI (csrc/rnn_fp32.cu; any hidden size) -- selected
 #: by `set_precision('fp32')`, and automatically for sizes the cluster kernels lack
 RNN_IMPL = 'ws'
-CLUSTER_KERNEL_SIZES = (64, 128, 192, 256)
+CLUSTER_KERNEL_SIZES = (32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 448)   # = ty_rnn_um_supported
+
+
+_warned_sizes = set()
+
+
+def _warn_slow_size(H):
+    if H not in _warned_sizes:
+        _warned_sizes.add(H)
+        import warnings
+        warnings.warn('taiyaki_b200: hidden size %d has no bf16 cluster kernel (sizes: %s); the recurrence '
+                      'runs through the fp32 parity kernels, ~50x slower' % (H, list(CLUSTER_KERNEL_SIZES)))
 
 
 class _Recurrence(torch.autograd.Function):
@@ -251,6 +263,8 @@ class _Recurrence(torch.autograd.Function):
         H = w_hh.shape[1]
         use16 = PROJECTION_DTYPE == 'bf16'
         um = use16 and RNN_IMPL == 'ws' and H in CLUSTER_KERNEL_SIZES
+        if use16 and RNN_IMPL == 'ws' and not um:
+            _warn_slow_size(H)
         w_hh_c = w_hh.detach().contiguous().float()
         if use16 and x16 is not None:
             xo = x16.view(T * N, I)            # bf16 copy written by the producing layer

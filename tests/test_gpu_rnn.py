@@ -130,7 +130,9 @@ def kernel_backward(cell, dy, w_hh, reverse, y, reserve, impl='fp32'):
 @pytest.mark.parametrize('cell', ['lstm', 'gru'])
 @pytest.mark.parametrize('H,N,T,reverse', [
     (256, 8, 24, False), (256, 13, 17, True), (64, 3, 9, False), (128, 16, 11, True),
-    (192, 9, 7, False), (256, 64, 3, False), (128, 20, 1, True)])
+    (192, 9, 7, False), (256, 64, 3, False), (128, 20, 1, True),
+    (96, 5, 12, False), (384, 9, 10, True), (32, 3, 6, False), (160, 8, 5, True), (224, 4, 7, False),
+    (320, 11, 6, False), (448, 8, 9, True)])
 def test_forward_vs_emulated(dev, cell, H, N, T, reverse, impl):
     torch.manual_seed(H + N + T)
     G = 4 if cell == 'lstm' else 3
@@ -153,7 +155,9 @@ def test_forward_vs_emulated(dev, cell, H, N, T, reverse, impl):
 @pytest.mark.parametrize('cell', ['lstm', 'gru'])
 @pytest.mark.parametrize('H,N,T,reverse', [(256, 8, 20, False), (256, 11, 13, True),
                                            (64, 5, 8, True), (192, 17, 6, False),
-                                           (128, 8, 1, False)])
+                                           (128, 8, 1, False), (96, 5, 12, True), (384, 9, 10, False),
+                                           (32, 3, 6, True), (160, 8, 5, False), (224, 4, 7, True),
+                                           (320, 11, 6, True), (448, 8, 9, False)])
 def test_backward_vs_autograd_of_emulated(dev, cell, H, N, T, reverse, impl):
     torch.manual_seed(7 + H + N)
     G = 4 if cell == 'lstm' else 3
@@ -301,13 +305,21 @@ def test_bf16_kernels_vs_parity_mode_800_steps(dev, cell, monkeypatch):
         assert ((a - b).norm() / b.norm()).item() < 3e-2
 
 
-@pytest.mark.parametrize('H', [96, 384])
+def test_cluster_kernel_sizes_match_the_library():
+    from taiyaki_b200 import _lib, layers
+    lib = _lib.lib()
+    assert tuple(h for h in range(1, 600) if lib.ty_rnn_um_supported(h)) == layers.CLUSTER_KERNEL_SIZES
+
+
+@pytest.mark.parametrize('H', [96, 384, 288])
 @pytest.mark.parametrize('cell', ['lstm', 'gru'])
-def test_hidden_sizes_outside_the_cluster_kernels(dev, cell, H):
+def test_hidden_sizes_of_the_reference(dev, cell, H):
     """size 96 (the reference's 'fast' models, README.md:354-359) and 384 (the default of
-    bin/_bin_argparse.py:16) run through the fp32 recurrence with bf16 projections and match
-    torch.nn at the tolerance of the bf16 projections."""
+    bin/_bin_argparse.py:16) run on the bf16 cluster kernels (clusters of 4 / W_hh partly in
+    shared memory); 288 has no cluster kernel and runs through the fp32 recurrence with bf16
+    projections.  All match torch.nn at the tolerance of the bf16 products."""
     from taiyaki_b200 import layers
+    assert (H in layers.CLUSTER_KERNEL_SIZES) == (H != 288)
     torch.manual_seed(H)
     np.random.seed(H)
     T, N, I = 40, 5, 64
