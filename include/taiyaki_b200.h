@@ -71,6 +71,15 @@ void cat_mod_flipflop_cost(const float *logprob, size_t ntrans, size_t nblk,
                            const float *modmovefacts, const int32_t *seqlen,
                            float *score);
 
+/* Tuning knobs for A/B timing (tools/microbench.py); negative = leave unchanged.
+ * forced_p: DP positions per thread (1, 2, 4, 8, 16; 0 = automatic, default, or TY_CRF_P);
+ * fused: 1 = chains with the posterior fused in where the chunk fits (default), 0 = always
+ * the chain kernel + posterior kernel pair (or TY_CRF_FUSED=0). */
+void ty_crf_tuning(int forced_p, int fused);
+/* Which kernels the last ty_crf_flipflop call of this process launched: 1 = chain kernel +
+ * posterior kernel, 2 = chains with the posterior fused in, 3 = cost only (0 = none yet). */
+int ty_crf_last_path(void);
+
 /* ---------------------------------------------------------------- (B) ---
  * Label-constrained CRF, device pointers.
  *

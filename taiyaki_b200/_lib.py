@@ -24,6 +24,8 @@ c_void_p, c_int, c_float, c_size_t, c_int64 = (
 _SIGNATURES = {
     'ty_last_error_string': (ctypes.c_char_p, []),
     'ty_version': (ctypes.c_char_p, []),
+    'ty_crf_tuning': (None, [c_int, c_int]),
+    'ty_crf_last_path': (c_int, []),
     'ty_crf_flipflop_workspace_bytes': (c_size_t, [c_int] * 5),
     'ty_crf_flipflop': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_float, c_int, c_float, c_void_p,

@@ -30,86 +30,9 @@
 //                      score minus the accumulated offsets); the 40 canonical
 //                      bins are then renormalised to sum to one exactly like
 //                      the reference's softmax, so Z_t only has to be close.
-#include "common.cuh"
+#include "crf_common.cuh"
 
 namespace ty {
-
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
-struct CrfArgs {
-    const float *logprob;
-    int ntrans, nblk, nbatch;
-    const int32_t *moveidx, *stayidx, *modmoveidx;
-    const float *modmovefact;
-    const int32_t *seqlen;
-    float sharp;
-    int nsharp;        // columns < nsharp are multiplied by sharp
-    int ncan;          // columns < ncan are stay / move transitions (carry the shift); the rest are cat-mod
-    float score_scale;
-    float *score_out;
-    float grad_scale;
-    float *grad_out;
-    // workspace
-    int *seqoff;       // [nbatch] prefix sums of seqlen
-    float *fb;         // [nbatch][2] forward / backward log2-scores
-    float *coff;       // [2][nbatch][nblk] accumulated log2 offsets of the stored rows
-    float *fwd_ws;     // [nbatch][nblk][Ls] alpha_t         (log2 domain, normalised)
-    float *bwd_ws;     // [nbatch][nblk][Ls] beta_{t+1}
-    // entries sorted by transition bin, per chunk; word = pos | move << 13 | bin << 14 | mm << 20
-    int *ent_n;        // [nbatch][2] entries in each list
-    uint32_t *ent_w;   // [nbatch][2 * Ls]  stays + moves, keyed by their own transition
-    float *ent_mf;     // [nbatch][2 * Ls]  MOD: factor of a move entry (0 for stays)
-    uint32_t *ent2_w;  // [nbatch][Ls]      MOD: moves keyed by their mod transition (bin = mod, mm = move)
-    float *ent2_mf;    // [nbatch][Ls]
-    int Ls;
-    int want_grad;
-    int nchain;        // CTAs that run chains; the rest sort
-};
-
-constexpr int kRing = 8;      // cp.async ring slots for raw score rows
-constexpr int kDepth = 6;     // rows in flight
-constexpr int kRowPad = 64;   // floats per row slot (ntrans <= 63); slot 63 = -1e30 pad
-constexpr int kPadSlot = 63;
-
-__device__ __forceinline__ float ex2f(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2f(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// log2(2^x + 2^y)
-__device__ __forceinline__ float logaddexp2(float x, float y) {
-    return fmaxf(x, y) + lg2f(1.0f + ex2f(-fabsf(x - y)));
-}
-
-// ---------------------------------------------------------------------------
-// Shared-memory accesses of the chain's step loop use 32-bit shared-window
-// addresses computed once and kept opaque: through generic pointers the compiler
-// re-derives the window base (S2R SR_CgaCtaId, ~25 cycles of latency) and the
-// thread index (S2R SR_TID.X) inside the loop, on the step's dependency chain.
-__device__ __forceinline__ float lds_v_f32(unsigned a) {
-    float v;
-    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_v_f32(unsigned a, float v) {
-    asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(a), "f"(v));
-}
-__device__ __forceinline__ unsigned opaque(unsigned x) {   // keeps a loop-invariant value in a register
-    unsigned y;
-    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
-    return y;
-}
-__device__ __forceinline__ unsigned pinned_tid() {         // not rematerialised as S2R in the loop
-    unsigned t;
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
-    return t;
-}
 
 // One chain.  Warp-specialised: warps 0..ncw-1 run the DP; the LAST warp is the
 // "transformer": it owns the cp.async ring, turns raw score rows into
@@ -685,9 +608,10 @@ static CrfWsLayout crf_layout(int nblk, int nbatch, int max_seqlen, int want_gra
     w.fb = take((size_t)nbatch * 2 * sizeof(float));
     if (want_grad) {
         const size_t ne = (size_t)nbatch * 2 * w.Ls;
-        w.coff = take((size_t)2 * nbatch * nblk * sizeof(float));
-        w.fwd = take((size_t)nbatch * nblk * w.Ls * sizeof(float));
-        w.bwd = take((size_t)nbatch * nblk * w.Ls * sizeof(float));
+        // nblk + 1 rows per chunk: the fused kernel also spills the vector both chains meet at
+        w.coff = take((size_t)2 * nbatch * (nblk + 1) * sizeof(float));
+        w.fwd = take((size_t)nbatch * (nblk + 1) * w.Ls * sizeof(float));
+        w.bwd = take((size_t)nbatch * (nblk + 1) * w.Ls * sizeof(float));
         w.ent_n = take((size_t)nbatch * 2 * sizeof(int));
         w.ent_w = take(ne * sizeof(uint32_t));
         w.ent_mf = take(ne * sizeof(float));
@@ -720,15 +644,33 @@ extern "C" size_t ty_crf_flipflop_workspace_bytes(int ntrans, int nblk, int nbat
     return crf_layout(nblk, nbatch, max_seqlen, want_grad).total;
 }
 
+ty::CrfTuning &ty::crf_tuning() {
+    // defaults from the environment, read once per process; ty_crf_tuning() changes them at run time
+    static CrfTuning t = [] {
+        CrfTuning v;
+        const char *e = getenv("TY_CRF_P");
+        v.forced_p = e ? atoi(e) : 0;
+        e = getenv("TY_CRF_FUSED");
+        v.fused = !(e && e[0] == '0');
+        return v;
+    }();
+    return t;
+}
+
+static int g_last_path = 0;
+extern "C" int ty_crf_last_path(void) { return g_last_path; }
+
+extern "C" void ty_crf_tuning(int forced_p, int fused) {
+    if (forced_p >= 0) crf_tuning().forced_p = forced_p;
+    if (fused >= 0) crf_tuning().fused = fused != 0;
+}
+
 int ty::crf_pick_p(int max_seqlen, bool mod) {
     // positions per thread: 4 keeps a 440-base chunk in four warps (one per
     // SM sub-partition); longer chunks widen the thread block first.  The cat-mod
     // chain (three gathers per position) measures 7 % faster with 8 positions
     // per thread and two DP warps (profiles/r1_microbench_v4.jsonl, tag B).
-    static const int forced = [] {          // tuning override, read once per process
-        const char *e = getenv("TY_CRF_P");
-        return e ? atoi(e) : 0;
-    }();
+    const int forced = crf_tuning().forced_p;      // TY_CRF_P / ty_crf_tuning(): tuning override
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) {
         const int cap = forced >= 8 ? 512 : 992;
         if ((max_seqlen + forced - 1) / forced <= cap) return forced;
@@ -800,6 +742,12 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
     a.nchain = want_grad ? 2 * nbatch : nbatch;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool mod = modmoveidx != nullptr;
+    // gradient wanted and the rows fit in shared memory: chains with the posterior fused in
+    if (want_grad && crf_fused_eligible(P, mod, w.Ls, max_seqlen)) {
+        g_last_path = 2;
+        return launch_crf_fused(a, P, mod, max_seqlen, s);
+    }
+    g_last_path = want_grad ? 1 : 3;
 #define TY_CHAIN(PP)                                           \
     case PP:                                                   \
         if (mod) launch_chain<PP, true>(a, max_seqlen, s);     \

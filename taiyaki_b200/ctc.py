@@ -153,7 +153,7 @@ def _run_crf(logprob, move, stay, modmove, modfact, seqlen32, max_len, sharpfact
             nsharp, -1.0 / (nblk * float(sharpfact)), _lib.ptr(cost), -1.0 / nblk,
             _lib.ptr(grads), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device))
     _lib.check(rc, 'ty_crf_flipflop')
-    _lib.count_launches(2 if want_grad else 1)
+    _lib.count_launches(2 if lib.ty_crf_last_path() == 1 else 1)   # chain + posterior kernels, or one fused kernel
     if CHECK_FINITE:
         assert bool(torch.isfinite(cost).all()), _FINITE_MSG.format(cost.cpu().numpy())
         if grads is not None:
@@ -259,7 +259,8 @@ class FlipFlopTrainLoss(torch.autograd.Function):
                 float(sharpfact), ncan, _lib.ptr(cost), _lib.ptr(logz), _lib.ptr(grads),
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device))
         _lib.check(rc, 'ty_flipflop_train_loss')
-        _lib.count_launches(4 if want_grad else 2)
+        # logZ chains + logZ posterior + CRF chains (+ CRF posterior kernel unless it is fused into the chains)
+        _lib.count_launches((3 + (lib.ty_crf_last_path() == 1)) if want_grad else 2)
         if want_grad:
             ctx.save_for_backward(grads)
         return cost + logz

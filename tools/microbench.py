@@ -81,17 +81,21 @@ def bench_crf(nblk, nbatch, ntrans, stride, tag):
     else:
         def run(want_grad):
             return ctc.crf_flipflop_cost_grad(scores, seqs_t, seqlen_t, 1.0, want_grad)
-    for P in ([1, 2, 4, 8] if nblk <= 2000 else [4, 8]):
-        os.environ['TY_CRF_P'] = str(P)
+    from taiyaki_b200 import _lib
+    lib = _lib.lib()
+    for fused, P in [(1, 0), (0, 0), (0, 1), (0, 2), (0, 4), (0, 8)]:
+        if nblk > 2000 and P in (1, 2):
+            continue
+        lib.ty_crf_tuning(P, fused)
         try:
             med, mn = timeit(lambda: run(True))
         except Exception as e:
-            emit(what='crf_grad', tag=tag, P=P, error=str(e))
+            emit(what='crf_grad', tag=tag, P=P, fused=fused, error=str(e))
             continue
-        emit(what='crf_grad(indices+chain+post)', tag=tag, nblk=nblk, N=nbatch, S=ntrans, P=P,
-             ms_median=med, ms_min=mn, alg_GBps=alg_bytes / med / 1e6,
+        emit(what='crf_grad(indices+chain+post)', tag=tag, nblk=nblk, N=nbatch, S=ntrans, P=P or 'auto',
+             fused=fused, ms_median=med, ms_min=mn, alg_GBps=alg_bytes / med / 1e6,
              mean_L=float(np.mean(seqlen)))
-    os.environ.pop('TY_CRF_P', None)
+    lib.ty_crf_tuning(0, 1)
     med, mn = timeit(lambda: run(False))
     emit(what='crf_cost_only', tag=tag, nblk=nblk, N=nbatch, ms_median=med, ms_min=mn)
     x = scores.detach()[:, :, :40]
