@@ -120,6 +120,63 @@ def test_train_flipflop_entry_point(dev, tmp_path):
     assert 'ksample/s' in (out / 'model.log').read_text()
 
 
+def test_train_flipflop_entry_point_all_default_flags(dev, tmp_path):
+    """Every flag at its default (size 384, bin/_bin_argparse.py:16; chunk lengths 3000-8000 in
+    sub-batches of 128): the round-1 library refused size 384.  Only the number of iterations is
+    cut."""
+    out = tmp_path / 'training'
+    cmd = [sys.executable, os.path.join(ROOT, 'bin', 'train_flipflop.py'), '--niteration', '8',
+           '--warmup_batches', '2', '--quiet', '--overwrite', '--outdir', str(out),
+           os.path.join(ROOT, 'models', 'mLstm_flipflop.py'), 'synthetic:48']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert 'no bf16 cluster kernel' not in r.stderr
+    batch = (out / 'batch.log').read_text().strip().splitlines()
+    assert len(batch) == 9
+    assert all(np.isfinite(float(line.split('\t')[1])) for line in batch[1:])
+    assert (out / 'model_final.checkpoint').exists()
+
+
+def test_training_curve_bf16_kernels_vs_fp32_parity_mode(dev):
+    """200 optimiser steps of mLstm_flipflop on the same batches, initial weights and seeds, once
+    with the production kernels (bf16 tensor-core products) and once in the fp32 parity mode
+    (`layers.set_precision('fp32')`, pinned against cuDNN fp32 at 1e-4 in test_gpu_rnn.py): the
+    curves track each other and the smoothed final losses agree within 1 %."""
+    from taiyaki_b200 import chunk_selection, layers, signal_mapping, training
+    from taiyaki_b200.alphabet import AlphabetInfo
+    ai = AlphabetInfo('ACGT', 'ACGT')
+    reads = signal_mapping.synthetic_reads(24, seed=4)
+    curves = {}
+    try:
+        for mode in ('bf16', 'fp32'):
+            layers.set_precision(mode)
+            np.random.seed(7)
+            torch.manual_seed(7)
+            net_info = build(dev, 'mLstm_flipflop.py', 64, ai)
+            fp = chunk_selection.sample_filter_parameters(reads, 50, 1000, 10.0, 10.0, 0.1, net_info.stride, 1.1)
+            opt = torch.optim.AdamW(net_info.net.parameters(), lr=2e-3, eps=1e-6)
+            step = training.TrainStep(net_info, opt, mod_info=training.MOD_INFO(np.ones(4, dtype=np.float32), None))
+            batches = [list(training.prepare_random_batches(reads, 1000, 16, 1, ai, fp, net_info, None))
+                       for _ in range(20)]
+            losses = []
+            for it in range(200):
+                _, loss, gmax = step(iter(batches[it % 20]), sharpen=1.0, mod_factor=1.0)
+                assert np.isfinite(loss), (mode, it)
+                losses.append(loss)
+            curves[mode] = np.array(losses)
+    finally:
+        layers.set_precision('bf16')
+    a, b = curves['bf16'], curves['fp32']
+    fa, fb = a[-20:].mean(), b[-20:].mean()
+    print('loss first %.4f / %.4f, last-20 mean %.4f (bf16) / %.4f (fp32), max |diff| over the run %.4f'
+          % (a[0], b[0], fa, fb, np.abs(a - b).max()))
+    assert fb < b[0] - 0.1                      # the run trains
+    assert abs(a[0] - b[0]) < 2e-2 * abs(b[0])  # same first loss up to the bf16 products
+    assert abs(fa - fb) < 1e-2 * abs(fb), (fa, fb)
+    sm = lambda v: np.convolve(v, np.ones(10) / 10, mode='valid')
+    assert np.abs(sm(a) - sm(b)).max() < 3e-2 * np.abs(sm(b)).max()
+
+
 @pytest.mark.parametrize('fun', ['linear', 'swish', 'tanh'])
 @pytest.mark.parametrize('C,Cout,k,stride', [(1, 4, 5, 1), (4, 16, 5, 1), (16, 256, 19, 5),
                                              (1, 256, 19, 2), (3, 8, 7, 1)])
