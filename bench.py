@@ -45,16 +45,20 @@ sys.path.insert(0, ROOT)
 
 T_SIG, NCHUNK, SIZE, STRIDE, NTRANS = 4000, 64, 256, 5, 40
 METRIC = 'signal_samples_per_sec_flipflop_train_step'
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the four loss kernels at this
-# workload, from one `ncu --set full` capture (profiles/r1_ncu_full_summary_v4.csv)
-NCU_TRAFFIC_BYTES = int((8.95 + 122.64 + 198.96 + 6.45 + 8.24 + 0.0 + 11.47 + 0.0) * 1e6)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the loss kernels at this workload, from
+# `ncu --set full` captures (profiles/r2_ncu_loss_summary.csv): crf_fused_kernel 33.19 + 68.43 MB,
+# logz_chain_kernel 8.24 + 0, logz_post_kernel 11.47 + 0  (round 1, chain + posterior kernel pair
+# with the full alpha / beta spill: 356.7 MB)
+NCU_TRAFFIC_BYTES = int((33.19 + 68.43 + 8.24 + 0.0 + 11.47 + 0.0) * 1e6)
+NCU_TRAFFIC_SOURCE = ('profiles/r2_ncu_loss_summary.csv: dram read+write of crf_fused_kernel + logz_chain_kernel + '
+                      'logz_post_kernel, one launch each, config A')
 WORKLOAD = 'mLstm_flipflop size256 stride5, T_sig=4000 (nblk=800), 64 chunks/GPU, S=40'
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--ref-chunks', type=int, default=16,
@@ -358,14 +362,17 @@ def run_arm():
     rnnb_ms = [a.elapsed_time(b) for a, b in prof.get('rnn_bwd', [])]
     crf_avg = float(np.mean(crf_ms)) if crf_ms else float('nan')
     achieved = alg_bytes / (crf_avg * 1e-3) / 1e9
-    kname = ('ty_flipflop_train_loss: crf_chain_kernel || logz_chain_kernel, crf_post_kernel, '
-             'logz_post_kernel (fused CRF loss + logZ/nblk, fwd-bwd)' if key == 'loss_fwd_bwd'
-             else 'crf_chain_kernel + crf_post_kernel (CRF fwd-bwd)')
+    fused_crf = _lib.lib().ty_crf_last_path() == 2
+    crf_kernels = ('crf_fused_kernel (label-constrained chains with the posterior fused in)' if fused_crf
+                   else 'crf_chain_kernel, crf_post_kernel')
+    kname = ('ty_flipflop_train_loss: %s || logz_chain_kernel, logz_post_kernel (CRF loss + logZ/nblk, '
+             'forward-backward and gradient)' % crf_kernels if key == 'loss_fwd_bwd'
+             else crf_kernels + ' (CRF fwd-bwd)')
     roofline = {'bound': 'hbm', 'kernel': kname,
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': NCU_TRAFFIC_BYTES if key == 'loss_fwd_bwd' else None,
-                'traffic_source': 'profiles/r1_ncu_full_summary_v4.csv: dram read+write of crf_chain + '
-                                  'crf_post + logz_chain + logz_post, one launch each, config A',
+                'traffic': NCU_TRAFFIC_BYTES if (key == 'loss_fwd_bwd' and fused_crf and T_SIG == 4000
+                                                 and NTRANS == 40) else None,
+                'traffic_source': NCU_TRAFFIC_SOURCE,
                 'peak_source': peak_src, 'algorithmic_bytes': alg_bytes,
                 'avg_launch_ms': crf_avg, 'launches_timed': len(crf_ms),
                 'share_of_step': crf_avg / (ms_dev / K),
@@ -432,6 +439,36 @@ def run_arm():
                           % (args.ref_chunks, T_SIG)}
         except Exception as e:     # the baseline is informational; never fail the bench on it
             cpu_baseline = {'value': None, 'error': str(e)[:200]}
+        # the reference's GPU path for the partition function (its CuPy RawKernels compiled with nvcc by
+        # oracle/build_cupy_ref.py) next to csrc/logz.cu on the same scores, for context
+        try:
+            from oracle import oracle
+            from taiyaki_b200 import layers
+            if oracle.libcupy_ref() is not None:
+                sc = (5.0 * torch.tanh(torch.randn(nblk, NCHUNK, 40, device=device))).contiguous()
+
+                def gpu_ms(fn, reps=5):
+                    fn()
+                    torch.cuda.synchronize()
+                    ts = []
+                    for _ in range(reps):
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        fn()
+                        b.record()
+                        torch.cuda.synchronize()
+                        ts.append(a.elapsed_time(b))
+                    return float(np.median(ts))
+
+                def ours():
+                    x = sc.detach().requires_grad_(True)
+                    layers.flipflop_logpartition(x).sum().backward()
+                extra['reference_gpu_path'] = {
+                    'what': 'logZ + gradient of [%d, %d, 40] scores: the reference CuPy RawKernels '
+                            '(cupy_extensions/flipflop.py:10-296) under nvcc vs csrc/logz.cu' % (nblk, NCHUNK),
+                    'reference_ms': gpu_ms(lambda: oracle.cupy_ref_logz(sc)), 'ours_ms': gpu_ms(ours)}
+        except Exception as e:
+            extra['reference_gpu_path'] = {'error': str(e)[:200]}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': K,

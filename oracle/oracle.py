@@ -64,6 +64,54 @@ def have_ref():
     return libref() is not None
 
 
+LARGE_VAL = 1e30          # taiyaki/constants.py:8
+_libcupy = None
+
+
+def libcupy_ref():
+    """oracle/_ref/libcupy_ref.so: the reference's CuPy RawKernels compiled with nvcc
+    (oracle/build_cupy_ref.py), or None when it was not built."""
+    global _libcupy
+    if _libcupy is None:
+        _libcupy = _load(os.path.join(_HERE, '_ref', 'libcupy_ref.so')) or False
+    return _libcupy or None
+
+
+def cupy_ref_logz(scores, want_trans=True):
+    """The reference's GPU path for the partition function on a CUDA tensor [T, N, S]
+    (cupy_extensions/flipflop.py:88-126 flipflop_fwd, :211-246 flipflop_bwd, :299-336
+    flipflop_make_trans, :338-355 LogZ): returns (logZ [N], d logZ / d scores [T, N, S]).
+    The tensor set-up around the three launches is the reference wrappers'."""
+    import torch
+    lib = libcupy_ref()
+    assert lib is not None, 'oracle/_ref/libcupy_ref.so was not built'
+    c_void_p, c_ll = ctypes.c_void_p, ctypes.c_longlong
+    T, N, S = scores.shape
+    nbase = nbase_flipflop(S)
+    scores = scores.contiguous()
+    stream = c_void_p(torch.cuda.current_stream(scores.device).cuda_stream)
+    fwd = torch.zeros((T + 1, N, 2 * nbase), dtype=scores.dtype, device=scores.device)
+    fwd[0, :, nbase:] = -LARGE_VAL
+    fwd_fact = torch.zeros((T + 1, N, 1), dtype=scores.dtype, device=scores.device)
+    rc = lib.ref_cupy_flipflop_fwd(c_void_p(scores.data_ptr()), c_void_p(fwd.data_ptr()),
+                                   c_void_p(fwd_fact.data_ptr()), c_ll(T), c_ll(N), c_ll(nbase), stream)
+    assert rc == 0, rc
+    logz = fwd_fact.sum(0)[:, 0]
+    if not want_trans:
+        return logz, None
+    bwd = torch.zeros((T + 1, N, 2 * nbase), dtype=scores.dtype, device=scores.device)
+    bwd_fact = torch.zeros((T + 1, N, 1), dtype=scores.dtype, device=scores.device)
+    rc = lib.ref_cupy_flipflop_bwd(c_void_p(scores.data_ptr()), c_void_p(bwd.data_ptr()),
+                                   c_void_p(bwd_fact.data_ptr()), c_ll(T), c_ll(N), c_ll(nbase), stream)
+    assert rc == 0, rc
+    trans = torch.zeros_like(scores)
+    rc = lib.ref_cupy_flipflop_make_trans(c_void_p(scores.data_ptr()), c_void_p(fwd.data_ptr()),
+                                          c_void_p(bwd.data_ptr()), c_void_p(trans.data_ptr()),
+                                          c_ll(T), c_ll(N), c_ll(nbase), stream)
+    assert rc == 0, rc
+    return logz, trans.softmax(2)
+
+
 # --------------------------------------------------------------------------
 # flip-flop coding (taiyaki/flipflopfings.py)
 # --------------------------------------------------------------------------

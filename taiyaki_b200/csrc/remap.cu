@@ -170,6 +170,8 @@ extern "C" int ty_flipflop_remap(const float *scores, const int64_t *t_off, cons
     const int Sp = (S + 3) & ~3;
     int threads = ((max_m + 31) / 32) * 32;
     threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
+    // thread t stages score column t of a row: at least S threads (alphabets of 6+ bases have S > 64)
+    if (threads < ((S + 31) / 32) * 32) threads = ((S + 31) / 32) * 32;
     const size_t smem = (size_t)a.mp * 18 + (size_t)2 * Sp * 4;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (smem + 2048 <= 227 * 1024) {          // 2 KB left for the traceback window

@@ -9,8 +9,10 @@ of the reader on layouts the reference's per-read fixture files do not contain.
 Status: files are read back by hdf5_min.py; this image has no libhdf5 / h5py, so they have
 NOT been opened with the HDF5 library itself.  Node sizes and fan-outs follow the library's
 rules (symbol-table nodes of 2 x leaf-K entries, B-tree nodes padded to full size, chunk
-trees of at most 64 entries per node with as many levels as needed).  Limits: one global
-heap collection of 1 MiB for all strings (read ids), at most 256 links per group."""
+trees of at most 64 entries per node with as many levels as needed).  Strings (read ids) go
+to global heap collections of 1 MiB that are added as they fill up (at most 65535 objects
+each; a string that was already stored is referenced again instead of stored twice).
+Limit: at most 256 links per group."""
 import struct
 import zlib
 
@@ -28,9 +30,13 @@ def _pad8(b):
 
 class Writer:
     def __init__(self):
-        self.buf = bytearray(96 + GCOL_BYTES)    # superblock and heap collection written last
-        self.gcol = 96
-        self.strings = []                        # global heap objects
+        self.buf = bytearray(96)                 # superblock, written last
+        self.collections = []                    # global heap collections: [address, objects, bytes used]
+        self.string_refs = {}                    # raw string -> (collection address, object index)
+        self._new_collection()
+
+    def _new_collection(self):
+        self.collections.append([self.alloc(bytes(GCOL_BYTES)), [], 16])   # 16 = collection header
 
     def alloc(self, data):
         self.buf += bytes(-len(self.buf) % 8)
@@ -63,8 +69,19 @@ class Writer:
         out = b''
         for v in values:
             raw = v.encode('utf-8')
-            self.strings.append(raw)
-            out += struct.pack('<IQI', len(raw), self.gcol, len(self.strings))
+            ref = self.string_refs.get(raw)
+            if ref is None:
+                need = 16 + len(raw) + (-len(raw) % 8)               # object header + padded data
+                assert need + 32 <= GCOL_BYTES, 'string longer than a heap collection'
+                coll = self.collections[-1]
+                # keep room for the free-space object that ends a collection
+                if coll[2] + need + 16 > GCOL_BYTES or len(coll[1]) >= 65535:
+                    self._new_collection()
+                    coll = self.collections[-1]
+                coll[1].append(raw)
+                coll[2] += need
+                ref = self.string_refs[raw] = (coll[0], len(coll[1]))
+            out += struct.pack('<IQI', len(raw), ref[0], ref[1])
         return out
 
     def header(self, messages):
@@ -166,14 +183,15 @@ class Writer:
         return self.header(msgs), btree, heap
 
     def close(self, root_header, root_btree, root_heap, filename):
-        coll = b''
-        for i, raw in enumerate(self.strings):
-            coll += struct.pack('<HHIQ', i + 1, 1, 0, len(raw)) + _pad8(raw)
-        head = b'GCOL' + struct.pack('<B3xQ', 1, GCOL_BYTES)
-        free = GCOL_BYTES - len(head) - len(coll)
-        assert free >= 16, 'global heap collection of the minimal writer is full'
-        coll += struct.pack('<HHIQ', 0, 0, 0, free)
-        self.buf[self.gcol:self.gcol + len(head) + len(coll)] = head + coll
+        for addr, objects, used in self.collections:
+            coll = b''
+            for i, raw in enumerate(objects):
+                coll += struct.pack('<HHIQ', i + 1, 1, 0, len(raw)) + _pad8(raw)
+            head = b'GCOL' + struct.pack('<B3xQ', 1, GCOL_BYTES)
+            free = GCOL_BYTES - len(head) - len(coll)
+            assert len(head) + len(coll) == used and free >= 16
+            coll += struct.pack('<HHIQ', 0, 0, 0, free)
+            self.buf[addr:addr + len(head) + len(coll)] = head + coll
         sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, GROUP_LEAF_K, GROUP_INTERNAL_K, 0)
         sb += struct.pack('<QQQQ', 0, UNDEF, len(self.buf), UNDEF)
         sb += struct.pack('<QQII', 0, root_header, 1, 0) + struct.pack('<QQ', root_btree, root_heap)

@@ -133,11 +133,22 @@ def remap_reads(reads, model, per_read_params_dict, alphabet_info, max_read_leng
                 localpen=localpen)
             for (i, _, _, start, params), (_, path) in zip(todo, aligned):
                 read = reads[i]
-                int_ref = SignalMapping.get_integer_reference(read['ref'], alphabet_info.alphabet)
-                sig_mapping = SignalMapping.from_remapping_path(
-                    path, int_ref, model_stride, np.asarray(read['dacs']), start,
-                    read_id=read['read_id'], shift_frompA=params['shift'],
-                    scale_frompA=params['scale'], range=read['range'], offset=read['offset'],
-                    digitisation=read['digitisation'])
+                # a bad reference or mapping fails THIS read, not the batch (the reference's
+                # oneread_remap returns (None, message) per read, prepare_mapping_funcs.py:77-110,
+                # and SignalMapping.check() keeps malformed mappings out of the training file)
+                try:
+                    int_ref = SignalMapping.get_integer_reference(read['ref'], alphabet_info.alphabet)
+                    sig_mapping = SignalMapping.from_remapping_path(
+                        path, int_ref, model_stride, np.asarray(read['dacs']), start,
+                        read_id=read['read_id'], shift_frompA=params['shift'],
+                        scale_frompA=params['scale'], range=read['range'], offset=read['offset'],
+                        digitisation=read['digitisation'])
+                    from .mapped_signal_files import check_read
+                    problem = check_read(sig_mapping)
+                except Exception as e:
+                    problem = 'remapping failed: %s' % e
+                if problem != 'pass':
+                    results[i] = (None, problem)
+                    continue
                 results[i] = (sig_mapping.get_read_dictionary(), RemapResult.SUCCESS)
     return results

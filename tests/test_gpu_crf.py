@@ -281,6 +281,24 @@ def test_golden_logz(dev, golden_random, tag):
     np.testing.assert_allclose(x.grad.cpu().numpy(), g[tag + '_logz_grad'], rtol=RTOL, atol=3e-6)
 
 
+@pytest.mark.parametrize('nblk,nbatch', [(1, 2), (7, 3), (100, 5), (800, 64)])
+def test_logz_matches_the_reference_gpu_kernels(dev, oracle, nblk, nbatch):
+    """csrc/logz.cu against the reference's OWN GPU path on the same device: the CUDA C of its
+    CuPy RawKernels (cupy_extensions/flipflop.py:10-296) compiled by oracle/build_cupy_ref.py;
+    logZ and its gradient (LogZ.forward / backward, flipflop.py:338-355)."""
+    from taiyaki_b200 import layers
+    if oracle.libcupy_ref() is None:
+        pytest.skip('oracle/_ref/libcupy_ref.so was not built (needs /root/reference at build time)')
+    scores = torch.tensor(oracle.synth_scores(nblk, nbatch, 40, seed=nblk), device=dev)
+    lz_ref, g_ref = oracle.cupy_ref_logz(scores)
+    x = scores.clone().requires_grad_(True)
+    lz = layers.flipflop_logpartition(x)
+    lz.sum().backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(lz.detach().cpu().numpy(), lz_ref.cpu().numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g_ref.cpu().numpy(), rtol=RTOL, atol=3e-6)
+
+
 def test_logz_decodeutil_golden(dev, kat):
     from taiyaki_b200 import layers
     w = torch.tensor(kat['du_weights'][:, None, :], device=dev)

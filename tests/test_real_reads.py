@@ -128,6 +128,36 @@ def test_batched_mapped_signal_file(g, tmp_path):
         np.testing.assert_array_equal(msr.get_read(reads[4].read_id).Dacs, reads[4].Dacs)
 
 
+def test_batched_file_with_tens_of_thousands_of_reads(tmp_path):
+    """Read ids are variable-length strings in global heap collections: the writer adds collections
+    as they fill up (round-1 advice: a single 1 MiB collection overflowed at ~9.3k reads, at close(),
+    after all the remapping work) and stores an id once although two datasets reference it."""
+    from taiyaki_b200 import mapped_signal_files
+    from taiyaki_b200.hdf5_min_write import Writer, write_batched_mapped_signal_file
+    n = 40000
+    rng = np.random.RandomState(0)
+    reads = [dict(read_id='%08x-%04x-4%03x-a%03x-%012x' % tuple(rng.randint(0, 2 ** 31, size=5) % (
+                      16 ** 8, 16 ** 4, 16 ** 3, 16 ** 3, 16 ** 12)),
+                  Dacs=np.arange(6, dtype=np.int16) + i % 7, Ref_to_signal=np.array([0, 2, 4, 6], dtype=np.int32),
+                  Reference=np.array([0, 1, 2], dtype=np.int16), shift_frompA=0.0, scale_frompA=1.0,
+                  range=1.0, offset=0.0, digitisation=1.0) for i in range(n)]
+    fn = str(tmp_path / 'many.hdf5')
+    write_batched_mapped_signal_file(fn, reads, batch_size=1000, chunk=4096)
+    with mapped_signal_files.MappedSignalReader(fn) as msr:
+        ids = msr.get_read_ids()
+        # (batch groups are name-ordered, Batch_10 before Batch_2, in the reference's files too)
+        assert len(ids) == n and sorted(ids) == sorted(r['read_id'] for r in reads)
+        assert len(msr.batch_names) == 40
+        last = msr.get_read(reads[-1]['read_id'])
+        np.testing.assert_array_equal(last.Dacs, reads[-1]['Dacs'])
+        got = [r.read_id for r in msr.reads([reads[12345]['read_id'], reads[777]['read_id']])]
+        assert sorted(got) == sorted([reads[12345]['read_id'], reads[777]['read_id']])
+    w = Writer()
+    w.vlen_refs(['x' * 40 + str(i) for i in range(70000)] * 2)
+    assert len(w.collections) >= 2 and all(len(c[1]) <= 65535 for c in w.collections)
+    assert sum(len(c[1]) for c in w.collections) == 70000          # stored once, referenced twice
+
+
 def test_mapped_signal_writer_round_trip(g, tmp_path):
     """MappedSignalWriter (read dictionaries in, batched file out) -> MappedSignalReader,
     with a modified-base alphabet and one batch per two reads."""

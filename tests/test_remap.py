@@ -186,6 +186,25 @@ def test_remap_batch_equals_single(g, dev):
 
 
 @pytest.mark.gpu
+def test_remap_six_base_alphabet_short_reference(dev):
+    """84 transitions per row with fewer than 64 positions: every score column must be staged
+    (round-1 advice: the block had max(64, positions) threads and thread t staged column t)."""
+    from oracle import oracle
+    from taiyaki_b200 import flipflop_remap
+    rng = np.random.RandomState(6)
+    alphabet = 'ACGTXY'
+    T, L = 120, 30
+    seq = ''.join(alphabet[b] for b in rng.randint(0, 6, size=L))
+    step, stay = flipflop_remap.remap_indices(seq, alphabet)
+    assert max(step.max(), stay.max()) >= 64
+    scores = rng.standard_normal((T, 84)).astype('f4')
+    score, path = flipflop_remap.flipflop_remap(torch.tensor(scores, device=dev), seq, alphabet=alphabet)
+    oscore, opath = oracle.map_to_crf_viterbi(scores, step, stay, 1e30)
+    assert score == oscore
+    np.testing.assert_array_equal(path, opath)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('T,L,pen', [(8000, 3500, 1e30), (6000, 2500, 2.0), (15000, 13500, 1e30),
                                      (300, 400, 1e30)])
 def test_remap_full_size(dev, T, L, pen):

@@ -104,6 +104,14 @@ def bench_crf(nblk, nbatch, ntrans, stride, tag):
     emit(what='logz+posterior', tag=tag, nblk=nblk, N=nbatch, ms_median=med, ms_min=mn)
     med, mn = timeit(lambda: layers.flipflop_logpartition(x))
     emit(what='logz_only', tag=tag, nblk=nblk, N=nbatch, ms_median=med, ms_min=mn)
+    if oracle.libcupy_ref() is not None:
+        # the reference's GPU path: its CuPy RawKernels compiled with nvcc (oracle/build_cupy_ref.py)
+        med, mn = timeit(lambda: oracle.cupy_ref_logz(x))
+        emit(what='reference_gpu_logz+posterior (CuPy RawKernels under nvcc)', tag=tag, nblk=nblk, N=nbatch,
+             ms_median=med, ms_min=mn)
+        med, mn = timeit(lambda: oracle.cupy_ref_logz(x, want_trans=False))
+        emit(what='reference_gpu_logz_only (CuPy RawKernels under nvcc)', tag=tag, nblk=nblk, N=nbatch,
+             ms_median=med, ms_min=mn)
 
 
 def bench_rnn(cell, T, N, H, tag, kernels_only=False):
