@@ -283,7 +283,11 @@ def load_network(args, alphabet_info, res_info, log):
         rolling_mads = None
     else:
         nparams = len([p for p in network.parameters() if p.requires_grad])
-        rolling_mads = maths.RollingMAD(nparams, args.gradient_clip_num_mads)
+        # history and thresholds on the training device: the loop does not have to read the maxima
+        # back before it can enqueue the next step
+        param_device = next(network.parameters()).device
+        rolling_mads = maths.RollingMAD(nparams, args.gradient_clip_num_mads,
+                                        device=param_device if param_device.type == 'cuda' else None)
         log.write(('* Gradients will be clipped (by value) at {:3.2f} MADs above the median of '
                    'the last {} gradient maximums.\n').format(rolling_mads.n_mads,
                                                               rolling_mads.window))
@@ -386,6 +390,7 @@ class TrainLoop:
         self.curr_iter = 0
         self.next_shape = None
         self.deferred_log = None
+        self.lr_of_iter = {}
         self.time_last = time.time()
 
     def draw_batch_shape(self):
@@ -408,6 +413,27 @@ class TrainLoop:
         last = min(tp.niteration, self.curr_iter + niter)
         if self.next_shape is None and self.curr_iter < tp.niteration:
             self.next_shape = self.draw_batch_shape()
+        # With `step.pipelined` (no host-side clipping state) iteration k+1 is enqueued BEFORE the
+        # results of iteration k are read back, so the device never drains between optimiser steps;
+        # the results of k are processed while k+1 runs.  `in_flight` = the enqueued, unread iteration.
+        in_flight = None
+
+        def complete(item):
+            pending, curr_iter, batch_chunk_len = item
+            (chunk_count, _, chunk_samples, chunk_bases, batch_rejections), fval, grad_maxs = \
+                self.step.finish(pending)
+            assert np.isfinite(fval), (
+                "Error: all costs must be finite, got {}.\n"
+                "Try restarting from a checkpoint with a lower learning rate.").format(fval)
+            assert np.all(np.isfinite(grad_maxs)), (
+                "Error: Gradients not finite.\n"
+                "Try restarting from a checkpoint with a lower learning rate.")
+            self.samples_seen += chunk_samples
+            self.flush_log()
+            self.deferred_log = (curr_iter, fval, grad_maxs, self.step.grad_max_threshs,
+                                 self.lr_of_iter.pop(curr_iter), batch_chunk_len,
+                                 chunk_samples, chunk_bases, batch_rejections)
+
         while self.curr_iter < last:
             curr_iter = self.curr_iter
             sharpen = float(tp.sharpen.min + (tp.sharpen.max - tp.sharpen.min) *
@@ -422,26 +448,21 @@ class TrainLoop:
                 main_batch_gen = training.prepare_random_batches(
                     self.read_data, batch_chunk_len, sub_batch_size, tp.sub_batches,
                     self.alphabet_info, self.filter_params, net_info, logs.main)
+            self.lr_of_iter[curr_iter] = optim_info.lr_scheduler.get_last_lr()[0]
             pending = self.step.enqueue(main_batch_gen, sharpen, mod_factor)
             # With the step on the stream: the batches of iteration k+1 go onto the batching
             # stream (assembly and its read-back run under this step), and the log lines of
             # iteration k-1 are written -- the device never waits for host bookkeeping.
             if self.prefetcher is not None and curr_iter + 1 < tp.niteration:
                 self.next_shape = self.draw_batch_shape()
-            self.flush_log()
-            (chunk_count, _, chunk_samples, chunk_bases, batch_rejections), fval, grad_maxs = \
-                self.step.finish(pending)
-            assert np.isfinite(fval), (
-                "Error: all costs must be finite, got {}.\n"
-                "Try restarting from a checkpoint with a lower learning rate.").format(fval)
-            assert np.all(np.isfinite(grad_maxs)), (
-                "Error: Gradients not finite.\n"
-                "Try restarting from a checkpoint with a lower learning rate.")
-            self.samples_seen += chunk_samples
-            self.deferred_log = (curr_iter, fval, grad_maxs, self.step.grad_max_threshs,
-                                 optim_info.lr_scheduler.get_last_lr()[0], batch_chunk_len,
-                                 chunk_samples, chunk_bases, batch_rejections)
-            if (curr_iter + 1) % tp.save_every == 0:
+            if in_flight is not None:
+                complete(in_flight)
+            in_flight = (pending, curr_iter, batch_chunk_len)
+            save_now = (curr_iter + 1) % tp.save_every == 0
+            if not self.step.pipelined or save_now or curr_iter + 1 >= last:
+                complete(in_flight)
+                in_flight = None
+            if save_now:
                 self.flush_log()
                 if res_info.is_lead_process:
                     saved = helpers.save_model(net_info.net, tp.outdir,

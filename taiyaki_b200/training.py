@@ -245,8 +245,11 @@ def apply_clipping(net_info, grad_max_threshs, flat=None):
         [p for p in net_info.net.parameters() if p.requires_grad]
     grad_maxs = torch.stack(torch._foreach_norm([p.grad for p in parameters], float('inf')))
     if grad_max_threshs is not None:
-        thr = torch.as_tensor(np.asarray(grad_max_threshs, dtype=np.float32),
-                              device=grad_maxs.device)
+        if torch.is_tensor(grad_max_threshs):     # device-resident thresholds (maths.RollingMAD(device=...))
+            thr = grad_max_threshs.to(device=grad_maxs.device, dtype=torch.float32)
+        else:
+            thr = torch.as_tensor(np.asarray(grad_max_threshs, dtype=np.float32),
+                                  device=grad_maxs.device)
         for p, t in zip(parameters, thr):
             # clamp to [-t, t] is a no-op where max|grad| <= t
             torch.minimum(torch.maximum(p.grad, -t, out=p.grad), t, out=p.grad)
@@ -266,8 +269,16 @@ class TrainStep:
         self.lr_scheduler = lr_scheduler
         self.mod_info = mod_info
         self.flat = FlatGradients(net_info.net.parameters())
-        self.grad_max_threshs = None
-        self._host_buf = None
+        self.grad_max_threshs = None        # host copy (what batch.log prints)
+        self._thr_dev = None                # device-resident thresholds of the next step's clipping
+        self._host_bufs = [None, None]      # two steps can be in flight (see `pipelined`)
+        self._nstep = 0
+
+    @property
+    def pipelined(self):
+        """True when step k+1 may be enqueued before the results of step k have been read back:
+        the clipping thresholds either do not exist or live on the device."""
+        return self.rolling_mads is None or getattr(self.rolling_mads, 'device', None) is not None
 
     def enqueue(self, batch_gen, sharpen=1.0, mod_factor=1.0):
         """Put one optimiser step on the stream without waiting for it; `finish` reads its
@@ -284,36 +295,46 @@ class TrainStep:
             if layers.GRADS_FINAL_ABOVE_HOOK is not None and self.flat.world <= 1:
                 layers.GRADS_FINAL_ABOVE_HOOK = None
         self.flat.all_reduce()
-        grad_maxs = apply_clipping(self.net_info, self.grad_max_threshs, self.flat)
+        device_thr = self.rolling_mads is not None and getattr(self.rolling_mads, 'device', None) is not None
+        grad_maxs = apply_clipping(self.net_info, self._thr_dev if device_thr else self.grad_max_threshs,
+                                   self.flat)
         self.optimiser.step()
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
-        # one device->host copy per optimiser step: loss and gradient maxima together
-        # label-range flag of the loss operators, read back with the loss (ctc.pyx:133-134)
+        if device_thr:      # thresholds of the NEXT step, computed where the maxima are (train_flipflop.py:577-578)
+            self._thr_dev = self.rolling_mads.update(grad_maxs)
+        # one device->host copy per optimiser step: loss, gradient maxima, (device thresholds for the
+        # log,) and the label-range flag of the loss operators (ctc.pyx:133-134)
         flag = ctc.pending_flags(res[1].device) if res[1].is_cuda else None
+        nthr = len(grad_maxs) if (device_thr and self._thr_dev is not None) else 0
         packed = torch.cat([res[1].reshape(1), grad_maxs] +
+                           ([self._thr_dev.to(torch.float32)] if nthr else []) +
                            ([flag.to(torch.float32)] if flag is not None else []))
-        self._has_flag = flag is not None
-        if self._host_buf is None or self._host_buf.numel() != packed.numel():
-            self._host_buf = torch.empty(packed.numel(), dtype=torch.float32,
-                                         pin_memory=packed.is_cuda)
-        self._host_buf.copy_(packed, non_blocking=True)
+        buf = self._host_bufs[self._nstep & 1]
+        if buf is None or buf.numel() != packed.numel():
+            buf = self._host_bufs[self._nstep & 1] = torch.empty(packed.numel(), dtype=torch.float32,
+                                                                pin_memory=packed.is_cuda)
+        self._nstep += 1
+        buf.copy_(packed, non_blocking=True)
         done = None
         if packed.is_cuda:
             done = torch.cuda.Event()
             done.record()
-        return res, grad_maxs, done
+        return res, grad_maxs, done, buf, flag is not None, nthr, device_thr
 
     def finish(self, pending):
         """Wait for an enqueued step; returns (calculate_loss tuple, loss, gradient maxima)."""
-        res, _, done = pending
+        res, _, done, buf, has_flag, nthr, device_thr = pending
         if done is not None:
             done.synchronize()
-        host = self._host_buf.numpy().copy()
-        if self._has_flag:
+        host = buf.numpy().copy()
+        if has_flag:
             ctc.raise_if_flagged(host[-1] != 0)
             host = host[:-1]
-        if self.rolling_mads is not None:
+        if nthr:
+            self.grad_max_threshs = host[-nthr:]
+            host = host[:-nthr]
+        if self.rolling_mads is not None and not device_thr:
             self.grad_max_threshs = self.rolling_mads.update(host[1:])
         return res, float(host[0]), host[1:]
 
