@@ -262,6 +262,16 @@ int ty_im2col_time_major_bf16(const float *x, int T, int N, int C, int k, int st
  * (db may be NULL) and writes dx [T][N][C] unless it is NULL.
  * ty_conv_small_supported() tells which (C, Cout, k) are instantiated. */
 int ty_conv_small_supported(int C, int Cout, int k);
+/* Single-channel strided feature convolution (first layer of the reference's mGru models,
+ * Convolution(1, size, 19, stride=2); layers.py:795) as direct fp32 kernels: x [T][N][1],
+ * w [Cout][k], z [Tout][N][Cout] = b + conv (pre-activation); ty_conv_in1_wgrad ADDS the weight
+ * and bias gradients of dz into dw [Cout][k] / db [Cout] (zero them first).  The input is the
+ * signal, so there is no input gradient.  Supported: C == 1, k <= 32. */
+int ty_conv_in1_supported(int C, int Cout, int k);
+int ty_conv_in1_forward(const float *x, const float *w, const float *b, int T, int N, int Cout,
+                        int k, int stride, int pad_left, int Tout, float *z, void *stream);
+int ty_conv_in1_wgrad(const float *x, const float *dz, int T, int N, int Cout, int k, int stride,
+                      int pad_left, int Tout, float *dw, float *db, void *stream);
 int ty_conv_small_forward(const float *x, const float *w, const float *b, int T, int N,
                           int C, int Cout, int k, int pad_left, int act, float *z,
                           float *a, void *stream);

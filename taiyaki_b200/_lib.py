@@ -53,6 +53,9 @@ _SIGNATURES = {
     'ty_im2col_time_major_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_int, c_int, c_void_p, c_void_p]),
     'ty_conv_small_supported': (c_int, [c_int] * 3),
+    'ty_conv_in1_supported': (c_int, [c_int] * 3),
+    'ty_conv_in1_forward': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p, c_void_p]),
+    'ty_conv_in1_wgrad': (c_int, [c_void_p] * 2 + [c_int] * 7 + [c_void_p] * 3),
     'ty_conv_small_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'ty_conv_small_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

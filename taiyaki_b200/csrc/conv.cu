@@ -292,6 +292,96 @@ __global__ void __launch_bounds__(256) col2im_tm_ld_kernel(const float *__restri
     }
 }
 
+// ---------------------------------------------------------------------------
+// Single-channel strided feature convolution (the first layer of mGru_flipflop.py /
+// mGru_cat_mod_flipflop.py: Convolution(1, size, 19, stride=2), layers.py:795 nn.Conv1d) as direct
+// fp32 kernels -- as a GEMM it is [T_out*N x 19] . [19 x size]: too narrow for a tensor-core tile,
+// and bf16 would round the raw signal.  z[t][n][c] = b[c] + sum_j w[c][j] x[t*stride + j - pad][n].
+// Tile = one output time x kIn1Rows chunks: the k x rows signal window is staged in shared memory
+// (rows are contiguous in x), thread c keeps its k weights in registers; persistent blocks.
+constexpr int kIn1Rows = 32, kIn1MaxK = 32;
+
+template <int K>
+__global__ void __launch_bounds__(256) conv_in1_fwd_kernel(const float *__restrict__ x,
+                                                           const float *__restrict__ w,
+                                                           const float *__restrict__ b, int T, int N,
+                                                           int Cout, int stride, int pad_left, int Tout,
+                                                           float *__restrict__ z) {
+    __shared__ float xs[kIn1MaxK][kIn1Rows];
+    const int k = K > 0 ? K : Cout >> 16, cout = K > 0 ? Cout : Cout & 0xffff;
+    const int ntile_n = (N + kIn1Rows - 1) / kIn1Rows;
+    const int ntiles = Tout * ntile_n;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t = tile / ntile_n, n0 = (tile - t * ntile_n) * kIn1Rows;
+        __syncthreads();
+        for (int i = threadIdx.x; i < k * kIn1Rows; i += blockDim.x) {
+            const int j = i / kIn1Rows, r = i - j * kIn1Rows;
+            const int ts = t * stride + j - pad_left, n = n0 + r;
+            xs[j][r] = (ts >= 0 && ts < T && n < N) ? x[(size_t)ts * N + n] : 0.f;
+        }
+        __syncthreads();
+        const int rows = min(kIn1Rows, N - n0);
+        for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+            float wr[K > 0 ? K : kIn1MaxK];
+#pragma unroll
+            for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++) wr[j] = j < k ? w[(size_t)c * k + j] : 0.f;
+            const float bc = b ? b[c] : 0.f;
+            float *zo = z + ((size_t)t * N + n0) * cout + c;
+            for (int r = 0; r < rows; r++) {
+                float acc = bc;
+#pragma unroll
+                for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++) acc = fmaf(wr[j], xs[j][r], acc);
+                zo[(size_t)r * cout] = acc;
+            }
+        }
+    }
+}
+
+// dw[c][j] += sum_{t,n} dz[t][n][c] x[t*stride + j - pad][n],  db[c] += sum dz[t][n][c]
+template <int K>
+__global__ void __launch_bounds__(256) conv_in1_wgrad_kernel(const float *__restrict__ x,
+                                                             const float *__restrict__ dz, int T, int N,
+                                                             int Cout, int stride, int pad_left, int Tout,
+                                                             float *__restrict__ dw, float *__restrict__ db) {
+    __shared__ float xs[kIn1MaxK][kIn1Rows];
+    const int k = K > 0 ? K : Cout >> 16, cout = K > 0 ? Cout : Cout & 0xffff;
+    const int ntile_n = (N + kIn1Rows - 1) / kIn1Rows;
+    const int ntiles = Tout * ntile_n;
+    // a thread serves channels c = tid, tid + 256, ...: one register set per pass over the tiles
+    for (int c0 = 0; c0 < cout; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        float acc[K > 0 ? K : kIn1MaxK], accb = 0.f;
+#pragma unroll
+        for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++) acc[j] = 0.f;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int t = tile / ntile_n, n0 = (tile - t * ntile_n) * kIn1Rows;
+            __syncthreads();
+            for (int i = threadIdx.x; i < k * kIn1Rows; i += blockDim.x) {
+                const int j = i / kIn1Rows, r = i - j * kIn1Rows;
+                const int ts = t * stride + j - pad_left, n = n0 + r;
+                xs[j][r] = (ts >= 0 && ts < T && n < N) ? x[(size_t)ts * N + n] : 0.f;
+            }
+            __syncthreads();
+            if (c < cout) {
+                const int rows = min(kIn1Rows, N - n0);
+                const float *dzo = dz + ((size_t)t * N + n0) * cout + c;
+                for (int r = 0; r < rows; r++) {
+                    const float d = dzo[(size_t)r * cout];
+                    accb += d;
+#pragma unroll
+                    for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++) acc[j] = fmaf(d, xs[j][r], acc[j]);
+                }
+            }
+        }
+        if (c < cout) {
+#pragma unroll
+            for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++)
+                if (j < k) atomicAdd(dw + (size_t)c * k + j, acc[j]);
+            if (db) atomicAdd(db + c, accb);
+        }
+    }
+}
+
 static inline unsigned grid_for(long long work, int per_block) {
     long long b = (work + per_block - 1) / per_block;
     if (b > 148 * 16) b = 148 * 16;
@@ -390,3 +480,44 @@ extern "C" int ty_col2im_time_major_ld(const float *dcols, int ld, int Tout, int
                                                                pad_left, T, dx);
     return check_launch("col2im_tm_ld_kernel");
 }
+
+extern "C" int ty_conv_in1_supported(int C, int Cout, int k) {
+    return C == 1 && k >= 1 && k <= kIn1MaxK && Cout >= 1 && Cout <= 0xffff;
+}
+
+// grid: persistent blocks, a few per SM
+static inline unsigned in1_grid(int Tout, int N) {
+    const long long tiles = (long long)Tout * ((N + kIn1Rows - 1) / kIn1Rows);
+    return (unsigned)(tiles < 148 * 4 ? (tiles < 1 ? 1 : tiles) : 148 * 4);
+}
+
+extern "C" int ty_conv_in1_forward(const float *x, const float *w, const float *b, int T, int N, int Cout,
+                                   int k, int stride, int pad_left, int Tout, float *z, void *stream) {
+    if (!x || !w || !z || T <= 0 || N <= 0 || stride <= 0 || Tout <= 0 || !ty_conv_in1_supported(1, Cout, k)) {
+        set_error("ty_conv_in1_forward: bad argument (T=%d N=%d Cout=%d k=%d stride=%d)", T, N, Cout, k, stride);
+        return TY_EINVAL;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (k == 19)
+        conv_in1_fwd_kernel<19><<<in1_grid(Tout, N), 256, 0, s>>>(x, w, b, T, N, Cout, stride, pad_left, Tout, z);
+    else
+        conv_in1_fwd_kernel<0><<<in1_grid(Tout, N), 256, 0, s>>>(x, w, b, T, N, Cout | (k << 16), stride, pad_left,
+                                                                Tout, z);
+    return check_launch("conv_in1_fwd_kernel");
+}
+
+extern "C" int ty_conv_in1_wgrad(const float *x, const float *dz, int T, int N, int Cout, int k, int stride,
+                                 int pad_left, int Tout, float *dw, float *db, void *stream) {
+    if (!x || !dz || !dw || T <= 0 || N <= 0 || stride <= 0 || Tout <= 0 || !ty_conv_in1_supported(1, Cout, k)) {
+        set_error("ty_conv_in1_wgrad: bad argument (T=%d N=%d Cout=%d k=%d stride=%d)", T, N, Cout, k, stride);
+        return TY_EINVAL;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (k == 19)
+        conv_in1_wgrad_kernel<19><<<in1_grid(Tout, N), 256, 0, s>>>(x, dz, T, N, Cout, stride, pad_left, Tout, dw, db);
+    else
+        conv_in1_wgrad_kernel<0><<<in1_grid(Tout, N), 256, 0, s>>>(x, dz, T, N, Cout | (k << 16), stride, pad_left,
+                                                                  Tout, dw, db);
+    return check_launch("conv_in1_wgrad_kernel");
+}
+

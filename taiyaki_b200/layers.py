@@ -655,6 +655,44 @@ class _ConvSmall(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class _ConvIn1(torch.autograd.Function):
+    """Strided convolution of the single-channel signal (first layer of the mGru models,
+    Convolution(1, size, 19, stride=2)) as direct fp32 kernels (csrc/conv.cu: conv_in1_*): as a
+    GEMM it is too narrow for a tensor-core tile and bf16 would round the raw signal.  Returns the
+    pre-activation; the signal carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding):
+        T, N, _ = x.shape
+        Cout, _, k = weight.shape
+        Tout = (T + padding[0] + padding[1] - k) // stride + 1
+        xc = x.detach().contiguous().float()
+        wc = weight.detach().contiguous().float()
+        bc = bias.detach().contiguous().float() if bias is not None else None
+        z = torch.empty(Tout, N, Cout, dtype=torch.float32, device=x.device)
+        rc = _lib.lib().ty_conv_in1_forward(_lib.ptr(xc), _lib.ptr(wc), _lib.ptr(bc), T, N, Cout, k,
+                                            stride, padding[0], Tout, _lib.ptr(z),
+                                            _lib.stream_ptr(x.device))
+        _lib.check(rc, 'ty_conv_in1_forward')
+        _lib.count_launches(1)
+        ctx.save_for_backward(xc)
+        ctx.cfg = (T, N, Cout, k, stride, padding[0], Tout, bias is not None)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        xc, = ctx.saved_tensors
+        T, N, Cout, k, stride, pad_left, Tout, has_bias = ctx.cfg
+        dz = dz.contiguous().float()
+        dw = torch.zeros(Cout, 1, k, dtype=torch.float32, device=dz.device)
+        db = torch.zeros(Cout, dtype=torch.float32, device=dz.device) if has_bias else None
+        rc = _lib.lib().ty_conv_in1_wgrad(_lib.ptr(xc), _lib.ptr(dz), T, N, Cout, k, stride, pad_left,
+                                          Tout, _lib.ptr(dw), _lib.ptr(db), _lib.stream_ptr(dz.device))
+        _lib.check(rc, 'ty_conv_in1_wgrad')
+        _lib.count_launches(1)
+        return None, dw, db, None, None
+
+
 class Convolution(nn.Module):
     """1D convolution over time for [T, N, F] tensors (layers.py:744-850)."""
 
@@ -689,8 +727,12 @@ class Convolution(nn.Module):
                     self.padding[0] + self.padding[1] == self.winlen - 1 and
                     _lib.lib().ty_conv_small_supported(self.insize, self.size, self.winlen)):
                 return _ConvSmall.apply(x, self.conv.weight, self.conv.bias, self.padding[0], act)
-            out = _ConvTimeMajor.apply(x, self.conv.weight, self.conv.bias, self.stride,
-                                       self.padding)
+            if (self.insize == 1 and x.dim() == 3 and not x.requires_grad and
+                    _lib.lib().ty_conv_in1_supported(1, self.size, self.winlen)):
+                out = _ConvIn1.apply(x, self.conv.weight, self.conv.bias, self.stride, self.padding)
+            else:
+                out = _ConvTimeMajor.apply(x, self.conv.weight, self.conv.bias, self.stride,
+                                           self.padding)
             return self.activation(out)
         x = x.permute(1, 2, 0)
         out = self.activation(self.conv(self.pad(x)))

@@ -251,6 +251,30 @@ def test_convolution_matches_conv1d(dev, C, Cout, k, stride, fun):
     assert ((gb1 - conv.conv.bias.grad).norm() / conv.conv.bias.grad.norm()).item() < tol
 
 
+@pytest.mark.parametrize('Cout,k,stride,T,N', [(256, 19, 2, 403, 5), (256, 19, 5, 1000, 64), (96, 19, 2, 77, 33),
+                                               (64, 11, 3, 50, 1), (300, 32, 2, 64, 40), (8, 1, 1, 9, 2)])
+def test_single_channel_strided_convolution_matches_conv1d(dev, Cout, k, stride, T, N):
+    """The mGru models' first layer (Convolution(1, size, 19, stride=2)) through the direct fp32
+    kernels (conv_in1_*) against nn.Conv1d in fp32: outputs, weight and bias gradients."""
+    from taiyaki_b200 import activation, layers
+    torch.manual_seed(Cout + k)
+    np.random.seed(Cout + k)
+    torch.backends.cudnn.allow_tf32 = False
+    conv = layers.Convolution(1, Cout, k, stride=stride, fun=activation.swish).to(dev)
+    x = torch.randn(T, N, 1, device=dev)
+    y1 = conv(x)
+    y2 = activation.swish(conv.conv(conv.pad(x.permute(1, 2, 0))).permute(2, 0, 1))
+    assert y1.shape == y2.shape
+    g = torch.randn_like(y2)
+    y1.backward(g)
+    gw1, gb1 = conv.conv.weight.grad.clone(), conv.conv.bias.grad.clone()
+    conv.zero_grad()
+    y2.backward(g)
+    assert (y1 - y2).abs().max().item() < 1e-5 * max(1.0, y2.abs().max().item())
+    assert ((gw1 - conv.conv.weight.grad).norm() / conv.conv.weight.grad.norm()).item() < 1e-5
+    assert ((gb1 - conv.conv.bias.grad).norm() / conv.conv.bias.grad.norm()).item() < 1e-5
+
+
 def test_deferred_weight_grads_match(dev):
     """layers.DEFER_WEIGHT_GRADS (weight-gradient GEMMs on a side stream, added into
     .grad there) gives the gradients plain autograd gives."""
