@@ -70,6 +70,8 @@ def parse():
                              'mLstm_cat_mod_flipflop'],
                     help='model definition under models/ (default: the contract workload)')
     ap.add_argument('--tsig', type=int, default=T_SIG, help='chunk length in samples (sweep E)')
+    ap.add_argument('--chunks', type=int, default=NCHUNK,
+                    help='chunks per GPU and step (BASELINE configs[0]: --model mGru_flipflop --tsig 2000 --chunks 8)')
     return ap.parse_args()
 
 
@@ -139,17 +141,24 @@ def reference_arm(args, rank, world):
     from oracle import oracle, ref_train_step
     oracle.build()
     steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
-    r = ref_train_step.time_reference('lstm', T_SIG, args.ref_chunks, steps, warmup, STRIDE,
-                                      threads=cores)
-    sample = ('%d chunks x T_sig=%d per step, %d timed steps, torch CPU nn.LSTM + reference C '
-              'loss (%s)' % (args.ref_chunks, T_SIG, steps,
+    # the contract workload by default; --model / --tsig / --chunks select another BASELINE configuration
+    # (configs[0] as written: --model mGru_flipflop --tsig 2000 --chunks 8 --steps 10)
+    cell = 'gru' if 'Gru' in args.model else 'lstm'
+    stride = 2 if cell == 'gru' else STRIDE
+    custom = args.model != 'mLstm_flipflop' or args.tsig != T_SIG or args.chunks != NCHUNK
+    ref_chunks = args.chunks if custom else args.ref_chunks
+    workload = WORKLOAD if not custom else '%s size%d stride%d, T_sig=%d (nblk=%d), %d chunks, S=40' % (
+        args.model.replace('_cat_mod', ''), SIZE, stride, args.tsig, -(-args.tsig // stride), ref_chunks)
+    r = ref_train_step.time_reference(cell, args.tsig, ref_chunks, steps, warmup, stride, threads=cores)
+    sample = ('%d chunks x T_sig=%d per step, %d timed steps, torch CPU nn.%s + reference C '
+              'loss (%s)' % (ref_chunks, args.tsig, steps, 'GRU' if cell == 'gru' else 'LSTM',
                              'oracle/_ref' if r['reference_c'] else 'oracle port'))
     line = {
         'metric': METRIC, 'value': r['samples_per_s'], 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'impl': 'reference',
-        'config': {'workload': WORKLOAD, 'sample': sample},
+        'config': {'workload': workload, 'sample': sample},
         'cpu_baseline': {'value': r['samples_per_s'], 'unit': 'samples/s', 'cores': r['threads'],
                          'kind': 'reference' if r['reference_c'] else 'port', 'sample': sample},
         'e2e': {'value': r['samples_per_s'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
@@ -213,9 +222,10 @@ def run_arm():
     torch.manual_seed(seed)
 
     # ---- model, optimiser (train_flipflop.py:332-429) ----
-    global T_SIG, STRIDE, NTRANS, WORKLOAD
+    global T_SIG, STRIDE, NTRANS, WORKLOAD, NCHUNK
     cat_mod = 'cat_mod' in args.model
-    if args.model != 'mLstm_flipflop' or args.tsig != T_SIG:
+    if args.model != 'mLstm_flipflop' or args.tsig != T_SIG or args.chunks != NCHUNK:
+        NCHUNK = args.chunks
         args.no_cpu_baseline = True          # the CPU arm times the contract workload only
         T_SIG = args.tsig
         STRIDE = 5 if 'Lstm' in args.model else 2
