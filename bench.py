@@ -70,6 +70,9 @@ def parse():
                              'mLstm_cat_mod_flipflop'],
                     help='model definition under models/ (default: the contract workload)')
     ap.add_argument('--tsig', type=int, default=T_SIG, help='chunk length in samples (sweep E)')
+    ap.add_argument('--graphs', action='store_true',
+                    help='replay forward + loss + backward as a CUDA graph (training.GraphedBody): for the '
+                         'launch-bound short-chunk configurations; the chunk length of a bench run is fixed')
     ap.add_argument('--chunks', type=int, default=NCHUNK,
                     help='chunks per GPU and step (BASELINE configs[0]: --model mGru_flipflop --tsig 2000 --chunks 8)')
     return ap.parse_args()
@@ -249,6 +252,8 @@ def run_arm():
     mod_info = training.MOD_INFO(np.ones(alphabet_info.nbase, dtype=np.float32), None) \
         if cat_mod else None
     step_fn = training.TrainStep(net_info, optimiser, mod_info=mod_info)
+    if args.graphs:
+        step_fn.use_graphs(True, min_repeats=1)
     nparam = sum(p.numel() for p in net.parameters() if p.requires_grad)
 
     # ---- synthetic batches through the reference's batching surface ----
@@ -335,6 +340,8 @@ def run_arm():
         tf.RESOURCE_INFO(world > 1, rank == 0, device), reads, alphabet_info, fp,
         training.MOD_INFO(np.ones(alphabet_info.nbase, dtype=np.float32), tf.MOD_FACTOR(1.0, 1.0, 1)),
         [], tf.LOGS(main=NullLog()))
+    if args.graphs:
+        loop.step.use_graphs(True, min_repeats=1)
     loop.run(W)
     if world > 1:
         dist.barrier()
@@ -486,7 +493,7 @@ def run_arm():
         'vs_baseline': None, 'dtype': 'bf16 tensor-core products (fp32 accumulate) / f32 state, gates and loss',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'chunks_per_gpu': NCHUNK, 'global_chunks': NCHUNK * world,
-                   'parallelism': 'dp%d' % world,
+                   'parallelism': 'dp%d' % world, 'cuda_graphs': bool(args.graphs),
                    'l2': 'per-step working set (activations + reserve, >2 GB) exceeds the 126 MB L2'},
         'e2e': {'value': e2e, 'unit': 'samples/s',
                 'path': "bin/train_flipflop.py TrainLoop.run (what the entry point executes): host "

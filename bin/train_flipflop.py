@@ -112,6 +112,10 @@ def get_train_flipflop_parser():
     g.add_argument('--overwrite', default=False, action='store_true')
     g.add_argument('--quiet', default=False, action='store_true')
     g.add_argument('--save_every', type=int, default=2500)
+    g.add_argument('--cuda_graphs', default=False, action='store_true',
+                   help='Replay forward + loss + backward as a CUDA graph once a batch shape has been '
+                        'seen three times (useful with --chunk_len_min == --chunk_len_max and short '
+                        'chunks, where the step is bound by kernel launches; same results)')
     g.add_argument('--host_batching', default=False, action='store_true',
                    help='Assemble training batches with the numpy path of the reference '
                         'instead of on the device (taiyaki_b200.device_batching)')
@@ -509,12 +513,16 @@ def train_model(train_params, net_info, optim_info, res_info, read_data, alphabe
                 filter_params, mod_info, reporting_batch_list, logs):
     loop = TrainLoop(train_params, net_info, optim_info, res_info, read_data, alphabet_info,
                      filter_params, mod_info, reporting_batch_list, logs)
+    if os.environ.get('TY_GRAPHS', '0') == '1' and train_params.sub_batches == 1:
+        loop.step.use_graphs(True)
     loop.run(train_params.niteration)
     if res_info.is_lead_process:
         helpers.save_model(net_info.net, train_params.outdir)
 
 
 def main(args):
+    if getattr(args, 'cuda_graphs', False):
+        os.environ['TY_GRAPHS'] = '1'
     res_info, logs = parse_init_args(args)
     read_data, alphabet_info, mod_info = load_data(args, logs.main, res_info)
     net_info, optim_info = load_network(args, alphabet_info, res_info, logs.main)

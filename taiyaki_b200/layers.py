@@ -938,9 +938,16 @@ class GlobalNormFlipFlopCatMod(nn.Module):
             init_(self.linear.bias, truncated_normal(list(self.linear.bias.shape), sd=0.5))
 
     def get_softmax_cat_mods(self, cat_mod_scores):
+        # index tensors live on the scores' device (indexing with the numpy arrays copies them to
+        # the device on every call, which a CUDA-graph capture does not even allow)
+        # (kept outside the module so that they are not pickled into checkpoints)
+        key = (tuple(tuple(int(i) for i in ix) for ix in self.can_indices), cat_mod_scores.device)
+        if key not in _CAN_INDEX_CACHE:
+            _CAN_INDEX_CACHE[key] = [torch.as_tensor(np.asarray(ix), dtype=torch.long, device=key[1])
+                                     for ix in self.can_indices]
         mod_layers = []
-        for lab_indices in self.can_indices:
-            mod_layers.append(self.lsm(cat_mod_scores[:, :, lab_indices]))
+        for lab_indices in _CAN_INDEX_CACHE[key]:
+            mod_layers.append(self.lsm(cat_mod_scores.index_select(2, lab_indices)))
         return torch.cat(mod_layers, dim=2)
 
     def forward(self, x):
@@ -955,6 +962,9 @@ class GlobalNormFlipFlopCatMod(nn.Module):
             'Invalid softmax categorical mod scores:  Expected: {}  got: {}'.format(
                 self.nmod_base + self.ncan_base, cat_mod_scores.shape[2]))
         return torch.cat((trans_scores, cat_mod_scores), dim=2)
+
+
+_CAN_INDEX_CACHE = {}
 
 
 def is_cat_mod_model(net):

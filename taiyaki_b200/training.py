@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import chunk_selection, ctc, flipflopfings, layers
+from . import _lib, chunk_selection, ctc, flipflopfings, layers
 
 NETWORK_METADATA = namedtuple('NETWORK_METADATA', (
     'reverse', 'standardize', 'is_cat_mod', 'can_mods_offsets', 'can_labels', 'mod_labels'))
@@ -256,6 +256,107 @@ def apply_clipping(net_info, grad_max_threshs, flat=None):
     return grad_maxs
 
 
+class GraphedBody:
+    """zero_grad -> forward -> loss -> backward of ONE sub-batch as a CUDA graph, replayed with the
+    batch copied into static buffers.  For launch-bound steps (short chunks: ~110 launches of a few
+    microseconds of work each, the host cannot keep ahead) when the chunk length is FIXED
+    (`--chunk_len_min == --chunk_len_max`; the default entry point draws a new length every iteration,
+    train_flipflop.py:554-562, and then every step has another shape -- `TrainStep` falls back to
+    eager launches for any shape it has not captured `min_repeats` times).
+
+    What makes the body capturable: everything in it is stream-ordered on the capturing stream (the
+    loss's and the weight-gradient GEMMs' side streams fork from and join it by events), gradients
+    accumulate into the static flat buffer, and the only data-dependent sizes -- the number of labels
+    and the longest chunk -- enter the kernels as CAPACITIES: label tensors are padded to N * Lcap
+    entries (valid labels, ignored beyond each chunk's length) and the loss kernels are launched for
+    Lcap = the longest chunk rounded up to 64 positions, one graph per (T, N, Lcap, sharpen, ...)."""
+
+    LCAP_STEP = 64
+
+    def __init__(self, net_info, flat, min_repeats=3):
+        self.net_info, self.flat, self.min_repeats = net_info, flat, min_repeats
+        self.entries, self.seen = {}, defaultdict(int)
+        self.replays = 0
+
+    def _key(self, batch, sharpen, mcw_scaled):
+        indata, seqs, seqlens, mod_cats = batch[:4]
+        max_len, total = ctc._max_len(seqlens)
+        lcap = -(-max(1, max_len) // self.LCAP_STEP) * self.LCAP_STEP
+        mk = None if mcw_scaled is None else tuple(np.asarray(mcw_scaled, dtype=np.float32).tolist())
+        return (tuple(indata.shape), lcap, float(sharpen), mk, mod_cats is not None), total
+
+    def _body(self, e, sharpen, mcw_scaled):
+        can_mods_offsets = self.net_info.metadata.can_mods_offsets
+        self.flat.zero()
+        outputs = self.net_info.net(e['indata'])
+        if self.net_info.metadata.is_cat_mod:
+            lossvector = flipflop_loss(outputs, e['seqs'], e['seqlens'], sharpen, e['mod_cats'],
+                                       can_mods_offsets, mcw_scaled)
+        else:
+            lossvector = flipflop_loss(outputs, e['seqs'], e['seqlens'], sharpen)
+        loss = lossvector.mean()
+        prev = layers.DEFER_WEIGHT_GRADS
+        layers.DEFER_WEIGHT_GRADS = DEFER_WEIGHT_GRADS
+        try:
+            loss.backward()
+        finally:
+            layers.DEFER_WEIGHT_GRADS = prev
+            layers.flush_weight_grads()
+        return loss.detach()
+
+    def _capture(self, key, batch, sharpen, mcw_scaled):
+        (shape, lcap, _, _, has_mod) = key
+        indata, seqs, seqlens, mod_cats = batch[:4]
+        dev = indata.device
+        N = shape[1]
+        e = {'indata': torch.empty(shape, dtype=torch.float32, device=dev),
+             'seqs': torch.zeros(N * lcap, dtype=torch.int64, device=dev),
+             'seqlens': torch.ones(N, dtype=torch.int64, device=dev),
+             'mod_cats': torch.zeros(N * lcap, dtype=torch.int64, device=dev) if has_mod else None}
+        ctc.hint_lengths(e['seqlens'], lcap, N * lcap)       # capacities, not this batch's values
+        self._load(e, batch)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                        # warm-up outside capture (allocator, lazy init)
+            self._body(e, sharpen, mcw_scaled)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        launches0 = _lib.LAUNCHES
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            e['loss'] = self._body(e, sharpen, mcw_scaled)
+        e['graph'], e['launches'] = graph, _lib.LAUNCHES - launches0
+        return e
+
+    @staticmethod
+    def _load(e, batch):
+        indata, seqs, seqlens, mod_cats = batch[:4]
+        e['indata'].copy_(indata, non_blocking=True)
+        n = seqs.numel()
+        e['seqs'][:n].copy_(seqs, non_blocking=True)
+        e['seqlens'].copy_(seqlens, non_blocking=True)
+        if e['mod_cats'] is not None:
+            e['mod_cats'][:n].copy_(mod_cats, non_blocking=True)
+
+    def run(self, batch, sharpen, mcw_scaled):
+        """Loss (device scalar) of the batch with its gradients in the flat buffer, or None when this
+        shape is still run eagerly."""
+        indata, seqs, seqlens = batch[:3]
+        if not (indata.is_cuda and seqs.is_cuda and seqlens.is_cuda):
+            return None
+        key, total = self._key(batch, sharpen, mcw_scaled)
+        e = self.entries.get(key)
+        if e is None:
+            self.seen[key] += 1
+            if self.seen[key] < self.min_repeats:
+                return None
+            e = self.entries[key] = self._capture(key, batch, sharpen, mcw_scaled)
+        self._load(e, batch)
+        e['graph'].replay()
+        _lib.count_launches(e['launches'])
+        self.replays += 1
+        return e['loss']
+
+
 class TrainStep:
     """zero_grad -> calculate_loss(calc_grads) -> all-reduce -> clipping ->
     AdamW step (train_flipflop.py:570-578) as one callable."""
@@ -273,6 +374,13 @@ class TrainStep:
         self._thr_dev = None                # device-resident thresholds of the next step's clipping
         self._host_bufs = [None, None]      # two steps can be in flight (see `pipelined`)
         self._nstep = 0
+        #: CUDA-graph replay of forward + loss + backward for repeated shapes (see GraphedBody);
+        #: off by default, `use_graphs()` / TY_GRAPHS=1 turn it on
+        self.graphed = GraphedBody(net_info, self.flat) if os.environ.get('TY_GRAPHS', '0') == '1' else None
+
+    def use_graphs(self, on=True, min_repeats=3):
+        self.graphed = GraphedBody(self.net_info, self.flat, min_repeats) if on else None
+        return self
 
     @property
     def pipelined(self):
@@ -284,16 +392,30 @@ class TrainStep:
         """Put one optimiser step on the stream without waiting for it; `finish` reads its
         results back.  Splitting the two lets the caller enqueue the next batch's assembly
         (and do its host bookkeeping) while the device is busy with this step."""
-        self.flat.zero()
         mcw = None if self.mod_info is None else self.mod_info.mod_cat_weights
-        if self.sub_batches == 1 and DEFER_WEIGHT_GRADS:
-            self.flat.begin_overlap()
-        try:
-            res = calculate_loss(self.net_info, batch_gen, sharpen, mcw, mod_factor,
-                                 calc_grads=True)
-        finally:
-            if layers.GRADS_FINAL_ABOVE_HOOK is not None and self.flat.world <= 1:
-                layers.GRADS_FINAL_ABOVE_HOOK = None
+        res = None
+        if self.graphed is not None and self.sub_batches == 1:
+            batches = list(batch_gen)
+            if len(batches) == 1:
+                b = batches[0]
+                scaled = mcw * mod_factor if (mcw is not None and self.net_info.metadata.is_cat_mod) else None
+                loss = self.graphed.run(b, sharpen, scaled)
+                if loss is not None:       # gradients are in the flat buffer (zeroed inside the graph)
+                    rej = defaultdict(int)
+                    for k, v in b[5].items():
+                        rej[k] += v
+                    res = (b[4], loss, int(b[0].nelement()), ctc._max_len(b[2])[1], rej)
+            batch_gen = iter(batches)
+        if res is None:
+            self.flat.zero()
+            if self.sub_batches == 1 and DEFER_WEIGHT_GRADS:
+                self.flat.begin_overlap()
+            try:
+                res = calculate_loss(self.net_info, batch_gen, sharpen, mcw, mod_factor,
+                                     calc_grads=True)
+            finally:
+                if layers.GRADS_FINAL_ABOVE_HOOK is not None and self.flat.world <= 1:
+                    layers.GRADS_FINAL_ABOVE_HOOK = None
         self.flat.all_reduce()
         device_thr = self.rolling_mads is not None and getattr(self.rolling_mads, 'device', None) is not None
         grad_maxs = apply_clipping(self.net_info, self._thr_dev if device_thr else self.grad_max_threshs,

@@ -157,6 +157,23 @@ def test_entry_point_with_clipping_is_pipelined(dev, tmp_path):
     assert (out / 'model_final.checkpoint').exists()
 
 
+def test_entry_point_with_cuda_graphs(dev, tmp_path):
+    """--cuda_graphs with a fixed chunk length: shapes repeat, the body is captured and replayed;
+    the run trains and logs as usual."""
+    out = tmp_path / 'training'
+    cmd = [sys.executable, os.path.join(ROOT, 'bin', 'train_flipflop.py'), '--size', '64',
+           '--niteration', '60', '--warmup_batches', '10', '--chunk_len_min', '600',
+           '--chunk_len_max', '600', '--min_sub_batch_size', '16', '--cuda_graphs', '--seed', '2',
+           '--quiet', '--overwrite', '--outdir', str(out),
+           os.path.join(ROOT, 'models', 'mLstm_flipflop.py'), 'synthetic:12']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    batch = (out / 'batch.log').read_text().strip().splitlines()
+    assert len(batch) == 61
+    first, last = float(batch[1].split('\t')[1]), float(batch[-1].split('\t')[1])
+    assert np.isfinite(last) and last < first
+
+
 def test_train_flipflop_entry_point_all_default_flags(dev, tmp_path):
     """Every flag at its default (size 384, bin/_bin_argparse.py:16; chunk lengths 3000-8000 in
     sub-batches of 128): the round-1 library refused size 384.  Only the number of iterations is
@@ -273,6 +290,43 @@ def test_single_channel_strided_convolution_matches_conv1d(dev, Cout, k, stride,
     assert (y1 - y2).abs().max().item() < 1e-5 * max(1.0, y2.abs().max().item())
     assert ((gw1 - conv.conv.weight.grad).norm() / conv.conv.weight.grad.norm()).item() < 1e-5
     assert ((gb1 - conv.conv.bias.grad).norm() / conv.conv.bias.grad.norm()).item() < 1e-5
+
+
+@pytest.mark.parametrize('model,alpha', [('mLstm_flipflop.py', 'ACGT'), ('mGru_cat_mod_flipflop.py', 'ACGTZ')])
+def test_cuda_graph_replay_matches_eager_steps(dev, model, alpha):
+    """training.GraphedBody: forward + loss + backward captured once per (shape, label capacity) and
+    replayed with the batch copied into static buffers -- same losses and the same weights after 15
+    optimiser steps as eager launches, on batches whose label counts differ from step to step."""
+    from taiyaki_b200 import chunk_selection, ctc, signal_mapping, training
+    from taiyaki_b200.alphabet import AlphabetInfo
+    ai = AlphabetInfo('ACGTZ', 'ACGTC', ['5mC']) if alpha == 'ACGTZ' else AlphabetInfo('ACGT', 'ACGT')
+    reads = signal_mapping.synthetic_reads(10, seed=3, mod_fraction=0.5 if alpha == 'ACGTZ' else 0.0)
+    results = {}
+    for mode in ('eager', 'graph'):
+        np.random.seed(5)
+        torch.manual_seed(5)
+        net_info = build(dev, model, 64, ai)
+        fp = chunk_selection.sample_filter_parameters(reads, 50, 600, 10.0, 10.0, 0.1, net_info.stride, 1.1)
+        opt = torch.optim.AdamW(net_info.net.parameters(), lr=2e-3, eps=1e-6)
+        step = training.TrainStep(net_info, opt, mod_info=training.MOD_INFO(np.ones(ai.nbase, dtype=np.float32), None))
+        if mode == 'graph':
+            step.use_graphs(True, min_repeats=2)
+        batches = []
+        for b in training.prepare_random_batches(reads, 600, 10, 5, ai, fp, net_info, None):
+            sl = b[2].to(dev)
+            ctc.hint_lengths(sl, int(b[2].max()), int(b[2].sum()))
+            batches.append((b[0].to(dev), b[1].to(dev), sl, None if b[3] is None else b[3].to(dev), b[4], b[5]))
+        assert len({int(b[1].numel()) for b in batches}) > 1          # label counts differ
+        losses = []
+        for it in range(15):
+            _, loss, gmax = step(iter([batches[it % 5]]), sharpen=1.0, mod_factor=1.0)
+            losses.append(loss)
+        if mode == 'graph':
+            assert step.graphed.replays >= 10 and len(step.graphed.entries) >= 1
+        results[mode] = (np.array(losses), [p.detach().clone() for p in net_info.net.parameters()])
+    np.testing.assert_allclose(results['graph'][0], results['eager'][0], rtol=2e-4)
+    for a, b in zip(results['graph'][1], results['eager'][1]):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-4)
 
 
 def test_deferred_weight_grads_match(dev):
