@@ -101,6 +101,23 @@ def _max_len(seqlen):
     return int(seqlen.max()) if seqlen.numel() else 0, int(seqlen.sum())
 
 
+_SMALL_ARRAYS = {}
+
+
+def _small_device_array(values, dtype, device):
+    """Device copy of a small host array (mod offsets / weights), cached by value: the same few
+    arrays come back every step, and a host -> device copy per call is neither free nor allowed
+    while a CUDA graph is being captured."""
+    arr = np.ascontiguousarray(np.asarray(values, dtype=dtype))
+    key = (arr.tobytes(), arr.dtype.str, str(device))
+    t = _SMALL_ARRAYS.get(key)
+    if t is None:
+        if len(_SMALL_ARRAYS) > 256:        # mod factors ramp during training: bounded cache
+            _SMALL_ARRAYS.clear()
+        t = _SMALL_ARRAYS[key] = torch.from_numpy(arr.copy()).to(device)
+    return t
+
+
 def build_indices(seqs, seqlen, nbase, device, mod_cats=None, can_mods_offsets=None,
                   mod_cat_weights=None):
     """Device-side move/stay (and mod) transition indices in the reference packing."""
@@ -117,10 +134,8 @@ def build_indices(seqs, seqlen, nbase, device, mod_cats=None, can_mods_offsets=N
     modmove = modfact = mod_d = off_d = w_d = None
     if mod_cats is not None:
         mod_d = _as_device_i64(mod_cats, device)
-        off_d = torch.as_tensor(np.asarray(can_mods_offsets)).to(
-            device=device, dtype=torch.int32).contiguous()
-        w_d = torch.as_tensor(np.asarray(mod_cat_weights, dtype=np.float32)).to(
-            device=device, dtype=torch.float32).contiguous()
+        off_d = _small_device_array(can_mods_offsets, np.int32, device)
+        w_d = _small_device_array(mod_cat_weights, np.float32, device)
         modmove = torch.zeros(n, dtype=torch.int32, device=device)
         modfact = torch.zeros(n, dtype=torch.float32, device=device)
     rc = lib.ty_flipflop_indices_checked(
