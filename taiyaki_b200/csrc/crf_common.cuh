@@ -37,7 +37,6 @@ struct CrfArgs {
     int Ls;
     int want_grad;
     int nchain;        // CTAs that run chains; the rest sort
-    int ring;          // fused kernel: slots of the posterior ring
 };
 
 constexpr int kRing = 8;      // cp.async ring slots for raw score rows

@@ -604,7 +604,6 @@ static int launch_fused(const CrfArgs &a, int max_seqlen, cudaStream_t s) {
 
 int launch_crf_fused(CrfArgs a, int P, bool mod, int max_seqlen, cudaStream_t s) {
     const int pw = fused_pick_pw(P, a.Ls, max_seqlen);
-    a.ring = kFRing;
 #define TY_FUSED(PP, MM, WW) \
     if (P == PP && mod == MM && pw == WW) return launch_fused<PP, MM, WW>(a, max_seqlen, s);
     TY_FUSED(4, false, 8) TY_FUSED(4, false, 4) TY_FUSED(4, true, 8) TY_FUSED(4, true, 4)

@@ -272,6 +272,9 @@ class GraphedBody:
     Lcap = the longest chunk rounded up to 64 positions, one graph per (T, N, Lcap, sharpen, ...)."""
 
     LCAP_STEP = 64
+    #: a captured graph owns the activations of a whole step (gigabytes at training sizes): shapes
+    #: beyond this many stay eager, so a run with randomly drawn chunk lengths cannot exhaust memory
+    MAX_GRAPHS = 8
 
     def __init__(self, net_info, flat, min_repeats=3):
         self.net_info, self.flat, self.min_repeats = net_info, flat, min_repeats
@@ -346,6 +349,10 @@ class GraphedBody:
         key, total = self._key(batch, sharpen, mcw_scaled)
         e = self.entries.get(key)
         if e is None:
+            if len(self.entries) >= self.MAX_GRAPHS:
+                return None
+            if len(self.seen) > 4096:      # (sharpening / mod-factor ramps give every step a new key)
+                self.seen.clear()
             self.seen[key] += 1
             if self.seen[key] < self.min_repeats:
                 return None
