@@ -356,7 +356,15 @@ class GraphedBody:
             self.seen[key] += 1
             if self.seen[key] < self.min_repeats:
                 return None
-            e = self.entries[key] = self._capture(key, batch, sharpen, mcw_scaled)
+            try:
+                e = self.entries[key] = self._capture(key, batch, sharpen, mcw_scaled)
+            except Exception as err:      # a step that cannot be captured stays eager, for good
+                import warnings
+                warnings.warn('taiyaki_b200: CUDA-graph capture of the train step failed (%s); '
+                              'continuing with eager launches' % str(err).splitlines()[0][:200])
+                self.MAX_GRAPHS = 0
+                torch.cuda.synchronize()
+                return None
         self._load(e, batch)
         e['graph'].replay()
         _lib.count_launches(e['launches'])
