@@ -28,15 +28,9 @@ struct CrfArgs {
     float *coff;       // [2][nbatch][nblk] accumulated log2 offsets of the stored rows
     float *fwd_ws;     // [nbatch][nblk][Ls] alpha_t         (log2 domain, normalised)
     float *bwd_ws;     // [nbatch][nblk][Ls] beta_{t+1}
-    // entries sorted by transition bin, per chunk; word = pos | move << 13 | bin << 14 | mm << 20
-    int *ent_n;        // [nbatch][2] entries in each list
-    uint32_t *ent_w;   // [nbatch][2 * Ls]  stays + moves, keyed by their own transition
-    float *ent_mf;     // [nbatch][2 * Ls]  MOD: factor of a move entry (0 for stays)
-    uint32_t *ent2_w;  // [nbatch][Ls]      MOD: moves keyed by their mod transition (bin = mod, mm = move)
-    float *ent2_mf;    // [nbatch][Ls]
     int Ls;
     int want_grad;
-    int nchain;        // CTAs that run chains; the rest sort
+    int nchain;        // CTAs of the chain kernel
 };
 
 constexpr int kRing = 8;      // cp.async ring slots for raw score rows

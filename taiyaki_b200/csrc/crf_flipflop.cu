@@ -4,32 +4,23 @@
 // modified-base term).
 //
 // Structure (DESIGN.md "CRF kernels"):
-//   crf_chain_kernel   one CTA per (chunk, direction) + one "binning" CTA per
-//                      chunk in the same launch.
-//       chains: the sequence positions of the chunk are striped over the
-//         threads, P consecutive positions per thread in registers; time is the
-//         only sequential dimension and the kernel is bound by the per-step
-//         dependency latency, so the step is written for minimum instruction
-//         count: the DP runs in the log2 domain (bare ex2/lg2 SFU ops); a few
-//         "transformer" threads turn the raw score row (cp.async ring) into
-//         w*sharp*log2(e) - c one step ahead, so a position costs 2 LDS gathers
-//         and 8 arithmetic instructions; masked positions point at a -1e30 pad
-//         slot instead of being selected away; the normaliser c is the block
-//         max of the vector two steps earlier (any finite per-(t,chunk) scalar
-//         is valid: the shifts are summed into the score, c_crf_flipflop.c:73-77,
-//         :124) so no reduction sits on the dependency chain.  alpha_t /
-//         beta_{t+1} rows and their accumulated offsets go to the HBM workspace.
-//       binning: a counting sort of the chunk's stay / move entries by
-//         transition index (CSR), once per call, so the posterior kernel needs
-//         no atomics.
-//   crf_post_kernel    posterior of c_crf_flipflop.c:372-413 /
-//                      c_cat_mod_flipflop.c:419-468.  One thread per (block,
-//                      transition bin): it sums 2^(alpha+beta+w - Z_t) over the
-//                      bin's entries from shared-memory copies of the alpha /
-//                      beta rows, where Z_t is the analytic normaliser (total
-//                      score minus the accumulated offsets); the 40 canonical
-//                      bins are then renormalised to sum to one exactly like
-//                      the reference's softmax, so Z_t only has to be close.
+//   crf_chain_kernel   one CTA per (chunk, direction).  The sequence positions of the chunk are
+//                      striped over the threads, P consecutive positions per thread in
+//                      registers; time is the only sequential dimension and the kernel is bound
+//                      by the per-step dependency latency, so the step is written for minimum
+//                      instruction count: the DP runs in the log2 domain (bare ex2/lg2 SFU ops);
+//                      a "transformer" warp turns the raw score row (cp.async ring) into
+//                      w*sharp*log2(e) - c one step ahead, so a position costs 2 LDS gathers and
+//                      8 arithmetic instructions; masked positions point at a -1e30 pad slot
+//                      instead of being selected away; the normaliser c is the block max of the
+//                      vector two steps earlier (any finite per-(t,chunk) scalar is valid: the
+//                      shifts are summed into the score, c_crf_flipflop.c:73-77, :124) so no
+//                      reduction sits on the dependency chain.  alpha_t / beta_{t+1} rows and
+//                      their accumulated offsets go to the HBM workspace.
+//   crf_post_kernel    posterior of c_crf_flipflop.c:372-413 / c_cat_mod_flipflop.c:419-468 from
+//                      the spilled rows, one warp per (block, chunk) row, position-major.
+// Since round 2 this pair serves cost-only calls and chunks beyond the range of the fused
+// kernel (crf_fused.cu), which runs the same DP step and the same posterior scatter in one launch.
 #include "crf_common.cuh"
 
 namespace ty {
@@ -255,116 +246,8 @@ __device__ __forceinline__ void crf_chain_body(const CrfArgs &a, const int b, co
     }
 }
 
-// ---------------------------------------------------------------------------
-// Counting sort of one chunk's entries by transition index, once per call, so
-// the posterior kernel can sum bins without atomics on every entry.  List 1:
-// stays (position p, key stay[p]) and moves (position p, key move[p], p < L-1).
-// Cat-mod list 2: the moves again, keyed by their mod transition.  Order inside
-// a bin is by position, so the sums are deterministic.
-// Entry word: pos | is_move << 13 | key << 14 | other << 20   (pos < 8192)
-template <bool MOD>
-__device__ void crf_sort_chunk(const CrfArgs &a, const int b) {
-    __shared__ int cnt[4][kRowPad];
-    __shared__ int cnt2[4][kRowPad];
-    __shared__ int s_off;
-    const int tid = threadIdx.x;
-    if (tid < 32) {
-        int s = 0;
-        for (int i = tid; i < b; i += 32) s += a.seqlen[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
-        if (tid == 0) s_off = s;
-    }
-    __syncthreads();
-    const int off = s_off;
-    const int L = a.seqlen[b];
-    const int nthr = blockDim.x;
-    if (L <= 0) {
-        if (tid == 0) { a.ent_n[2 * b] = 0; a.ent_n[2 * b + 1] = 0; }
-        return;
-    }
-    const int32_t *st = a.stayidx + off;
-    const int32_t *mv = a.moveidx + (off - b);
-    const int32_t *mm = MOD ? a.modmoveidx + (off - b) : nullptr;
-    const float *mf = MOD ? a.modmovefact + (off - b) : nullptr;
-    const int chunk = (L + 3) / 4;
-    // work item = (bin, quarter of the positions); any block size
-    for (int item = tid; item < 4 * kRowPad; item += nthr) {
-        const int bin = item & 63, part = item >> 6;
-        const int lo = part * chunk, hi = min(L, lo + chunk);
-        int c = 0, c2 = 0;
-        for (int p = lo; p < hi; p++) {
-            c += st[p] == bin;
-            if (p < L - 1) {
-                c += mv[p] == bin;
-                if (MOD) c2 += mm[p] == bin;
-            }
-        }
-        cnt[part][bin] = c;
-        if (MOD) cnt2[part][bin] = c2;
-    }
-    __syncthreads();
-    // exclusive scan over (bin, part) in bin-major order by warp 0
-    if (tid < 32) {
-        for (int list = 0; list < (MOD ? 2 : 1); list++) {
-            int (*cn)[kRowPad] = list == 0 ? cnt : cnt2;
-            int run = 0;
-            for (int base = 0; base < kRowPad; base += 32) {
-                const int bb = base + tid;
-                const int n0 = cn[0][bb], n1 = cn[1][bb], n2 = cn[2][bb], n3 = cn[3][bb];
-                const int tot = n0 + n1 + n2 + n3;
-                int inc = tot;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(kFullMask, inc, o);
-                    if (tid >= o) inc += v;
-                }
-                const int excl = run + inc - tot;
-                cn[0][bb] = excl; cn[1][bb] = excl + n0; cn[2][bb] = excl + n0 + n1;
-                cn[3][bb] = excl + n0 + n1 + n2;
-                run += __shfl_sync(kFullMask, inc, 31);
-            }
-            if (tid == 0) a.ent_n[2 * b + list] = run;
-        }
-        if (!MOD && tid == 0) a.ent_n[2 * b + 1] = 0;
-    }
-    __syncthreads();
-    const size_t eb = (size_t)b * 2 * a.Ls;
-    const size_t eb2 = (size_t)b * a.Ls;
-    for (int item = tid; item < 4 * kRowPad; item += nthr) {
-        const int bin = item & 63, part = item >> 6;
-        const int lo = part * chunk, hi = min(L, lo + chunk);
-        int w = cnt[part][bin], w2 = MOD ? cnt2[part][bin] : 0;
-        for (int p = lo; p < hi; p++) {
-            if (st[p] == bin) {
-                a.ent_w[eb + w] = (uint32_t)p | ((uint32_t)bin << 14);
-                if (MOD) a.ent_mf[eb + w] = 0.f;
-                w++;
-            }
-            if (p < L - 1) {
-                if (mv[p] == bin) {
-                    a.ent_w[eb + w] = (uint32_t)p | (1u << 13) | ((uint32_t)bin << 14) |
-                                      (MOD ? (uint32_t)mm[p] << 20 : 0u);
-                    if (MOD) a.ent_mf[eb + w] = mf[p];
-                    w++;
-                }
-                if (MOD && mm[p] == bin) {
-                    a.ent2_w[eb2 + w2] = (uint32_t)p | (1u << 13) | ((uint32_t)bin << 14) |
-                                         ((uint32_t)mv[p] << 20);
-                    a.ent2_mf[eb2 + w2] = mf[p];
-                    w2++;
-                }
-            }
-        }
-    }
-}
-
 template <int P, bool MOD>
 __global__ void __launch_bounds__(P <= 4 ? 1024 : 544) crf_chain_kernel(const CrfArgs a) {
-    if ((int)blockIdx.x >= a.nchain) {        // sorting CTAs (want_grad only)
-        crf_sort_chunk<MOD>(a, blockIdx.x - a.nchain);
-        return;
-    }
     __shared__ int s_off;
     const int b = a.want_grad ? (blockIdx.x >> 1) : blockIdx.x;
     const int dir = a.want_grad ? (blockIdx.x & 1) : 0;
@@ -393,36 +276,35 @@ __global__ void __launch_bounds__(P <= 4 ? 1024 : 544) crf_chain_kernel(const Cr
 }
 
 // ---------------------------------------------------------------------------
-// Posterior.  grid = (row tiles, chunks); one WARP per row (block, chunk).
-// The row's alpha_t / beta_{t+1} vectors and the chunk's sorted entry words are
-// staged in shared memory; each lane walks a contiguous slice of the sorted
-// entries, accumulating 2^(alpha + beta + w - Z_t) per run of equal bin and
-// flushing a run with one shared-memory add, so adds are rare and collide only
-// at slice boundaries.  Z_t is the analytic normaliser (total score minus the
-// accumulated offsets of the two rows); the canonical bins are then
-// renormalised to sum to one exactly like the reference's softmax
+// Posterior of the chain kernel's spill (c_crf_flipflop.c:372-413 / c_cat_mod_flipflop.c:419-468).
+// grid = (row tiles, chunks); one WARP per row (block, chunk), position-major: lane l takes
+// positions l, l + 32, ... -- alpha_t, beta_{t+1} and the transition indices are read where they
+// lie, coalesced, with no staging and therefore no limit on the chunk length -- and adds
+// 2^(alpha + beta + w - Z_t) of the position's stay and move edges into ITS OWN column of a
+// [transition][lane] table in shared memory (plain read-modify-writes, no atomics, a fixed order);
+// the 32 columns of a transition are then summed with a rotated start.  Z_t is the analytic
+// normaliser (total score minus the accumulated offsets of the two rows); the canonical
+// transitions are renormalised to sum to one exactly like the reference's softmax
 // (c_crf_flipflop.c:401), so Z_t only has to be close.
+// (Round 1 walked transition-sorted entry lists from shared-memory copies of the rows; beyond the
+// rows that fit it gathered them from global memory, 4 bytes per 32-byte sector: 170 ms at
+// nblk 8000 x 4400 positions, 0.9 GB/s.  The same scatter runs inside crf_fused.cu.)
 constexpr int kPostWarps = 8;
 
-// STAGED = false (chunks too long for the rows to fit in shared memory): the alpha /
-// beta rows are read where the chain kernel left them (L2 / HBM), only the entry lists
-// are staged -- slower per row, but no limit on the chunk length below the chain's own.
-template <bool MOD, bool STAGED>
+template <bool MOD>
 __global__ void __launch_bounds__(kPostWarps * 32) crf_post_kernel(const CrfArgs a) {
-    extern __shared__ __align__(16) float dyn[];   // al[R][Ls], be[R][Ls+4], words[2Ls] (+ MOD extras)
-    __shared__ float q[kPostWarps][kRowPad];       // w2 - Z_t (canonical), w2 (mod)
-    __shared__ float bins[kPostWarps][kRowPad];
+    extern __shared__ __align__(16) float cols_all[];      // [kPostWarps][S][32]
+    __shared__ float q[kPostWarps][kRowPad];                // w2 - Z_t (canonical), w2 (mod)
 
     const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kPostWarps;
     const int S = a.ntrans, Ls = a.Ls;
     const int L = a.seqlen[b];
-    const int nrow = min(kPostWarps, a.nblk - t0);
     const int t = t0 + r;
 
     if (L <= 0) {
-        if (r < nrow)
+        if (t < a.nblk)
             for (int s = lane; s < S; s += 32)
                 a.grad_out[((size_t)t * a.nbatch + b) * S + s] = 0.f;
         if (t0 == 0 && tid == 0) a.score_out[b] = 0.f;
@@ -431,105 +313,83 @@ __global__ void __launch_bounds__(kPostWarps * 32) crf_post_kernel(const CrfArgs
     // total log2 score = mean of forward and backward (c_crf_flipflop.c:482-491)
     const float score2 = 0.5f * (a.fb[2 * b] + a.fb[2 * b + 1]);
     if (t0 == 0 && tid == 0) a.score_out[b] = a.score_scale * kLn2 * score2;
+    if (t >= a.nblk) return;                                 // (no block-wide barrier below)
 
-    const int bes = Ls + 4;
-    float *al = dyn;
-    float *be = al + (STAGED ? (size_t)kPostWarps * Ls : 0);
-    uint32_t *words = reinterpret_cast<uint32_t *>(be + (STAGED ? (size_t)kPostWarps * bes : 0));
-    float *wmf = reinterpret_cast<float *>(words + 2 * Ls);        // MOD only
-    uint32_t *words2 = reinterpret_cast<uint32_t *>(wmf + 2 * Ls); // MOD only
-    float *wmf2 = reinterpret_cast<float *>(words2 + Ls);          // MOD only
-    const int n1 = a.ent_n[2 * b], n2 = MOD ? a.ent_n[2 * b + 1] : 0;
-
-    // ---- stage: each warp its own row (float4, coalesced), all warps the entry lists ----
-    if (r < nrow) {
-        if (STAGED) {
-            const size_t g = ((size_t)b * a.nblk + t) * Ls;
-            const float4 *fa = reinterpret_cast<const float4 *>(a.fwd_ws + g);
-            const float4 *fbp = reinterpret_cast<const float4 *>(a.bwd_ws + g);
-            float4 *sa = reinterpret_cast<float4 *>(al + (size_t)r * Ls);
-            float4 *sb = reinterpret_cast<float4 *>(be + (size_t)r * bes);
-            for (int i = lane; i < (L + 3) / 4; i += 32) {
-                sa[i] = __ldcs(fa + i);
-                sb[i] = __ldcs(fbp + i);
-            }
+    float *cols = cols_all + (size_t)r * S * 32;
+    float *mycol = cols + lane;
+    for (int s = 0; s < S; s++) mycol[s * 32] = 0.f;
+    for (int s = lane; s < kRowPad; s += 32) {
+        float v = 0.f;
+        if (s < S) {
+            const float w = a.logprob[((size_t)t * a.nbatch + b) * S + s];
+            // Z_t = score - offset(alpha_t) - offset(beta_{t+1})
+            const float z = score2 - a.coff[(size_t)b * a.nblk + t] -
+                            a.coff[((size_t)a.nbatch + b) * a.nblk + t];
+            const float sc = s < a.nsharp ? a.sharp * kLog2e : kLog2e;
+            v = s < a.ncan ? fmaf(w, sc, -z) : w * sc;
         }
-        for (int s = lane; s < kRowPad; s += 32) {
-            float v = 0.f;
-            if (s < S) {
-                const float w = a.logprob[((size_t)t * a.nbatch + b) * S + s];
-                // Z_t = score - offset(alpha_t) - offset(beta_{t+1})
-                const float z = score2 - a.coff[(size_t)b * a.nblk + t] -
-                                a.coff[((size_t)a.nbatch + b) * a.nblk + t];
-                const float sc = s < a.nsharp ? a.sharp * kLog2e : kLog2e;
-                v = s < a.ncan ? fmaf(w, sc, -z) : w * sc;
-            }
-            q[r][s] = v;
-            bins[r][s] = 0.f;
-        }
-    }
-    {
-        const uint32_t *gw = a.ent_w + (size_t)b * 2 * Ls;
-        for (int i = tid; i < n1; i += kPostWarps * 32) words[i] = gw[i];
-        if (MOD) {
-            const float *gf = a.ent_mf + (size_t)b * 2 * Ls;
-            const uint32_t *gw2 = a.ent2_w + (size_t)b * Ls;
-            const float *gf2 = a.ent2_mf + (size_t)b * Ls;
-            for (int i = tid; i < n1; i += kPostWarps * 32) wmf[i] = gf[i];
-            for (int i = tid; i < n2; i += kPostWarps * 32) { words2[i] = gw2[i]; wmf2[i] = gf2[i]; }
-        }
-    }
-    __syncthreads();
-    if (r >= nrow) return;
-
-    const float *ar = STAGED ? al + (size_t)r * Ls : a.fwd_ws + ((size_t)b * a.nblk + t) * Ls;
-    const float *br = STAGED ? be + (size_t)r * bes : a.bwd_ws + ((size_t)b * a.nblk + t) * Ls;
-    const float *qr = q[r];
-    float *binr = bins[r];
-    {
-        // contiguous slice of the sorted entries for this lane
-        const int per = (n1 + 31) / 32;
-        const int lo = min(n1, lane * per), hi = min(n1, lo + per);
-        float acc = 0.f;
-        int cur = -1;
-        for (int j = lo; j < hi; j++) {
-            const uint32_t w = words[j];
-            const int pa = w & 0x1fff, mvf = (w >> 13) & 1, bin = (w >> 14) & 63;
-            if (bin != cur) {
-                if (cur >= 0) atomicAdd(&binr[cur], acc);
-                cur = bin; acc = 0.f;
-            }
-            float x = ar[pa] + br[pa + mvf] + qr[bin];
-            if (MOD) x = fmaf(qr[(w >> 20) & 63], wmf[j], x);   // 0 * w for stays
-            acc += ex2f(x);
-        }
-        if (cur >= 0) atomicAdd(&binr[cur], acc);
-    }
-    if (MOD) {
-        const int per = (n2 + 31) / 32;
-        const int lo = min(n2, lane * per), hi = min(n2, lo + per);
-        float acc = 0.f;
-        int cur = -1;
-        for (int j = lo; j < hi; j++) {
-            const uint32_t w = words2[j];
-            const int pa = w & 0x1fff, bin = (w >> 14) & 63, mvb = (w >> 20) & 63;
-            const float f = wmf2[j];
-            if (bin != cur) {
-                if (cur >= 0) atomicAdd(&binr[cur], acc);
-                cur = bin; acc = 0.f;
-            }
-            const float x = fmaf(qr[bin], f, ar[pa] + br[pa + 1] + qr[mvb]);
-            acc = fmaf(ex2f(x), f, acc);              // c_cat_mod_flipflop.c:465-466
-        }
-        if (cur >= 0) atomicAdd(&binr[cur], acc);
+        q[r][s] = v;
     }
     __syncwarp();
-    // normalise the canonical bins to sum to one and write the row once
-    float part = 0.f;
-    for (int s = lane; s < a.ncan; s += 32) part += binr[s];
-    const float scale = a.grad_scale / warp_sum(part);
-    for (int s = lane; s < S; s += 32)
-        a.grad_out[((size_t)t * a.nbatch + b) * S + s] = scale * binr[s];
+    const int off = a.seqoff[b];
+    const float *ar = a.fwd_ws + ((size_t)b * a.nblk + t) * Ls;
+    const float *br = a.bwd_ws + ((size_t)b * a.nblk + t) * Ls;
+    const int32_t *st = a.stayidx + off;
+    const int32_t *mv = a.moveidx + (off - b);
+    const int32_t *mm = MOD ? a.modmoveidx + (off - b) : nullptr;
+    const float *mf = MOD ? a.modmovefact + (off - b) : nullptr;
+    const float *qr = q[r];
+    for (int p0 = lane; p0 < L; p0 += 4 * 32) {
+        float al[4], be[4], be1[4], f[4];
+        int is[4], im[4], ix[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {                        // loads of four positions in flight together
+            const int p = min(p0 + 32 * u, L - 1);
+            const bool has_move = p < L - 1;
+            al[u] = __ldcs(ar + p);
+            be[u] = __ldcs(br + p);
+            be1[u] = has_move ? __ldcs(br + p + 1) : 0.f;
+            is[u] = st[p];
+            im[u] = has_move ? mv[p] : -1;
+            ix[u] = (MOD && has_move) ? mm[p] : 0;
+            f[u] = (MOD && has_move) ? mf[p] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (p0 + 32 * u < L) {
+                float *cs = mycol + is[u] * 32;
+                *cs += ex2f(al[u] + be[u] + qr[is[u]]);
+                if (im[u] >= 0) {
+                    float x = al[u] + be1[u] + qr[im[u]];
+                    if (MOD) x = fmaf(qr[ix[u]], f[u], x);
+                    const float e = ex2f(x);
+                    float *cm = mycol + im[u] * 32;
+                    *cm += e;
+                    if (MOD) {                               // c_cat_mod_flipflop.c:465-466
+                        float *cx = mycol + ix[u] * 32;
+                        *cx = fmaf(e, f[u], *cx);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // sum the 32 columns of each transition: lane l rows l and l + 32, rotated start
+    float tot[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r2 = 0; r2 < 2; r2++) {
+        const int row = lane + 32 * r2;
+        if (row < S) {
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) tot[r2] += cols[row * 32 + ((k + lane) & 31)];
+        }
+    }
+    // normalise the canonical transitions to sum to one and write the row once
+    const float psum = (lane < a.ncan ? tot[0] : 0.f) + (lane + 32 < a.ncan ? tot[1] : 0.f);
+    const float scale = a.grad_scale / warp_sum(psum);
+    float *g = a.grad_out + ((size_t)t * a.nbatch + b) * S;
+    if (lane < S) g[lane] = scale * tot[0];
+    if (lane + 32 < S) g[lane + 32] = scale * tot[1];
 }
 
 // ---------------------------------------------------------------------------
@@ -595,7 +455,7 @@ __global__ void indices_kernel(const int64_t *seqs, const int64_t *seqlen, int n
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct CrfWsLayout {
-    size_t seqoff, fb, coff, fwd, bwd, ent_n, ent_w, ent_mf, ent2_w, ent2_mf, total;
+    size_t seqoff, fb, coff, fwd, bwd, total;
     int Ls;
 };
 
@@ -607,16 +467,10 @@ static CrfWsLayout crf_layout(int nblk, int nbatch, int max_seqlen, int want_gra
     w.seqoff = take((size_t)nbatch * sizeof(int));
     w.fb = take((size_t)nbatch * 2 * sizeof(float));
     if (want_grad) {
-        const size_t ne = (size_t)nbatch * 2 * w.Ls;
         // nblk + 1 rows per chunk: the fused kernel also spills the vector both chains meet at
         w.coff = take((size_t)2 * nbatch * (nblk + 1) * sizeof(float));
         w.fwd = take((size_t)nbatch * (nblk + 1) * w.Ls * sizeof(float));
         w.bwd = take((size_t)nbatch * (nblk + 1) * w.Ls * sizeof(float));
-        w.ent_n = take((size_t)nbatch * 2 * sizeof(int));
-        w.ent_w = take(ne * sizeof(uint32_t));
-        w.ent_mf = take(ne * sizeof(float));
-        w.ent2_w = take(ne / 2 * sizeof(uint32_t));
-        w.ent2_mf = take(ne / 2 * sizeof(float));
     }
     w.total = o;
     return w;
@@ -628,7 +482,7 @@ static void launch_chain(const CrfArgs &a, int max_seqlen, cudaStream_t s) {
     threads = (threads + 31) / 32 * 32;
     if (threads < 32) threads = 32;
     threads += 32;       // the transformer warp
-    const int grid = a.nchain + (a.want_grad ? a.nbatch : 0);
+    const int grid = a.nchain;
     crf_chain_kernel<P, MOD><<<grid, threads, 0, s>>>(a);
 }
 
@@ -732,11 +586,6 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
     a.coff = reinterpret_cast<float *>(base + w.coff);
     a.fwd_ws = reinterpret_cast<float *>(base + w.fwd);
     a.bwd_ws = reinterpret_cast<float *>(base + w.bwd);
-    a.ent_n = reinterpret_cast<int *>(base + w.ent_n);
-    a.ent_w = reinterpret_cast<uint32_t *>(base + w.ent_w);
-    a.ent_mf = reinterpret_cast<float *>(base + w.ent_mf);
-    a.ent2_w = reinterpret_cast<uint32_t *>(base + w.ent2_w);
-    a.ent2_mf = reinterpret_cast<float *>(base + w.ent2_mf);
     a.Ls = w.Ls;
     a.want_grad = want_grad;
     a.nchain = want_grad ? 2 * nbatch : nbatch;
@@ -760,34 +609,17 @@ extern "C" int ty_crf_flipflop(const float *logprob, int ntrans, int nblk, int n
     int rc = check_launch("crf_chain_kernel");
     if (rc) return rc;
     if (want_grad) {
-        // one warp per row; alpha/beta rows + the chunk's entry lists in shared memory, or only
-        // the entry lists when the rows of a long chunk would not fit
-        size_t lists = 2 * (size_t)w.Ls * sizeof(uint32_t);
-        if (mod) lists += 2 * (size_t)w.Ls * sizeof(float) + (size_t)w.Ls * 8;
-        size_t smem = (size_t)kPostWarps * (2 * (size_t)w.Ls + 4) * sizeof(float) + lists;
-        const bool staged = smem <= 200 * 1024;
-        if (!staged) smem = lists;
-        if (smem > 200 * 1024) {
-            set_error("ty_crf_flipflop: max_seqlen %d needs %zu bytes of shared memory", max_seqlen, smem);
-            return TY_EINVAL;
-        }
+        // one warp per row; shared memory holds only the [transition][lane] tables of the block's warps
+        const size_t smem = (size_t)kPostWarps * ntrans * 32 * sizeof(float);
         const dim3 grid((nblk + kPostWarps - 1) / kPostWarps, nbatch);
-#define TY_POST(M, ST)                                                                          \
-    do {                                                                                        \
-        static bool attr = false;                                                               \
-        if (!attr) {                                                                            \
-            cudaFuncSetAttribute(crf_post_kernel<M, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 200 * 1024);                                                   \
-            attr = true;                                                                        \
-        }                                                                                       \
-        crf_post_kernel<M, ST><<<grid, kPostWarps * 32, smem, s>>>(a);                           \
-    } while (0)
-        if (mod) {
-            if (staged) TY_POST(true, true); else TY_POST(true, false);
-        } else {
-            if (staged) TY_POST(false, true); else TY_POST(false, false);
+        static bool opted = false;
+        if (!opted) {
+            cudaFuncSetAttribute(crf_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+            cudaFuncSetAttribute(crf_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+            opted = true;
         }
-#undef TY_POST
+        if (mod) crf_post_kernel<true><<<grid, kPostWarps * 32, smem, s>>>(a);
+        else crf_post_kernel<false><<<grid, kPostWarps * 32, smem, s>>>(a);
         rc = check_launch("crf_post_kernel");
     }
     return rc;

@@ -32,9 +32,9 @@
 
 namespace ty {
 
-// posterior warps per CTA: 8, or 4 when the chunk is too long for the shared memory of 8
-// (partner-row buffers and column tables are per warp); a ring slot is always consumed by the
-// same warp (kFRing % PW == 0) -- the parity waits below rely on it
+// posterior warps per CTA: 8 (template parameter PW; partner-row buffers and column tables are per
+// warp); a ring slot is always consumed by the same warp (kFRing % PW == 0) -- the parity waits
+// below rely on it
 constexpr int kFRing = 8;       // ring slots (a, b rows of the DP warps -> posterior warps)
 
 __device__ __forceinline__ uint32_t f_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -553,11 +553,12 @@ static int fused_threads(int P, int max_seqlen, int pw) {
 // posterior warps the shape runs with (0: outside the fused kernel's range)
 static int fused_pick_pw(int P, int Ls, int max_seqlen) {
     if (!crf_tuning().fused || max_seqlen <= 0 || (P != 4 && P != 8)) return 0;
-    for (int pw = 8; pw >= 4; pw -= 4) {
-        if (fused_threads(P, max_seqlen, pw) > (P <= 4 ? 640 : 544)) continue;
-        if (FusedSmem{Ls, pw}.total() <= 200 * 1024) return pw;
-    }
-    return 0;
+    // eight posterior warps or none: with four (all that fits beyond ~1140 positions) the posterior
+    // paces the chain and the kernel pair is faster (tools/microbench.py sweep, nblk 2000: 1.24 ms
+    // against 1.03 ms; cat-mod config B 1.55 against 1.44 ms)
+    const int pw = 8;
+    if (fused_threads(P, max_seqlen, pw) > (P <= 4 ? 640 : 544)) return 0;
+    return FusedSmem{Ls, pw}.total() <= 212 * 1024 ? pw : 0;
 }
 
 bool crf_fused_eligible(int P, bool mod, int Ls, int max_seqlen) {
@@ -575,9 +576,9 @@ static int launch_fused(const CrfArgs &a, int max_seqlen, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaError_t e = cudaSuccess;
     if (dev < 0 || dev >= 64 || !opted[dev]) {
-        e = cudaFuncSetAttribute(crf_fused_kernel<P, MOD, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaFuncSetAttribute(crf_fused_kernel<P, MOD, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
         if (e != cudaSuccess) {
-            set_error("crf_fused_kernel: cudaFuncSetAttribute(%d bytes): %s", 200 * 1024, cudaGetErrorString(e));
+            set_error("crf_fused_kernel: cudaFuncSetAttribute(%d bytes): %s", 212 * 1024, cudaGetErrorString(e));
             return TY_ECUDA;
         }
         if (dev >= 0 && dev < 64) opted[dev] = true;
@@ -606,8 +607,7 @@ int launch_crf_fused(CrfArgs a, int P, bool mod, int max_seqlen, cudaStream_t s)
     const int pw = fused_pick_pw(P, a.Ls, max_seqlen);
 #define TY_FUSED(PP, MM, WW) \
     if (P == PP && mod == MM && pw == WW) return launch_fused<PP, MM, WW>(a, max_seqlen, s);
-    TY_FUSED(4, false, 8) TY_FUSED(4, false, 4) TY_FUSED(4, true, 8) TY_FUSED(4, true, 4)
-    TY_FUSED(8, false, 8) TY_FUSED(8, false, 4) TY_FUSED(8, true, 8) TY_FUSED(8, true, 4)
+    TY_FUSED(4, false, 8) TY_FUSED(4, true, 8) TY_FUSED(8, false, 8) TY_FUSED(8, true, 8)
 #undef TY_FUSED
     set_error("crf_fused_kernel: P = %d with %d posterior warps not instantiated", P, pw);
     return TY_EINVAL;

@@ -100,8 +100,9 @@ def test_chunks_without_labels_in_the_batch(dev, mod):
 
 @pytest.mark.parametrize('L', [127, 128, 129, 511, 512, 513, 1024, 1100])
 def test_chunk_lengths_at_the_block_boundaries(dev, L):
-    """positions per thread x warps: a DP warp boundary falls at multiples of 128 (P = 4); from
-    about 1140 positions on the fused kernel runs with four posterior warps instead of eight."""
+    """positions per thread x warps: a DP warp boundary falls at multiples of 128 (P = 4); the
+    fused kernel takes chunks up to about 1100 positions (shared memory of its eight posterior
+    warps), the kernel pair the longer ones."""
     nblk = L + 40
     scores, seqs, seqlen, _ = _inputs(nblk, 2, False, seed=L, lengths=[L, max(1, L // 3)])
     c1, g1, p1 = _run(dev, scores, seqs, seqlen, None, 1.0, fused=True)
@@ -133,9 +134,9 @@ def test_sharpening_and_scaling(dev):
 
 
 def test_long_chunks_take_the_two_kernel_path(dev):
-    """Rows that do not fit in shared memory next to the ring (here 2600 positions) keep the
-    spill + posterior kernel pair."""
-    L = 2600
+    """Rows that do not fit in shared memory next to the ring (from about 1100 positions on) keep
+    the spill + posterior kernel pair."""
+    L = 1300
     scores, seqs, seqlen, _ = _inputs(L + 10, 1, False, seed=5, lengths=[L])
     c1, g1, p1 = _run(dev, scores, seqs, seqlen, None, 1.0, fused=True)
     assert p1 == TWO_KERNEL
