@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(256) conv_in1_fwd_kernel(const float *__restri
             for (int r = 0; r < rows; r++) {
                 float acc = bc;
 #pragma unroll
-                for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++) acc = fmaf(wr[j], xs[j][r], acc);
+                for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++)
+                    if (K > 0 || j < k) acc = fmaf(wr[j], xs[j][r], acc);     // rows >= k of xs are never written
                 zo[(size_t)r * cout] = acc;
             }
         }
@@ -369,7 +370,8 @@ __global__ void __launch_bounds__(256) conv_in1_wgrad_kernel(const float *__rest
                     const float d = dzo[(size_t)r * cout];
                     accb += d;
 #pragma unroll
-                    for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++) acc[j] = fmaf(d, xs[j][r], acc[j]);
+                    for (int j = 0; j < (K > 0 ? K : kIn1MaxK); j++)
+                        if (K > 0 || j < k) acc[j] = fmaf(d, xs[j][r], acc[j]);
                 }
             }
         }

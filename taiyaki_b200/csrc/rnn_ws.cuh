@@ -60,6 +60,17 @@ struct RnnWsArgs {
 };
 
 constexpr int kS = 4;         // ring slots
+// Bytes per partial dL/dh sum crossing the cluster in the backward kernel.  2 = bf16 pairs
+// (default): the reduce-scatter then moves 512 B per CTA pair and step, like the forward exchange,
+// instead of 1 KB -- backward kernel 0.435 ms per layer against 0.510 ms (config A, inside the
+// step), and against the fp32 parity mode over 800 steps the gradients are where they were
+// (input gradient 0.38 % relative, weight gradients 0.25-0.42 %): the partial sums are products of
+// bf16 operands whose rounding already sets that level.  4 = fp32 (-DTY_BWD_FP32_PARTIALS).
+#ifdef TY_BWD_FP32_PARTIALS
+constexpr int kPartialBytes = 4;
+#else
+constexpr int kPartialBytes = 2;
+#endif
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -456,7 +467,7 @@ struct BwdLayout {
     static_assert(H % CL == 0 && U % 8 == 0 && CL % 2 == 0 && (H / 16) % NCW == 0, "hidden size / cluster size");
     static constexpr int DS = KL + 8;                       // bf16 per chunk row of a ds slot
     static constexpr int CROW = U + 4;                      // floats per chunk row of dy / c / prev
-    static constexpr int RS_BYTES = 2 * CL * U * kNB * 4;
+    static constexpr int RS_BYTES = 2 * CL * U * kNB * kPartialBytes;
     static constexpr int DS_BYTES = kNB * DS * 2;           // one slot
     static constexpr int IG_BYTES = kNB * U * 16;
     static constexpr int IC_BYTES = kNB * CROW * 4;
@@ -650,7 +661,7 @@ __global__ void __launch_bounds__(BwdLayout<CELL, H, CL>::NCT + 32, 1)
             constexpr int SLOT = decltype(slot_c)::value;
             constexpr int cur = SLOT & 1, nxt = cur ^ 1;
             const int sf = T - 1 - s;
-            if (tid == 0 && s + 1 < T) mbar_arrive_expect_tx(&full[nxt], CL * U * kNB * 4);
+            if (tid == 0 && s + 1 < T) mbar_arrive_expect_tx(&full[nxt], CL * U * kNB * kPartialBytes);
             float dh[2] = {dyv[0], dyv[1]};
             if (s > 0) {
                 mbar_wait(&full[cur], (phase >> cur) & 1u);
@@ -658,9 +669,15 @@ __global__ void __launch_bounds__(BwdLayout<CELL, H, CL>::NCT + 32, 1)
                 float sx = 0.f, sy = 0.f;
 #pragma unroll
                 for (int j = 0; j < CL; j++) {
-                    const float2 v = *reinterpret_cast<const float2 *>(
-                        rs + ((cur * CL + j) * U + ul) * kNB + 2 * q);
-                    sx += v.x; sy += v.y;
+                    if (kPartialBytes == 4) {
+                        const float2 v = *reinterpret_cast<const float2 *>(
+                            rs + ((cur * CL + j) * U + ul) * kNB + 2 * q);
+                        sx += v.x; sy += v.y;
+                    } else {
+                        const uint32_t w = *reinterpret_cast<const uint32_t *>(
+                            reinterpret_cast<const unsigned char *>(rs) + (((cur * CL + j) * U + ul) * kNB + 2 * q) * 2);
+                        sx += __uint_as_float(w << 16); sy += __uint_as_float(w & 0xffff0000u);
+                    }
                 }
                 dh[0] += sx; dh[1] += sy;
             }
@@ -735,7 +752,7 @@ __global__ void __launch_bounds__(BwdLayout<CELL, H, CL>::NCT + 32, 1)
                     }
                 }
                 // reduce-scatter: rows of this warp's tiles belong to the CTA owning those units
-                const uint32_t rs_nxt = rs_base + (uint32_t)(((nxt * CL + rank) * U * kNB) * 4);
+                const uint32_t rs_nxt = rs_base + (uint32_t)(((nxt * CL + rank) * U * kNB) * kPartialBytes);
                 const uint32_t bar = bar_base + (uint32_t)(nxt * 8);
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
@@ -746,8 +763,9 @@ __global__ void __launch_bounds__(BwdLayout<CELL, H, CL>::NCT + 32, 1)
                         const int hl = h - dest * U;
                         const float x = acc[mt][0][2 * half] + acc[mt][1][2 * half];
                         const float y = acc[mt][0][2 * half + 1] + acc[mt][1][2 * half + 1];
-                        const uint32_t local = rs_nxt + (uint32_t)((hl * kNB + 2 * q) * 4);
-                        st_async_v2(mapa(local, dest), x, y, mapa(bar, dest));
+                        const uint32_t local = rs_nxt + (uint32_t)((hl * kNB + 2 * q) * kPartialBytes);
+                        if (kPartialBytes == 4) st_async_v2(mapa(local, dest), x, y, mapa(bar, dest));
+                        else st_async_b32(mapa(local, dest), pack_bf16(x, y), mapa(bar, dest));
                     }
                 }
                 mbar_wait(&ifull[(SLOT + 1) & (kS - 1)], (uint32_t)((s + 1) >> 2) & 1u);
