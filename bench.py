@@ -46,10 +46,10 @@ sys.path.insert(0, ROOT)
 T_SIG, NCHUNK, SIZE, STRIDE, NTRANS = 4000, 64, 256, 5, 40
 METRIC = 'signal_samples_per_sec_flipflop_train_step'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the loss kernels at this workload, from
-# `ncu --set full` captures (profiles/r2_ncu_loss_summary.csv): crf_fused_kernel 32.80 + 66.16 MB,
+# `ncu --set full` captures (profiles/r2_ncu_loss_summary.csv): crf_fused_kernel 33.50 + 67.44 MB,
 # logz_chain_kernel 8.24 + 0, logz_post_kernel 11.47 + 0  (round 1, chain + posterior kernel pair
 # with the full alpha / beta spill: 356.7 MB)
-NCU_TRAFFIC_BYTES = int((32.80 + 66.16 + 8.24 + 0.0 + 11.47 + 0.0) * 1e6)
+NCU_TRAFFIC_BYTES = int((33.50 + 67.44 + 8.24 + 0.0 + 11.47 + 0.0) * 1e6)
 NCU_TRAFFIC_SOURCE = ('profiles/r2_ncu_loss_summary.csv: dram read+write of crf_fused_kernel + logz_chain_kernel + '
                       'logz_post_kernel, one launch each, config A')
 WORKLOAD = 'mLstm_flipflop size256 stride5, T_sig=4000 (nblk=800), 64 chunks/GPU, S=40'
