@@ -169,7 +169,7 @@ int ty_flipflop_train_loss(const float *scores, int ntrans, int nblk, int nbatch
 
 /* ----------------------------------------------------------------------
  * Recurrent layers (time-major [T][N][H], PyTorch gate order, b_hh == 0).
- * See taiyaki_b200/csrc/rnn.cu for the data layout of `reserve`.
+ * See taiyaki_b200/csrc/rnn_fp32.cu / rnn_common.cuh for the data layout of `reserve`.
  * xproj: [T][N][G*H] = x W_ih^T computed by the caller (one large GEMM);
  * bias: [G*H] input bias b_ih added inside the kernel (NULL if already in
  * xproj); w_hh: [G*H][H] fp32; reverse != 0 iterates t downward

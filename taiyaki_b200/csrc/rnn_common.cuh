@@ -1,5 +1,5 @@
 // rnn_common.cuh -- PTX wrappers, argument block and cell traits shared by the
-// recurrent kernels (rnn.cu: one-role kernels behind the gate-major ABI;
+// recurrent kernels (rnn_fp32.cu: fp32 recurrence behind the gate-major ABI;
 // rnn_ws.cu: warp-specialised kernels behind the unit-major ABI).
 #pragma once
 #include <cuda_bf16.h>
