@@ -1,6 +1,6 @@
 // crf_fused.cu -- label-constrained flip-flop CRF forward / backward with the posterior
 // fused into the chains ("meet in the middle"); replaces crf_chain_kernel + crf_post_kernel
-// for chunks whose rows fit in shared memory.  Same mathematics as crf_flipflop.cu
+// for chunks whose rows fit in shared memory (up to ~1100 positions).  Same mathematics as crf_flipflop.cu
 // (c_crf_flipflop.c:43-516, c_cat_mod_flipflop.c:37-582).
 //
 // One CLUSTER of two CTAs per chunk: rank 0 runs the forward chain, rank 1 the backward
@@ -14,8 +14,8 @@
 //                a = alpha_t[p] + stay_t(p),   b = alpha_t[p-1] + move_t(p-1 -> p),
 //            are exactly the posterior exponents of those two lattice edges once
 //            beta_{t+1}[p] (spilled by the partner in phase 1) and the normaliser are added;
-//            the DP warps drop a, b into a shared-memory ring and carry on, and four
-//            POSTERIOR WARPS of the same CTA (one per SM sub-partition, in the issue slots
+//            the DP warps drop a, b into a shared-memory ring and carry on, and eight
+//            POSTERIOR WARPS of the same CTA (two per SM sub-partition, in the issue slots
 //            the latency-bound DP warps leave free) fetch the partner row with cp.async and
 //            scatter 2^x into per-LANE columns of a [transition][lane] table in shared
 //            memory (position p -> lane p % 32; a lane owns its column, so the adds are
