@@ -9,4 +9,4 @@ Mirrors the operator surface of nanoporetech/taiyaki v5.3.0 for that path:
 All compute runs in hand-written CUDA kernels behind the C ABI declared in
 include/taiyaki_b200.h; there is no CPU fallback.
 """
-__version__ = '0.1.0'
+__version__ = '0.2.0'

@@ -156,7 +156,7 @@ static void host_crf(const float *logprob, size_t ntrans, size_t nblk, size_t nb
 using namespace ty;
 
 extern "C" const char *ty_last_error_string(void) { return g_err; }
-extern "C" const char *ty_version(void) { return "taiyaki_b200 0.1 (sm_100a)"; }
+extern "C" const char *ty_version(void) { return "taiyaki_b200 0.2 (sm_100a)"; }
 
 extern "C" void crf_flipflop_grad(const float *logprob, size_t ntrans, size_t nblk,
                                   size_t nbatch, const size_t *moveidxs,
