@@ -358,11 +358,14 @@ def run_arm():
     torch.cuda.synchronize()
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     seen0, wall0 = loop.samples_seen, time.perf_counter()
+    loop.iter_times = []
     ev_a.record()
     loop.run(K)
     ev_b.record()
     torch.cuda.synchronize()
     wall_entry = time.perf_counter() - wall0
+    iter_ms = np.diff(np.array(loop.iter_times + [time.perf_counter()])) * 1e3
+    loop.iter_times = None
     ms_entry = torch.tensor([max(ev_a.elapsed_time(ev_b), wall_entry * 1e3)], device=device)
     entry_samples = torch.tensor([float(loop.samples_seen - seen0)], device=device)
     if world > 1:
@@ -515,6 +518,8 @@ def run_arm():
                 'reads_resident_bytes': int(store.dacs.numel() * 2 + store.r2s.numel() * 4 +
                                             store.ref.numel() * 2),
                 'ms_per_step': ms_entry / K, 'fraction_of_value': e2e / value,
+                'host_iteration_ms': {'median': float(np.median(iter_ms)), 'max': float(iter_ms.max()),
+                                      'argmax': int(iter_ms.argmax())},
                 'timed_as': 'max(CUDA events, host wall clock) around K iterations, max over ranks',
                 'host_signal_leg': {
                     'value': e2e_host, 'unit': 'samples/s', 'ms_per_step': ms_host / K,

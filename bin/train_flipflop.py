@@ -395,6 +395,7 @@ class TrainLoop:
         self.next_shape = None
         self.deferred_log = None
         self.lr_of_iter = {}
+        self.iter_times = None
         self.time_last = time.time()
 
     def draw_batch_shape(self):
@@ -440,6 +441,8 @@ class TrainLoop:
 
         while self.curr_iter < last:
             curr_iter = self.curr_iter
+            if self.iter_times is not None:          # host time stamp per iteration (bench.py diagnostics)
+                self.iter_times.append(time.perf_counter())
             sharpen = float(tp.sharpen.min + (tp.sharpen.max - tp.sharpen.min) *
                             min(1.0, curr_iter / tp.sharpen.niter))
             mod_factor = float(mod_info.mod_factor.start + (
