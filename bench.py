@@ -104,16 +104,31 @@ class ClockSampler(threading.Thread):
             'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
             'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4),
         }
-        while not self.stop_flag:
+        # NVML queries contend with kernel launches inside the driver: with a query every 50 ms the
+        # launching thread stalled 30-120 ms now and then (one iteration out of ~50; `e2e.host_iteration_ms`,
+        # A/B with the sampler off at 4 GPUs).  So: the SM clock every 200 ms, the throttle reasons every
+        # fifth sample and once more when the sampler is stopped (still inside the measured part of the run).
+        period = float(os.environ.get('TY_BENCH_NVML_PERIOD', '0.2'))
+
+        def reasons():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+        n = 0
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
+            if n % 5 == 0:
+                reasons()
+            n += 1
+            time.sleep(period)
+        reasons()
 
     def summary(self):
         return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
@@ -309,6 +324,8 @@ def run_arm():
     assert step_fn.flat.check_views(), 'gradient views detached from the flat buffer'
 
     sampler = ClockSampler(local_rank)
+    if os.environ.get('TY_BENCH_NO_NVML', '0') == '1':      # diagnostics: is the sampler itself the disturbance?
+        sampler.nv = None
     sampler.start()
     launches0 = _lib.LAUNCHES
     _lib.PROFILE = {}
@@ -357,6 +374,15 @@ def run_arm():
         dist.barrier()
     torch.cuda.synchronize()
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc_pauses, gc_t0 = [], [0.0]
+
+    def gc_cb(phase, info):
+        if phase == 'start':
+            gc_t0[0] = time.perf_counter()
+        else:
+            gc_pauses.append((time.perf_counter() - gc_t0[0]) * 1e3)
+    gc.callbacks.append(gc_cb)
     seen0, wall0 = loop.samples_seen, time.perf_counter()
     loop.iter_times = []
     ev_a.record()
@@ -366,12 +392,17 @@ def run_arm():
     wall_entry = time.perf_counter() - wall0
     iter_ms = np.diff(np.array(loop.iter_times + [time.perf_counter()])) * 1e3
     loop.iter_times = None
+    gc.callbacks.remove(gc_cb)
     ms_entry = torch.tensor([max(ev_a.elapsed_time(ev_b), wall_entry * 1e3)], device=device)
     entry_samples = torch.tensor([float(loop.samples_seen - seen0)], device=device)
     if world > 1:
         dist.all_reduce(ms_entry, op=dist.ReduceOp.MAX)
         dist.all_reduce(entry_samples, op=dist.ReduceOp.SUM)
     ms_entry, entry_samples = float(ms_entry), float(entry_samples)
+    gc_max = torch.tensor([max(gc_pauses) if gc_pauses else 0.0], device=device)
+    if world > 1:
+        dist.all_reduce(gc_max, op=dist.ReduceOp.MAX)
+    gc_max = float(gc_max)
     store = loop.prefetcher.store
     attempts = max(NCHUNK, int(NCHUNK / fp.filter_min_pass_fraction))
     sampler.stop_flag = True
@@ -519,7 +550,9 @@ def run_arm():
                                             store.ref.numel() * 2),
                 'ms_per_step': ms_entry / K, 'fraction_of_value': e2e / value,
                 'host_iteration_ms': {'median': float(np.median(iter_ms)), 'max': float(iter_ms.max()),
-                                      'argmax': int(iter_ms.argmax())},
+                                      'argmax': int(iter_ms.argmax()),
+                                      'gc_collections': len(gc_pauses),
+                                      'gc_pause_ms_max_over_ranks': gc_max},
                 'timed_as': 'max(CUDA events, host wall clock) around K iterations, max over ranks',
                 'host_signal_leg': {
                     'value': e2e_host, 'unit': 'samples/s', 'ms_per_step': ms_host / K,

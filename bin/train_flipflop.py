@@ -396,6 +396,14 @@ class TrainLoop:
         self.deferred_log = None
         self.lr_of_iter = {}
         self.iter_times = None
+        # Everything built so far (model, optimiser, reads, torch's own module graph) lives for the whole
+        # run: take it out of the garbage collector's generations, so that a full collection in the middle
+        # of training walks the few objects of a step instead of all of them (pauses of ~50 ms were
+        # measured, a whole iteration's worth of device time: `e2e.host_iteration_ms` of bench.py).
+        if os.environ.get('TY_GC_FREEZE', '1') != '0':
+            import gc
+            gc.collect()
+            gc.freeze()
         self.time_last = time.time()
 
     def draw_batch_shape(self):
