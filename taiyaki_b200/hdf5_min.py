@@ -77,8 +77,14 @@ def _dataspace(buf, off):
 
 class File:
     def __init__(self, filename):
+        # the file is mapped, not read: mapped-signal training files are tens of GB, and only the
+        # pages of the objects that are decoded get touched
+        import mmap
         with open(filename, 'rb') as fh:
-            self.buf = fh.read()
+            try:
+                self.buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except (ValueError, OSError):       # empty file / no mmap on this file system
+                self.buf = fh.read()
         b = self.buf
         if b[:8] != b'\x89HDF\r\n\x1a\n':
             raise Hdf5FormatError('not an HDF5 file: %s' % filename)
@@ -250,7 +256,7 @@ class Group(_Node):
                     e = child + 8 + 40 * s
                     name_off, header = struct.unpack_from('<QQ', b, e)
                     q = heap_data + name_off
-                    name = b[q:b.index(b'\0', q)].decode()
+                    name = b[q:b.find(b'\0', q)].decode()
                     self._links[name] = header + f.base
         walk(btree + f.base)
 
