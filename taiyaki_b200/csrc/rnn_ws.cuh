@@ -800,10 +800,29 @@ __global__ void __launch_bounds__(BwdLayout<CELL, H, CL>::NCT + 32, 1)
 template <typename K>
 static int launch_ws(K kernel, int cl, int smem_bytes, int groups, int threads, const RnnWsArgs &a,
                      cudaStream_t s, const char *what) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) {
-        set_error("%s: cudaFuncSetAttribute(%d bytes): %s", what, smem_bytes, cudaGetErrorString(e));
-        return TY_ECUDA;
+    // Opt in to the kernel's dynamic shared memory once per (kernel, device) instead of on every launch
+    // (a driver call).  Every instantiation has the same function type, so this template is
+    // instantiated once and the kernels are told apart by their address.
+    static const void *opted[8][96] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void *key = reinterpret_cast<const void *>(kernel);
+    bool known = false;
+    int slot = -1;
+    if (dev >= 0 && dev < 8) {
+        for (int i = 0; i < 96; i++) {
+            if (opted[dev][i] == key) { known = true; break; }
+            if (opted[dev][i] == nullptr) { slot = i; break; }
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    if (!known) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) {
+            set_error("%s: cudaFuncSetAttribute(%d bytes): %s", what, smem_bytes, cudaGetErrorString(e));
+            return TY_ECUDA;
+        }
+        if (slot >= 0) opted[dev][slot] = key;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * cl);
