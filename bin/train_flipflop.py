@@ -122,6 +122,11 @@ def get_train_flipflop_parser():
     g = p.add_argument_group('Modified Base Arguments')
     g.add_argument('--mod_factor', default=(8.0, 1.0, 50000), nargs=3, type=float,
                    metavar=('start', 'final', 'niter'))
+    g.add_argument('--mod_prior_factor', type=float, default=None,
+                   help='Exponent applied to the prior weights of the modified-base categories '
+                        'estimated from the training reads.  Default: no prior (all weights 1)')
+    g.add_argument('--num_mod_weight_reads', type=int, default=5000,
+                   help='Number of reads sampled to estimate the modified-base prior weights')
     p.add_argument('model', help='File to read python model (or checkpoint) from')
     p.add_argument('input', help='Mapped-signal HDF5 file, or synthetic:NREADS[:5mC]')
     return p
@@ -216,7 +221,7 @@ def load_data(args, log, res_info):
             log.write('* No reads remaining for training, exiting.\n')
             sys.exit(1)
         log.write('* Loaded {} reads.\n'.format(len(read_data)))
-        mod_cat_weights = np.ones(alphabet_info.nbase, dtype=np.float32)
+        mod_cat_weights = mod_prior_weights(args, alphabet_info, read_data, log)
         return read_data, alphabet_info, training.MOD_INFO(mod_cat_weights, MOD_FACTOR(*args.mod_factor))
     parts = args.input.split(':')
     nreads = int(parts[1])
@@ -229,9 +234,26 @@ def load_data(args, log, res_info):
                      AlphabetInfo('ACGT', 'ACGT'))
     log.write('* Using alphabet definition: {}\n'.format(str(alphabet_info)))
     log.write('* Loaded {} reads.\n'.format(len(read_data)))
-    mod_cat_weights = np.ones(alphabet_info.nbase, dtype=np.float32)
+    mod_cat_weights = mod_prior_weights(args, alphabet_info, read_data, log)
     mod_info = training.MOD_INFO(mod_cat_weights, MOD_FACTOR(*args.mod_factor))
     return read_data, alphabet_info, mod_info
+
+
+def mod_prior_weights(args, alphabet_info, read_data, log):
+    """Per-category weights of the cat-mod loss: ones, or with --mod_prior_factor the prior odds
+    estimated from the reads raised to that power (train_flipflop.py:312-326)."""
+    factor = getattr(args, 'mod_prior_factor', None)
+    if factor is None:
+        return np.ones(alphabet_info.nbase, dtype=np.float32)
+
+    def listing(w):
+        return '  '.join('{}:{:.4f}'.format(b, x) for b, x in zip(alphabet_info.alphabet, w))
+    weights = alphabet_info.compute_log_odds_weights(read_data, getattr(args, 'num_mod_weight_reads', 5000))
+    log.write('* Computed modbase log odds priors:  {}\n'.format(listing(weights)))
+    if factor != 1.0:
+        weights = np.power(weights, factor)
+        log.write('* Applied mod_prior_factor to modbase log odds priors:  {}\n'.format(listing(weights)))
+    return weights.astype(np.float32)
 
 
 def load_network(args, alphabet_info, res_info, log):

@@ -58,6 +58,47 @@ class AlphabetInfo(object):
         """Modified bases -> their canonical bases (alphabet.py:120-124)."""
         return sequence_with_mods.translate(self.translation_table)
 
+    def _label_counts(self, read_data, nreads):
+        """Occurrences of each label in the references of `nreads` reads drawn without
+        replacement from `read_data` (objects with .Reference, or read dictionaries)."""
+        picked = np.random.choice(len(read_data), min(nreads, len(read_data)), replace=False)
+        refs = [read_data[i] for i in picked]
+        refs = [r['Reference'] if isinstance(r, dict) else r.Reference for r in refs]
+        counts = np.bincount(np.concatenate(refs).astype(np.int64))
+        if len(counts) < self.nbase or not counts.all():
+            # a label that never occurs has no frequency ratio (alphabet.py:58-59, :89-90)
+            raise NotImplementedError
+        return counts
+
+    def _alternatives(self, can_label):
+        """Labels collapsing onto `can_label`, without the first of them -- the canonical base
+        itself in an alphabet that lists canonical bases before their modifications."""
+        return np.flatnonzero(self.collapse_labels == can_label)[1:]
+
+    def compute_mod_inv_freq_weights(self, read_data, N):
+        """canonical count / modified count per modified base, 1 per canonical base, in the
+        output order of the cat-mod layer (alphabet.py:35-66)."""
+        counts = self._label_counts(read_data, N)
+        weights = []
+        for can_label in range(self.ncan_base):
+            weights.append(1.0)
+            weights.extend(counts[can_label] / counts[m] for m in self._alternatives(can_label))
+        return np.array(weights, dtype=np.float32)
+
+    def compute_log_odds_weights(self, read_data, N):
+        """Prior odds of the modified-base categories from `N` sampled reads, in the output order
+        of the cat-mod layer: (sum of modified counts) / canonical count for each canonical base,
+        then canonical count / modified count for each of its modifications
+        (alphabet.py:68-100; used by --mod_prior_factor, train_flipflop.py:312-326)."""
+        counts = self._label_counts(read_data, N)
+        weights = []
+        for base in self.can_bases:
+            can_label = self.alphabet.index(base)
+            alts = self._alternatives(can_label)
+            weights.append(counts[alts].sum() / counts[can_label])
+            weights.extend(counts[can_label] / counts[m] for m in alts)
+        return np.array(weights, dtype=np.float32)
+
     def contains_modified_bases(self):
         return len(self.mod_long_names) > 0
 

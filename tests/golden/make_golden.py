@@ -540,6 +540,34 @@ def make_remap():
           {t: (float(out[t + '_score']), int((out[t + '_path'] == -1).sum())) for t in cases})
 
 
+MOD_WEIGHT_ALPHABETS = [('ACGTZ', 'ACGTC', ['5mC']), ('ACGTZY', 'ACGTCA', ['5mC', '6mA']),
+                        ('ACGTZYX', 'ACGTCAC', ['5mC', '6mA', '5hmC'])]
+
+
+def mod_weight_reads(nlabel, seed=11, nreads=7):
+    """The label sequences both sides of tests/test_host.py::test_mod_prior_weights use."""
+    rng = np.random.RandomState(seed)
+    return [rng.randint(0, nlabel, size=200 + 13 * i).astype(np.int16) for i in range(nreads)]
+
+
+def make_mod_weights():
+    """AlphabetInfo.compute_log_odds_weights / compute_mod_inv_freq_weights of the reference
+    (taiyaki/alphabet.py:35-100) on seeded label sequences, all reads sampled."""
+    from taiyaki import alphabet as ref_alphabet
+
+    class Read:
+        def __init__(self, ref):
+            self.Reference = ref
+    out = {}
+    for alpha, collapse, names in MOD_WEIGHT_ALPHABETS:
+        info = ref_alphabet.AlphabetInfo(alpha, collapse, names)
+        refs = mod_weight_reads(len(alpha))
+        out[alpha + '_log_odds'] = info.compute_log_odds_weights([Read(r) for r in refs], 100)
+        out[alpha + '_inv_freq'] = info.compute_mod_inv_freq_weights([{'Reference': r} for r in refs], 100)
+    np.savez_compressed(os.path.join(HERE, 'mod_weights.npz'), **out)
+    print('mod_weights.npz:', {k: v.tolist() for k, v in out.items()})
+
+
 if __name__ == '__main__':
     # `make_golden.py decode` / `make_golden.py basecall` regenerate that file only
     if sys.argv[1:] == ['basecall']:
@@ -550,6 +578,8 @@ if __name__ == '__main__':
         make_remap()
     elif sys.argv[1:] == ['trained']:
         make_trained()
+    elif sys.argv[1:] == ['mod_weights']:
+        make_mod_weights()
     else:
         if sys.argv[1:] != ['decode']:
             main()
@@ -558,3 +588,4 @@ if __name__ == '__main__':
             make_basecall()
             make_real()
             make_remap()
+            make_mod_weights()

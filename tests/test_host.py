@@ -137,6 +137,31 @@ def test_train_cli_parser_defaults_match_reference():
     assert a.lr_max == 4e-3 and a.lr_min == 1e-4 and a.niteration == 150000
     assert tuple(a.sharpen) == (1.0, 1.0, 25000) and a.gradient_clip_num_mads == 0
     assert a.weight_decay == 0.01 and a.eps == 1e-6 and a.warmup_batches == 200
+    assert a.mod_prior_factor is None and a.num_mod_weight_reads == 5000
+
+
+def test_train_cli_mod_prior_factor():
+    """--mod_prior_factor: prior odds of the sampled reads raised to the factor
+    (train_flipflop.py:312-326); without the flag every category weighs 1."""
+    import io
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    import importlib
+    tf = importlib.import_module('train_flipflop')
+    from taiyaki_b200 import signal_mapping
+    from taiyaki_b200.alphabet import AlphabetInfo
+    info = AlphabetInfo('ACGTZ', 'ACGTC', ['5mC'])
+    reads = signal_mapping.synthetic_reads(20, seed=7, mod_fraction=0.5)
+    parser = tf.get_train_flipflop_parser()
+    plain = parser.parse_args(['models/mGru_cat_mod_flipflop.py', 'synthetic:20:5mC'])
+    np.testing.assert_array_equal(tf.mod_prior_weights(plain, info, reads, io.StringIO()), np.ones(5, 'f4'))
+    log = io.StringIO()
+    args = parser.parse_args(['--mod_prior_factor', '0.5', 'models/mGru_cat_mod_flipflop.py', 'synthetic:20:5mC'])
+    w = tf.mod_prior_weights(args, info, reads, log)
+    np.random.seed(0)
+    expect = np.power(info.compute_log_odds_weights(reads, 5000), 0.5)
+    np.testing.assert_allclose(w, expect, rtol=1e-6)
+    assert w.dtype == np.float32 and w[1] > 0 and w[2] > 0
+    assert 'Computed modbase log odds priors' in log.getvalue() and 'Applied mod_prior_factor' in log.getvalue()
 
 
 def test_model_definition_files_build():
@@ -162,6 +187,32 @@ def test_model_definition_files_build():
                              alphabet_info=AlphabetInfo('ACGT', 'ACGT'))
     assert sum(p.numel() for p in big.parameters()) == 2720400
     assert sum(p.numel() for p in big.parameters() if p.requires_grad) == 2715280
+
+
+def test_mod_prior_weights():
+    """Modified-base prior weights (--mod_prior_factor) against the reference's
+    AlphabetInfo.compute_log_odds_weights / compute_mod_inv_freq_weights (alphabet.py:35-100),
+    golden values from tests/golden/make_golden.py mod_weights."""
+    from taiyaki_b200.alphabet import AlphabetInfo
+    from taiyaki_b200.signal_mapping import SignalMapping
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'mod_weights.npz'))
+    for alpha, collapse, names in [('ACGTZ', 'ACGTC', ['5mC']), ('ACGTZY', 'ACGTCA', ['5mC', '6mA']),
+                                   ('ACGTZYX', 'ACGTCAC', ['5mC', '6mA', '5hmC'])]:
+        rng = np.random.RandomState(11)
+        refs = [rng.randint(0, len(alpha), size=200 + 13 * i).astype(np.int16) for i in range(7)]
+        info = AlphabetInfo(alpha, collapse, names)
+        reads = [SignalMapping(np.zeros(4, 'i2'), np.arange(len(r) + 1), r) for r in refs]
+        np.testing.assert_array_equal(info.compute_log_odds_weights(reads, 100), gold[alpha + '_log_odds'])
+        np.testing.assert_array_equal(info.compute_mod_inv_freq_weights([{'Reference': r} for r in refs], 100),
+                                      gold[alpha + '_inv_freq'])
+        # a sample smaller than the read set is a draw without replacement from it
+        np.random.seed(3)
+        w = info.compute_log_odds_weights(reads, 3)
+        assert w.shape == (len(alpha),) and np.isfinite(w).all()
+    # a label that never occurs has no ratio: same refusal as the reference
+    info = AlphabetInfo('ACGTZ', 'ACGTC', ['5mC'])
+    with pytest.raises(NotImplementedError):
+        info.compute_log_odds_weights([{'Reference': np.array([0, 1, 2, 3], 'i2')}], 10)
 
 
 def test_bench_reference_arm_prints_contract_line():
