@@ -133,6 +133,21 @@ def test_sharpening_and_scaling(dev):
         np.testing.assert_allclose(g1, g64, rtol=1e-4, atol=5e-6 / 120)
 
 
+@pytest.mark.parametrize('fused', [True, False])
+def test_cat_mod_prior_weights_with_zero_entries(dev, fused, monkeypatch):
+    """Category weights as --mod_prior_factor produces them (alphabet.py:68-100): 0 for a canonical
+    base without modifications, odds around 1 for C and 5mC."""
+    import sys
+    weights = np.array([0.0, 1.0157232, 0.98452014, 0.0, 0.0], dtype=np.float32)
+    monkeypatch.setattr(sys.modules[__name__], 'WEIGHTS', weights)
+    scores, seqs, seqlen, mod_cats = _inputs(90, 6, True, seed=17)
+    c1, g1, p1 = _run(dev, scores, seqs, seqlen, mod_cats, 1.0, fused=fused)
+    assert p1 == (FUSED if fused else TWO_KERNEL)
+    c64, g64 = _oracle(scores, seqs, seqlen, mod_cats, 1.0)
+    np.testing.assert_allclose(c1, c64, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(g1, g64, rtol=1e-4, atol=5e-6 / 90)
+
+
 def test_long_chunks_take_the_two_kernel_path(dev):
     """Rows that do not fit in shared memory next to the ring (from about 1100 positions on) keep
     the spill + posterior kernel pair."""

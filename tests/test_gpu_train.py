@@ -174,6 +174,27 @@ def test_entry_point_with_cuda_graphs(dev, tmp_path):
     assert np.isfinite(last) and last < first
 
 
+def test_entry_point_with_mod_prior_factor(dev, tmp_path):
+    """Cat-mod model with --mod_prior_factor (train_flipflop.py:312-326): the prior odds of the
+    reads are logged and weigh the category terms of the loss; canonical bases without a
+    modification get weight 0, as in the reference."""
+    out = tmp_path / 'training'
+    cmd = [sys.executable, os.path.join(ROOT, 'bin', 'train_flipflop.py'), '--size', '64',
+           '--niteration', '40', '--warmup_batches', '10', '--chunk_len_min', '500',
+           '--chunk_len_max', '800', '--min_sub_batch_size', '16', '--seed', '3', '--stride', '2',
+           '--mod_prior_factor', '0.5', '--num_mod_weight_reads', '8',
+           '--quiet', '--overwrite', '--outdir', str(out),
+           os.path.join(ROOT, 'models', 'mGru_cat_mod_flipflop.py'), 'synthetic:12:5mC']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    log = (out / 'model.log').read_text()
+    assert 'Computed modbase log odds priors' in log and 'Applied mod_prior_factor' in log
+    batch = (out / 'batch.log').read_text().strip().splitlines()
+    assert len(batch) == 41
+    losses = [float(line.split('\t')[1]) for line in batch[1:]]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
 def test_train_flipflop_entry_point_all_default_flags(dev, tmp_path):
     """Every flag at its default (size 384, bin/_bin_argparse.py:16; chunk lengths 3000-8000 in
     sub-batches of 128): the round-1 library refused size 384.  Only the number of iterations is
