@@ -138,7 +138,7 @@ class RefTrainer:
         lossvec = lossvec + log_partition_flipflop(out).squeeze(1) / nblk
         loss = lossvec.mean()
         loss.backward()
-        fval = float(loss)
+        fval = float(loss.detach())
         _ = [float(torch.max(torch.abs(p.grad))) for p in self.net.parameters()
              if p.requires_grad and p.grad is not None]
         self.opt.step()
