@@ -6,10 +6,11 @@ weights, Viterbi, stitching).
 
     basecall.py [flags] input_folder model.checkpoint > calls.fa
 
-fast5 reading (ont_fast5_api) is not in this image and out of this path's scope:
-`input_folder` holds one `<read_id>.npy` per read (1-D array of current in pA, or
-raw DACs if --scaling gives shift / scale for the read), or is a single `.npz`
-whose keys are read ids.  One process drives the GPU; instead of a pool of
+`input_folder` is a directory of fast5 files (single- or multi-read, or one such file) as in
+the reference -- decoded by taiyaki_b200/fast5utils.py, this image has no ont_fast5_api -- whose
+reads are called from their current in pA (Signal(read).current, bin/basecall.py:92-116); or it
+holds one `<read_id>.npy` per read (1-D array of current in pA, or raw DACs if --scaling
+gives shift / scale for the read), or is a single `.npz` whose keys are read ids.  One process drives the GPU; instead of a pool of
 worker processes (--jobs), chunks of several reads share each batch
 (--reads_per_batch).  Beam search (--beam) is not supported.
 """
@@ -24,9 +25,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from taiyaki_b200 import basecall, basecall_helpers, helpers  # noqa: E402
+from taiyaki_b200 import basecall, basecall_helpers, fast5utils, helpers  # noqa: E402
 from taiyaki_b200.flipflopfings import nstate_flipflop  # noqa: E402
 from taiyaki_b200.prepare_mapping_funcs import get_per_read_params_dict_from_tsv  # noqa: E402
+from taiyaki_b200.signal import Signal  # noqa: E402
 
 
 def auto_bool(v):
@@ -66,13 +68,39 @@ def get_parser():
     p.add_argument('--scaling', default=None, help='Path to TSV containing per-read scaling params')
     p.add_argument('--temperature', default=1.0, type=float,
                    help='Scaling factor applied to network outputs before decoding')
-    p.add_argument('input_folder', help='Directory of <read_id>.npy signals, or one .npz')
+    p.add_argument('--recursive', default=True, type=auto_bool, nargs='?', const=True,
+                   help='Search for fast5s recursively within input_folder')
+    p.add_argument('input_folder', help='Directory containing single or multi-read fast5 files '
+                                        '(or <read_id>.npy signals, or one .npz)')
     p.add_argument('model', help='Model checkpoint file to use for basecalling')
     return p
 
 
-def iterate_signals(input_folder, limit=None, strand_list=None):
-    """Yield (read_id, signal) from a folder of .npy files or one .npz."""
+def get_signal(read_filename, read_id):
+    """Current in pA of one read of a fast5 file, None when it cannot be read
+    (bin/basecall.py:92-116)."""
+    try:
+        with fast5utils.get_fast5_file(read_filename, 'r') as f5file:
+            return Signal(f5file.get_read(read_id)).current
+    except Exception as e:
+        sys.stderr.write('Unable to obtain signal for {} from {}.\n{}\n'.format(
+            read_id, read_filename, repr(e)))
+        return None
+
+
+def _is_array_input(input_folder):
+    if os.path.isfile(input_folder):
+        return input_folder.endswith('.npz')
+    return any(fn.endswith('.npy') for fn in os.listdir(input_folder))
+
+
+def iterate_signals(input_folder, limit=None, strand_list=None, recursive=True):
+    """Yield (read_id, signal) from fast5 files, a folder of .npy files or one .npz."""
+    if not _is_array_input(input_folder):
+        for filename, read_id in fast5utils.iterate_fast5_reads(
+                input_folder, limit=limit, strand_list=strand_list, recursive=recursive):
+            yield read_id, get_signal(filename, read_id)
+        return
     keep = None
     if strand_list is not None:
         with open(strand_list) as fh:
@@ -145,7 +173,7 @@ def main(argv=None):
             nsample += read_nsample
 
     pending = []
-    for rec in iterate_signals(args.input_folder, args.limit, args.input_strand_list):
+    for rec in iterate_signals(args.input_folder, args.limit, args.input_strand_list, args.recursive):
         if args.scaling is not None and rec[0] not in all_read_params:
             continue
         pending.append(rec)

@@ -7,8 +7,10 @@ launch per group of reads, csrc/remap.cu).
     prepare_mapped_reads.py [flags] input_folder per_read_params.tsv output.hdf5 \\
         model.checkpoint references.fasta
 
-fast5 reading is not in this image and out of this path's scope: `input_folder` holds one
-`<read_id>.npz` per read with `dacs` (raw int16 samples), `offset`, `range`, `digitisation`.
+`input_folder` is a directory of fast5 files, single- or multi-read, as in the reference
+(decoded by taiyaki_b200/fast5utils.py over the package's plain-Python HDF5 reader -- this image
+has no ont_fast5_api / h5py), or a directory with one `<read_id>.npz` per read holding `dacs`
+(raw int16 samples), `offset`, `range`, `digitisation`.
 One process drives the GPU; --jobs is replaced by --reads_per_batch (reads aligned per
 launch).  The output is the batched mapped-signal format (read back by
 bin/train_flipflop.py).
@@ -23,7 +25,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from taiyaki_b200 import alphabet, helpers  # noqa: E402
+from taiyaki_b200 import alphabet, fast5utils, helpers  # noqa: E402
+from taiyaki_b200.signal import Signal  # noqa: E402
 from taiyaki_b200.prepare_mapping_funcs import (  # noqa: E402
     fasta_file_to_dict, generate_output_from_results, get_per_read_params_dict_from_tsv,
     remap_reads)
@@ -46,7 +49,11 @@ def get_parser():
                    help="Don't attempt remapping for reads longer than this")
     p.add_argument('--mod', nargs=3, metavar=('mod_base', 'canonical_base', 'mod_long_name'),
                    default=[], action='append', help='Modified base description')
-    p.add_argument('input_folder', help='Directory of <read_id>.npz raw reads')
+    p.add_argument('--recursive', default=True, nargs='?', const=True,
+                   type=lambda v: str(v).lower() in ('1', 'true', 'yes', 'on'),
+                   help='Search for fast5s recursively within input_folder')
+    p.add_argument('input_folder', help='Directory containing single or multi-read fast5 files '
+                                        '(or <read_id>.npz raw reads)')
     p.add_argument('input_per_read_params', help='Input per read parameter .tsv file')
     p.add_argument('output', help='Output HDF5 file')
     p.add_argument('model', help='Taiyaki model file')
@@ -71,7 +78,7 @@ def make_alphabet_info(canonical, mods):
                                  [elt[2] for elt in mods], do_reorder=True)
 
 
-def iterate_raw_reads(input_folder, limit=None, strand_list=None):
+def iterate_npz_reads(input_folder, limit=None, strand_list=None):
     keep = None
     if strand_list is not None:
         with open(strand_list) as fh:
@@ -93,6 +100,33 @@ def iterate_raw_reads(input_folder, limit=None, strand_list=None):
                    'range': float(z['range']), 'digitisation': float(z['digitisation'])}
 
 
+def iterate_fast5_reads(input_folder, limit=None, strand_list=None, recursive=True, wanted=None):
+    """Raw reads of the fast5 files below `input_folder` (fast5utils.iterate_fast5_reads: strand
+    list, limit) as the dictionaries remap_reads takes.  `wanted(read_id)` False skips loading the
+    samples of a read that will be rejected anyway; a read whose samples cannot be loaded is
+    passed on with dacs None and reported as READ_ID_INFO_NOT_FOUND
+    (prepare_mapping_funcs.py:62-68)."""
+    for filename, read_id in fast5utils.iterate_fast5_reads(
+            input_folder, limit=limit, strand_list=strand_list, recursive=recursive):
+        read = {'read_id': read_id, 'dacs': None, 'offset': 0.0, 'range': 1.0, 'digitisation': 1.0}
+        if wanted is None or wanted(read_id):
+            try:
+                with fast5utils.get_fast5_file(filename, 'r') as f5file:
+                    sig = Signal(f5file.get_read(read_id))
+                read.update(dacs=sig.untrimmed_dacs, offset=float(sig.offset), range=float(sig.range),
+                            digitisation=float(sig.digitisation))
+            except Exception as e:
+                sys.stderr.write('Unable to obtain signal for {} from {}.\n{}\n'.format(
+                    read_id, filename, repr(e)))
+        yield read
+
+
+def iterate_raw_reads(input_folder, limit=None, strand_list=None, recursive=True, wanted=None):
+    if os.path.isdir(input_folder) and any(fn.endswith('.npz') for fn in os.listdir(input_folder)):
+        return iterate_npz_reads(input_folder, limit, strand_list)
+    return iterate_fast5_reads(input_folder, limit, strand_list, recursive, wanted)
+
+
 def main(argv=None):
     args = get_parser().parse_args(argv)
     print('Running prepare_mapping using flip-flop remapping')
@@ -111,7 +145,10 @@ def main(argv=None):
 
     def results():
         pending = []
-        for read in iterate_raw_reads(args.input_folder, args.limit, args.input_strand_list):
+        def wanted(read_id):      # signals of reads without reference or parameters are not loaded
+            return read_id in references and read_id in per_read_params_dict
+        for read in iterate_raw_reads(args.input_folder, args.limit, args.input_strand_list,
+                                      args.recursive, wanted):
             read['ref'] = references.get(read['read_id'])
             pending.append(read)
             if len(pending) >= args.reads_per_batch:

@@ -62,6 +62,8 @@ class Writer:
             return struct.pack('<BBBBIHHBBBBI', 0x11, 0x20, 0x3f, 0, 8, 0, 64, 52, 11, 0, 52, 1023)
         if dt.kind == 'f' and dt.itemsize == 4:
             return struct.pack('<BBBBIHHBBBBI', 0x11, 0x20, 0x1f, 0, 4, 0, 32, 23, 8, 0, 23, 127)
+        if dt.kind == 'S':                                             # fixed-length, null-padded ASCII
+            return struct.pack('<BBBBI', 0x13, 0x01, 0, 0, dt.itemsize)
         raise ValueError(dtype)
 
     def vlen_refs(self, values):

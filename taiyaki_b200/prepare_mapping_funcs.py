@@ -1,7 +1,7 @@
 """Remapping reads to their references with a flip-flop model -- the flow of
 taiyaki/prepare_mapping_funcs.py:24-109 (`oneread_remap`) behind bin/prepare_mapped_reads.py,
-for raw signals passed in (fast5 reading is out of scope): trim and standardise with the
-per-read parameters, run the network over the whole read, align the reference to the
+for raw signals passed in (bin/prepare_mapped_reads.py reads them from fast5 files through
+fast5utils / signal.Signal): trim and standardise with the per-read parameters, run the network over the whole read, align the reference to the
 transition scores (csrc/remap.cu), turn the block path into Ref_to_signal.
 
 `remap_reads` does this for a list of reads with ONE remapping launch for all of them (one
@@ -93,8 +93,8 @@ def trim_bounds(nsample, trim_start, trim_end):
 
 def remap_reads(reads, model, per_read_params_dict, alphabet_info, max_read_length=None,
                 localpen=0.0, model_stride=None):
-    """`reads`: list of dicts with read_id, dacs (untrimmed int16), offset, range,
-    digitisation and ref (reference string, possibly with modified bases, or None).
+    """`reads`: list of dicts with read_id, dacs (untrimmed int16; None when the read could not be
+    loaded), offset, range, digitisation and ref (reference string, possibly with modified bases, or None).
     Returns [(read dictionary or None, RemapResult)] in the same order -- what
     `oneread_remap` returns per read."""
     device = helpers.get_model_device(model)
@@ -114,6 +114,9 @@ def remap_reads(reads, model, per_read_params_dict, alphabet_info, max_read_leng
             params = per_read_params_dict.get(read['read_id'])
             if params is None:
                 results[i] = (None, RemapResult.NO_PARAMS)
+                continue
+            if read.get('dacs') is None:          # the file did not yield this read's signal
+                results[i] = (None, RemapResult.READ_ID_INFO_NOT_FOUND)
                 continue
             dacs = np.asarray(read['dacs'])
             start, end = trim_bounds(len(dacs), int(params['trim_start']), int(params['trim_end']))

@@ -540,6 +540,122 @@ def make_remap():
           {t: (float(out[t + '_score']), int((out[t + '_path'] == -1).sum())) for t in cases})
 
 
+def make_prepare():
+    """The reference's data-preparation flow on its own raw-read fixtures -> tests/golden/prepare_remap.npz.
+
+    Inputs (all from /root/reference): the five single-read fast5 files of test/data/reads
+    (decoded with taiyaki_b200/hdf5_min.py -- no h5py / ont_fast5_api here; pinned below against
+    what the reference itself stored from the same files), test/data/readparams.tsv,
+    test/data/per_read_references.fasta and the shipped remapping model
+    models/mGru_flipflop_remapping_model_r9_DNA.checkpoint (mGru_flipflop, size 96, stride 4).
+
+    Computed with the REFERENCE's code on the CPU in fp32: signal.Signal (trim, DAC -> pA,
+    standardise), the network (the reference's taiyaki.layers classes; parameters rounded to
+    bf16 first, on both sides, as in make_trained), flipflop_remap.flipflop_remap and
+    SignalMapping.from_remapping_path / get_read_dictionary -- the body of
+    prepare_mapping_funcs.oneread_remap (:25-116), whose import needs ont_fast5_api (stubbed:
+    only its names are imported, the stub is never called).
+
+    Pins: (1) Dacs, Reference and the five scalars of the three reads in
+    test/data/mapped_signal_file/mapped_remap_samref.hdf5 -- written by the reference through
+    ont_fast5_api + h5py from these fast5 files -- equal what is stored here (that file's
+    Ref_to_signal came from another, stride-2, model and is not comparable); (2) the multi-read
+    file test/data/multireads holds the same samples; (3) shift / scale of readparams.tsv are
+    reproduced bit for bit by med_mad of Signal(read).current (bin/generate_per_read_params.py:
+    the UNTRIMMED current)."""
+    import types
+    import warnings
+    for m in ('ont_fast5_api', 'ont_fast5_api.conversion_tools', 'ont_fast5_api.fast5_interface',
+              'ont_fast5_api.conversion_tools.conversion_utils'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['ont_fast5_api.conversion_tools.conversion_utils'].get_fast5_file_list = None
+    sys.modules['ont_fast5_api.fast5_interface'].get_fast5_file = None
+    from taiyaki import flipflop_remap as ref_remap
+    from taiyaki import signal as ref_signal
+    from taiyaki import signal_mapping as ref_sm
+    from taiyaki.maths import med_mad as ref_med_mad
+    from taiyaki_b200 import hdf5_min, mapped_signal_files
+    from taiyaki_b200.helpers import _legacy_rnn_pickles
+    src = open(os.path.join(REF, 'taiyaki/flipflop_remap.py')).read()       # numpy 2 shim, see make_remap
+    exec(compile(src.replace('m -= move', 'm -= int(move)'), 'flipflop_remap.py', 'exec'), ref_remap.__dict__)
+    data = os.path.join(REF, 'test/data')
+    with _legacy_rnn_pickles(), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        net = torch.load(os.path.join(REF, 'models/mGru_flipflop_remapping_model_r9_DNA.checkpoint'),
+                         map_location='cpu', weights_only=False)
+    assert type(net).__module__ == 'taiyaki.layers'
+    net.eval()
+    out = {}
+    with torch.no_grad():
+        for name, p in net.state_dict().items():
+            r = p.detach().to(torch.bfloat16)
+            p.copy_(r.float())
+            out['param_' + name] = r.view(torch.int16).numpy().view(np.uint16)
+    stride = int(net.sublayers[0].stride)
+    out['model_cfg'] = np.array([net.sublayers[0].size, stride, net.sublayers[0].winlen])
+    params = {}
+    for line in open(os.path.join(data, 'readparams.tsv')).read().strip().splitlines()[1:]:
+        uuid, t0, t1, shift, scale = line.split('\t')
+        params[uuid] = {'trim_start': int(t0), 'trim_end': int(t1), 'shift': float(shift), 'scale': float(scale)}
+    refs, name = {}, None
+    for line in open(os.path.join(data, 'per_read_references.fasta')):
+        if line.startswith('>'):
+            name = line[1:].split()[0]
+            refs[name] = ''
+        elif name is not None:
+            refs[name] += line.strip()
+    stored = {}
+    with mapped_signal_files.HDF5Reader(os.path.join(data, 'mapped_signal_file/mapped_remap_samref.hdf5')) as msr:
+        for r in msr.reads():
+            stored[r.read_id] = r
+    multi = hdf5_min.File(os.path.join(data, 'multireads/FAK40126_2fd3b110ca0d020049836a61f0dfb2b9983808f9_0.fast5'))
+    ids = []
+    for fn in sorted(os.listdir(os.path.join(data, 'reads'))):
+        f = hdf5_min.File(os.path.join(data, 'reads', fn))
+        group = sorted(f['Raw/Reads'].keys())[-1]
+        attrs = f['Raw/Reads/' + group].attrs
+        rid = attrs['read_id'].decode()
+        assert fn == rid + '.fast5'
+        dacs = f['Raw/Reads/' + group + '/Signal'].read()
+        channel = f['UniqueGlobalKey/channel_id'].attrs
+        np.testing.assert_array_equal(dacs, multi['read_' + rid + '/Raw/Signal'].read())
+        ids.append(rid)
+        out[rid + '_dacs'] = dacs
+        out[rid + '_read_group'] = np.array(group)
+        out[rid + '_channel'] = np.array([channel[k] for k in ('offset', 'range', 'digitisation', 'sampling_rate')])
+        out[rid + '_read_attrs'] = np.array([int(attrs[k]) for k in ('start_time', 'duration', 'read_number', 'start_mux')])
+        p = params[rid]
+        out[rid + '_params'] = np.array([p['trim_start'], p['trim_end'], p['shift'], p['scale']])
+        info = {k: float(channel[k]) for k in ('offset', 'range', 'digitisation', 'sampling_rate')}
+        whole = ref_signal.Signal(dacs=dacs, channel_info=info, read_id=rid)
+        assert tuple(ref_med_mad(whole.current)) == (p['shift'], p['scale']), rid
+        if rid not in refs:
+            continue
+        sig = ref_signal.Signal(dacs=dacs, channel_info=info, read_id=rid, read_params=p)
+        x = torch.tensor(sig.standardized_current[:, None, None].astype(np.float32))
+        with torch.no_grad():
+            trans = net(x).numpy()
+        score, path = ref_remap.flipflop_remap(np.squeeze(trans).astype('f8'), refs[rid], alphabet='ACGT',
+                                               localpen=0.0)
+        int_ref = ref_sm.SignalMapping.get_integer_reference(refs[rid], 'ACGT')
+        d = ref_sm.SignalMapping.from_remapping_path(path, int_ref, stride, sig).get_read_dictionary()
+        g = stored[rid]
+        np.testing.assert_array_equal(d['Dacs'], g.Dacs)
+        np.testing.assert_array_equal(d['Reference'], g.Reference)
+        assert [d[k] for k in ('shift_frompA', 'scale_frompA', 'range', 'offset', 'digitisation')] == [
+            g.shift_frompA, g.scale_frompA, g.range, g.offset, g.digitisation]
+        out[rid + '_reference'] = np.array(refs[rid])
+        out[rid + '_Ref_to_signal'] = np.asarray(d['Ref_to_signal'], dtype=np.int32)
+        out[rid + '_Reference'] = np.asarray(d['Reference'], dtype=np.int16)
+        out[rid + '_remap_score'] = np.float64(score)
+        out[rid + '_path'] = path.astype(np.int32)
+    out['read_ids'] = np.array(ids)
+    np.savez_compressed(os.path.join(HERE, 'prepare_remap.npz'), **out)
+    print('prepare_remap.npz', os.path.getsize(os.path.join(HERE, 'prepare_remap.npz')), 'bytes;',
+          {r[:8]: (len(out[r + '_dacs']), float(out[r + '_remap_score']) if r + '_remap_score' in out else None)
+           for r in ids})
+
+
 MOD_WEIGHT_ALPHABETS = [('ACGTZ', 'ACGTC', ['5mC']), ('ACGTZY', 'ACGTCA', ['5mC', '6mA']),
                         ('ACGTZYX', 'ACGTCAC', ['5mC', '6mA', '5hmC'])]
 
@@ -580,6 +696,8 @@ if __name__ == '__main__':
         make_trained()
     elif sys.argv[1:] == ['mod_weights']:
         make_mod_weights()
+    elif sys.argv[1:] == ['prepare']:
+        make_prepare()
     else:
         if sys.argv[1:] != ['decode']:
             main()
@@ -589,3 +707,4 @@ if __name__ == '__main__':
             make_real()
             make_remap()
             make_mod_weights()
+            make_prepare()

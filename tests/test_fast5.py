@@ -1,0 +1,359 @@
+"""Raw reads from fast5 files into the data-preparation callers (the input
+side of bin/prepare_mapped_reads.py; bin/generate_per_read_params.py; bin/basecall.py).
+
+tests/golden/prepare_remap.npz (make_golden.py prepare) holds the five reads of the
+reference's test/data/reads, its per-read parameter table, its references, its shipped
+remapping model (bf16-rounded) and the mappings the REFERENCE's own code produces from them
+on the CPU in fp32.  The generator pins the decoded samples against a file the reference
+wrote from the same fast5 files through ont_fast5_api + h5py.
+
+CPU, build container only (reference tree present): the nine cases of the reference's
+test/unit/test_iterate_fast5_reads.py on its own fixture files, samples and parameter table.
+CPU, anywhere: the same reads as fast5 files written by tests/fast5_fixture.py.
+GPU: bin/prepare_mapped_reads.py and bin/basecall.py from fast5 input with the shipped
+remapping model, against the reference's mappings / reference sequences."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+import fast5_fixture  # noqa: E402
+
+REF_DATA = '/root/reference/test/data'
+needs_ref_files = pytest.mark.skipif(not os.path.isdir(REF_DATA),
+                                     reason='the reference tree is only in the build container')
+EXPECTED_READ_IDS = [
+    '0f776a08-1101-41d4-8097-89136494a46e', '1f1a0f33-e2ac-431a-8f48-c3c687a7a7dc',
+    'b7096acd-b528-474e-a863-51295d18d3de', 'db6b45aa-5d21-45cf-a435-05fb8f12e839',
+    'de1508c4-755b-489e-9ffb-51af35c9a7e6']
+MAPPED = [EXPECTED_READ_IDS[0], EXPECTED_READ_IDS[3], EXPECTED_READ_IDS[4]]     # reads with a reference
+
+
+@pytest.fixture(scope='module')
+def g():
+    return fast5_fixture.golden()
+
+
+def _load_cli(name):
+    import importlib
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    return importlib.import_module(name)
+
+
+def _ids(found):
+    return sorted(rid for _, rid in found)
+
+
+# ---------------------------------------------------------------- the reference's own files
+@needs_ref_files
+@pytest.mark.parametrize('folder,strand_list', [
+    ('multireads', None), ('reads', None),
+    ('multireads', 'basecaller_output/sequencing_summary.txt'),
+    ('reads', 'strand_lists/strand_list_single.txt'),
+    ('multireads', 'strand_lists/strand_list.txt'),
+    ('multireads', 'strand_lists/strand_list_no_filename.txt'),
+    ('reads', 'strand_lists/strand_list_no_filename.txt'),
+    ('multireads', 'strand_lists/strand_list_no_read_id.txt')])
+def test_iterate_fast5_reads_on_reference_fixtures(folder, strand_list):
+    """test/unit/test_iterate_fast5_reads.py:32-82, case by case."""
+    from taiyaki_b200.fast5utils import iterate_fast5_reads
+    sl = None if strand_list is None else os.path.join(REF_DATA, strand_list)
+    assert _ids(iterate_fast5_reads(os.path.join(REF_DATA, folder), strand_list=sl)) == EXPECTED_READ_IDS
+
+
+@needs_ref_files
+def test_strand_list_without_header_is_refused():
+    """test_iterate_fast5_reads.py:84-92."""
+    from taiyaki_b200.fast5utils import iterate_fast5_reads
+    with pytest.raises(Exception):
+        list(iterate_fast5_reads(os.path.join(REF_DATA, 'multireads'), strand_list=os.path.join(
+            REF_DATA, 'strand_lists/invalid_strand_list_no_header.txt')))
+
+
+@needs_ref_files
+@pytest.mark.parametrize('folder', ['reads', 'multireads'])
+def test_reference_fast5_files_decode_to_the_golden_reads(g, folder):
+    from taiyaki_b200 import fast5utils
+    from taiyaki_b200.signal import Signal
+    n = 0
+    for filename, rid in fast5utils.iterate_fast5_reads(os.path.join(REF_DATA, folder)):
+        with fast5utils.get_fast5_file(filename) as f5:
+            assert f5.file_type == ('single-read' if folder == 'reads' else 'multi-read')
+            read = f5.get_read(rid)
+            sig = Signal(read)
+            attrs = fast5utils.get_read_attributes(read)
+            assert attrs['read_id'].decode() == rid and int(attrs['duration']) == len(sig.untrimmed_dacs)
+            if folder == 'reads':       # context tag of the run (multi-read files of this set lack it)
+                assert fast5utils.get_filename(read).decode().startswith('minicol615_20190207')
+        np.testing.assert_array_equal(sig.untrimmed_dacs, g[rid + '_dacs'])
+        assert [sig.offset, sig.range, sig.digitisation, sig.sample_rate] == list(g[rid + '_channel'])
+        n += 1
+    assert n == 5
+
+
+@needs_ref_files
+def test_generate_per_read_params_reproduces_the_reference_table(tmp_path, capsys):
+    """bin/generate_per_read_params.py on test/data/reads gives test/data/readparams.tsv, the
+    table the reference's acceptance test feeds to prepare_mapped_reads.py, to the last digit."""
+    cli = _load_cli('generate_per_read_params')
+    out = tmp_path / 'params.tsv'
+    assert cli.main(['--output', str(out), os.path.join(REF_DATA, 'reads')]) == 5
+    want = open(os.path.join(REF_DATA, 'readparams.tsv')).read().strip().splitlines()
+    got = out.read_text().strip().splitlines()
+    assert got[0] == want[0] and sorted(got[1:]) == sorted(want[1:])
+    with pytest.raises(SystemExit):                     # existing output is not overwritten
+        cli.main(['--output', str(out), os.path.join(REF_DATA, 'reads')])
+
+
+# ---------------------------------------------------------------- the same reads, written here
+@pytest.mark.parametrize('multi', [False, True])
+def test_written_fast5_files_round_trip(g, tmp_path, multi):
+    from taiyaki_b200 import fast5utils, maths
+    from taiyaki_b200.signal import Signal
+    reads_dir, _, _ = fast5_fixture.write_inputs(tmp_path, g, multi)
+    found = list(fast5utils.iterate_fast5_reads(reads_dir))
+    assert _ids(found) == EXPECTED_READ_IDS
+    for filename, rid in found:
+        with fast5utils.get_fast5_file(filename) as f5:
+            assert f5.file_type == ('multi-read' if multi else 'single-read')
+            assert rid in f5.get_read_ids()
+            read = f5.get_read(rid)
+            sig = Signal(read)
+            with pytest.raises(KeyError):
+                f5.get_read('not-a-read')
+        np.testing.assert_array_equal(sig.untrimmed_dacs, g[rid + '_dacs'])
+        assert sig.read_id == rid and sig.untrimmed_dacs.dtype == np.int16
+        # bin/generate_per_read_params.py: med_mad of the whole read's current
+        assert maths.med_mad(sig.current) == tuple(g[rid + '_params'][2:])
+    assert len(list(fast5utils.iterate_fast5_reads(reads_dir, limit=2))) == 2
+    one = found[0][0]
+    assert _ids(fast5utils.iterate_fast5_reads(one)) == (EXPECTED_READ_IDS if multi else [found[0][1]])
+
+
+def test_strand_lists_on_written_files(g, tmp_path):
+    """The three kinds of strand list (fast5utils.py:121-134) and the files they may name."""
+    from taiyaki_b200.fast5utils import iterate_fast5_reads
+    reads_dir, _, _ = fast5_fixture.write_inputs(tmp_path, g, multi=False)
+    a, b = EXPECTED_READ_IDS[0], EXPECTED_READ_IDS[3]
+
+    def strand_list(text):
+        p = tmp_path / 'strands.tsv'
+        p.write_text(text)
+        return str(p)
+    only_ids = strand_list('read_id\n{}\n{}\nmissing-read\n'.format(a, b))
+    assert _ids(iterate_fast5_reads(reads_dir, strand_list=only_ids)) == [a, b]
+    only_files = strand_list('filename\n{}.fast5\nabsent.fast5\n'.format(a))
+    assert _ids(iterate_fast5_reads(reads_dir, strand_list=only_files)) == [a]
+    pairs = strand_list('filename_fast5\tread_id\n{0}.fast5\t{0}\n{1}.fast5\t{0}\nabsent.fast5\t{1}\n'.format(a, b))
+    assert _ids(iterate_fast5_reads(reads_dir, strand_list=pairs)) == [a]     # wrong pairing, missing file
+    with pytest.raises(Exception):
+        list(iterate_fast5_reads(reads_dir, strand_list=strand_list('{}.fast5\t{}\n'.format(a, a))))
+
+
+def test_recursive_search_and_unreadable_files(g, tmp_path, capsys):
+    from taiyaki_b200.fast5utils import get_fast5_file_list, iterate_fast5_reads
+    reads_dir, _, _ = fast5_fixture.write_inputs(tmp_path, g, multi=False)
+    sub = os.path.join(reads_dir, 'batch1')
+    os.makedirs(sub)
+    moved = EXPECTED_READ_IDS[1] + '.fast5'
+    os.rename(os.path.join(reads_dir, moved), os.path.join(sub, moved))
+    with open(os.path.join(reads_dir, 'broken.fast5'), 'wb') as fh:
+        fh.write(b'this is not an HDF5 file')
+    assert len(get_fast5_file_list(reads_dir, recursive=False)) == 5        # 4 reads + the broken file
+    assert len(get_fast5_file_list(reads_dir, recursive=True)) == 6
+    assert _ids(iterate_fast5_reads(reads_dir, recursive=True)) == EXPECTED_READ_IDS
+    flat = _ids(iterate_fast5_reads(reads_dir, recursive=False))
+    assert flat == [r for r in EXPECTED_READ_IDS if r != EXPECTED_READ_IDS[1]]
+    assert 'skipped this read' in capsys.readouterr().err                   # the broken file is reported
+
+
+def test_signal_trimming_and_units(g):
+    """taiyaki/signal.py:77-123."""
+    from taiyaki_b200.signal import Signal
+    rid = EXPECTED_READ_IDS[0]
+    dacs = g[rid + '_dacs']
+    offset, rng, digitisation, rate = g[rid + '_channel']
+    info = {'offset': offset, 'range': rng, 'digitisation': digitisation, 'sampling_rate': rate}
+    t0, t1, shift, scale = g[rid + '_params']
+    params = {'trim_start': int(t0), 'trim_end': int(t1), 'shift': shift, 'scale': scale}
+    sig = Signal(dacs=dacs, channel_info=info, read_id=rid, read_params=params)
+    assert (sig.signalstart, sig.signalend_exc) == (200, len(dacs) - 50)
+    np.testing.assert_array_equal(sig.dacs, dacs[200:-50])
+    np.testing.assert_array_equal(sig.untrimmed_current, (dacs + offset) * rng / digitisation)
+    np.testing.assert_array_equal(sig.current, sig.untrimmed_current[200:-50])
+    np.testing.assert_array_equal(sig.standardized_current, (sig.current - shift) / scale)
+    sig.dacs[0] = 0                                     # a copy: the stored samples are untouched
+    assert sig.untrimmed_dacs[200] == dacs[200]
+    short = Signal(dacs=dacs[:250], channel_info=info, read_params=params)   # nothing would be left
+    assert (short.signalstart, short.signalend_exc) == (0, 250)
+    with pytest.raises(Exception):
+        Signal(dacs=dacs, channel_info=info, read_params=dict(params, trim_end=-1))
+    with pytest.raises(Exception):
+        Signal()
+    plain = Signal(dacs=np.arange(10))
+    np.testing.assert_array_equal(plain.standardized_current, np.arange(10))
+
+
+def test_generate_per_read_params_cli(g, tmp_path, capsys):
+    cli = _load_cli('generate_per_read_params')
+    reads_dir, tsv, _ = fast5_fixture.write_inputs(tmp_path, g, multi=True)
+    out = tmp_path / 'out.tsv'
+    assert cli.main(['--output', str(out), '--trim', '200', '50', reads_dir]) == 5
+    assert sorted(out.read_text().splitlines()) == sorted(open(tsv).read().splitlines())
+    assert cli.main(['--limit', '2', '--trim', '10', '0', reads_dir]) == 2
+    rows = capsys.readouterr().out.strip().splitlines()
+    assert rows[0].split('\t') == ['UUID', 'trim_start', 'trim_end', 'shift', 'scale']
+    assert [r.split('\t')[1:3] for r in rows[1:]] == [['10', '0']] * 2
+
+
+def test_prepare_cli_reads_fast5_input(g, tmp_path):
+    """bin/prepare_mapped_reads.py's read iteration on fast5 input: the dictionaries remap_reads
+    takes; samples of reads that will be rejected anyway are not loaded."""
+    cli = _load_cli('prepare_mapped_reads')
+    reads_dir, _, _ = fast5_fixture.write_inputs(tmp_path, g, multi=False)
+    raw = {r['read_id']: r for r in cli.iterate_raw_reads(reads_dir)}
+    assert sorted(raw) == EXPECTED_READ_IDS
+    for rid, r in raw.items():
+        np.testing.assert_array_equal(r['dacs'], g[rid + '_dacs'])
+        assert [r['offset'], r['range'], r['digitisation']] == list(g[rid + '_channel'][:3])
+    some = list(cli.iterate_raw_reads(reads_dir, wanted=lambda rid: rid in MAPPED))
+    assert sorted(r['read_id'] for r in some if r['dacs'] is not None) == MAPPED
+    assert len(some) == 5 and len(list(cli.iterate_raw_reads(reads_dir, limit=3))) == 3
+
+
+def test_basecall_cli_reads_fast5_input(g, tmp_path):
+    """bin/basecall.py's signal iteration on fast5 input: the read's current in pA
+    (bin/basecall.py:92-116), None for a read that cannot be loaded."""
+    cli = _load_cli('basecall')
+    reads_dir, _, _ = fast5_fixture.write_inputs(tmp_path, g, multi=True)
+    got = dict(cli.iterate_signals(reads_dir))
+    assert sorted(got) == EXPECTED_READ_IDS
+    for rid, current in got.items():
+        offset, rng, digitisation, _ = g[rid + '_channel']
+        np.testing.assert_array_equal(current, (g[rid + '_dacs'] + offset) * rng / digitisation)
+    assert cli.get_signal(os.path.join(reads_dir, 'batch_0.fast5'), 'not-a-read') is None
+
+
+def test_remap_reads_reports_unloadable_reads():
+    """A read whose samples could not be loaded is READ_ID_INFO_NOT_FOUND
+    (prepare_mapping_funcs.py:62-68) -- after the checks that need no samples, as in the
+    reference.  No device work is reached."""
+    from taiyaki_b200 import prepare_mapping_funcs as pmf
+    from taiyaki_b200.alphabet import AlphabetInfo
+
+    class NoModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+    reads = [{'read_id': 'a', 'dacs': None, 'ref': 'ACGT'}, {'read_id': 'b', 'dacs': None, 'ref': None},
+             {'read_id': 'c', 'dacs': None, 'ref': 'ACGT'}]
+    params = {'a': {'trim_start': 0, 'trim_end': 0, 'shift': 0.0, 'scale': 1.0}}
+    res = pmf.remap_reads(reads, NoModel(), params, AlphabetInfo('ACGT', 'ACGT'), model_stride=4)
+    assert [r[1] for r in res] == [pmf.RemapResult.READ_ID_INFO_NOT_FOUND, pmf.RemapResult.NO_REF_FOUND,
+                                   pmf.RemapResult.NO_PARAMS]
+
+
+# ---------------------------------------------------------------- GPU: the flows end to end
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from taiyaki_b200 import _lib
+    _lib.lib()
+    return torch.device('cuda:0')
+
+
+def remapping_model(g, dev):
+    """The reference's shipped mGru_flipflop remapping model (size 96, stride 4) from the golden
+    file's bf16-rounded parameters."""
+    from taiyaki_b200 import helpers
+    from taiyaki_b200.alphabet import AlphabetInfo
+    size, stride, winlen = (int(v) for v in g['model_cfg'])
+    model = helpers.load_model(os.path.join(ROOT, 'models', 'mGru_flipflop.py'),
+                               model_metadata={'reverse': False, 'standardize': True}, size=size,
+                               stride=stride, winlen=winlen, insize=1,
+                               alphabet_info=AlphabetInfo('ACGT', 'ACGT'))
+    state = {k[len('param_'):]: torch.from_numpy(g[k].view(np.int16).copy()).view(torch.bfloat16).float()
+             for k in g.files if k.startswith('param_')}
+    model.load_state_dict(state)
+    return model.to(dev)
+
+
+def _mapping_agreement(got, want, stride):
+    d = np.abs(np.asarray(got, dtype=np.int64) - np.asarray(want, dtype=np.int64))
+    return float((d == 0).mean()), float((d <= stride).mean()), int(d.max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision,multi', [('fp32', False), ('bf16', True)])
+def test_prepare_mapped_reads_from_fast5_matches_reference_flow(g, dev, tmp_path, precision, multi):
+    """The reference's acceptance flow (test/acceptance/test_prepare_remap.py: reads + parameter
+    table + references + remapping model -> mapped-signal file) from fast5 input, against the
+    mappings the reference's own code computes from the same inputs on the CPU in fp32
+    (make_golden.py prepare).  Samples, labels and scalars are exact.  Ref_to_signal goes through
+    the network: in the fp32 parity mode the scores differ from the CPU's by summation order only
+    and every boundary of the three reads is the same (B200, profiles/r2_fast5_prepare_gpu.log);
+    with bf16 products 0 to 0.7 % of the 2100 - 3100 boundaries per read move, by at most 24
+    samples (stride 4) -- alignment is a max over paths, near-ties flip."""
+    from taiyaki_b200 import helpers, layers, mapped_signal_files
+    cli = _load_cli('prepare_mapped_reads')
+    reads_dir, tsv, fasta = fast5_fixture.write_inputs(tmp_path, g, multi)
+    ckpt, _ = helpers.save_model(remapping_model(g, dev), str(tmp_path))
+    out = str(tmp_path / 'mapped.hdf5')
+    stride = int(g['model_cfg'][1])
+    layers.set_precision(precision)
+    try:
+        count, errs = cli.main(['--reads_per_batch', '2', reads_dir, tsv, out, ckpt, fasta])
+    finally:
+        layers.set_precision('bf16')
+    assert count == 3 and sum(errs.values()) == 2               # two reads have no reference
+    with mapped_signal_files.MappedSignalReader(out) as msr:
+        assert msr.check() == 'pass' and sorted(msr.get_read_ids()) == MAPPED
+        for read in msr.reads():
+            rid = read.read_id
+            np.testing.assert_array_equal(read.Dacs, g[rid + '_dacs'])
+            np.testing.assert_array_equal(read.Reference, g[rid + '_Reference'])
+            t0, t1, shift, scale = g[rid + '_params']
+            offset, rng, digitisation, _ = g[rid + '_channel']
+            assert [read.shift_frompA, read.scale_frompA, read.range, read.offset, read.digitisation] == [
+                shift, scale, rng, offset, digitisation]
+            same, near, worst = _mapping_agreement(read.Ref_to_signal, g[rid + '_Ref_to_signal'], stride)
+            print('%s %s: identical %.4f  within one block %.4f  max %d samples' % (precision, rid[:8], same, near, worst))
+            if precision == 'fp32':
+                assert same >= 0.999 and near >= 0.999, (same, near, worst)     # measured: 1.0000 on all three
+            else:
+                assert same >= 0.98 and near >= 0.99, (same, near, worst)       # measured: 0.9931 .. 1.0000
+            # what the reference's acceptance test checks: a chunk with a plausible dwell
+            chunk = read.get_chunk_with_sample_length(1000, start_sample=10000)
+            assert 7 < chunk.sig_len / (chunk.seq_len + 0.0001) < 13
+
+
+@pytest.mark.gpu
+def test_basecall_from_fast5_recovers_the_reference_sequences(g, dev, tmp_path):
+    """bin/basecall.py on fast5 input with the shipped remapping model and the reference's scaling
+    table: the calls of real reads agree with the reads' known reference sequences to the extent
+    a small r9 model does (well above 80 % of the reference found in the call)."""
+    import difflib
+    from taiyaki_b200 import helpers
+    cli = _load_cli('basecall')
+    reads_dir, tsv, _ = fast5_fixture.write_inputs(tmp_path, g, multi=True)
+    ckpt, _ = helpers.save_model(remapping_model(g, dev), str(tmp_path))
+    out = tmp_path / 'calls.fa'
+    cli.main(['--scaling', tsv, '--output', str(out), reads_dir, ckpt])
+    lines = out.read_text().strip().splitlines()
+    calls = {lines[i][1:]: lines[i + 1] for i in range(0, len(lines), 2)}
+    assert sorted(calls) == EXPECTED_READ_IDS
+    for rid in MAPPED:
+        ref, call = str(g[rid + '_reference']), calls[rid]
+        # the reference sequence may cover only part of the read (read 0f776a08 maps from sample
+        # 7917 of 28005), so the measure is the share of the REFERENCE found in the call
+        assert set(call) <= set('ACGT') and 0.8 * len(ref) < len(call) < 2.0 * len(ref), (len(ref), len(call))
+        blocks = difflib.SequenceMatcher(None, ref, call, autojunk=False).get_matching_blocks()
+        found = sum(b.size for b in blocks) / len(ref)
+        print('%s: reference %d bases, call %d bases, %.3f of the reference found in the call' % (
+            rid[:8], len(ref), len(call), found))
+        assert found > 0.8, found
