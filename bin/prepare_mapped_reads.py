@@ -11,9 +11,16 @@ launch per group of reads, csrc/remap.cu).
 (decoded by taiyaki_b200/fast5utils.py over the package's plain-Python HDF5 reader -- this image
 has no ont_fast5_api / h5py), or a directory with one `<read_id>.npz` per read holding `dacs`
 (raw int16 samples), `offset`, `range`, `digitisation`.
-One process drives the GPU; --jobs is replaced by --reads_per_batch (reads aligned per
+One process drives one GPU; --jobs is replaced by --reads_per_batch (reads aligned per
 launch).  The output is the batched mapped-signal format (read back by
 bin/train_flipflop.py).
+
+Several GPUs: reads are independent, so the job shards by read with no exchange between
+devices.  `torchrun --nproc-per-node G bin/prepare_mapped_reads.py ...` gives rank r the reads
+whose position in the input order is r modulo G on device cuda:LOCAL_RANK; each rank writes
+`<output>.shard<r>of<G>`, and after a barrier rank 0 joins the shards into `<output>` and
+removes them.  `--shard r G` does one share by hand (another node, another time) and leaves its
+file for misc/merge_mappedsignalfiles.py.
 """
 import argparse
 import os
@@ -49,6 +56,9 @@ def get_parser():
                    help="Don't attempt remapping for reads longer than this")
     p.add_argument('--mod', nargs=3, metavar=('mod_base', 'canonical_base', 'mod_long_name'),
                    default=[], action='append', help='Modified base description')
+    p.add_argument('--shard', nargs=2, type=int, default=None, metavar=('index', 'count'),
+                   help='Remap only the reads whose position in the input order is index modulo count, '
+                        'into <output>.shard<index>of<count> (set from RANK / WORLD_SIZE under torchrun)')
     p.add_argument('--recursive', default=True, nargs='?', const=True,
                    type=lambda v: str(v).lower() in ('1', 'true', 'yes', 'on'),
                    help='Search for fast5s recursively within input_folder')
@@ -78,7 +88,11 @@ def make_alphabet_info(canonical, mods):
                                  [elt[2] for elt in mods], do_reorder=True)
 
 
-def iterate_npz_reads(input_folder, limit=None, strand_list=None):
+def in_shard(index, shard):
+    return shard is None or index % shard[1] == shard[0]
+
+
+def iterate_npz_reads(input_folder, limit=None, strand_list=None, shard=None):
     keep = None
     if strand_list is not None:
         with open(strand_list) as fh:
@@ -95,19 +109,24 @@ def iterate_npz_reads(input_folder, limit=None, strand_list=None):
         if limit is not None and n >= limit:
             return
         n += 1
+        if not in_shard(n - 1, shard):
+            continue
         with np.load(os.path.join(input_folder, fn)) as z:
             yield {'read_id': read_id, 'dacs': z['dacs'], 'offset': float(z['offset']),
                    'range': float(z['range']), 'digitisation': float(z['digitisation'])}
 
 
-def iterate_fast5_reads(input_folder, limit=None, strand_list=None, recursive=True, wanted=None):
+def iterate_fast5_reads(input_folder, limit=None, strand_list=None, recursive=True, wanted=None,
+                        shard=None):
     """Raw reads of the fast5 files below `input_folder` (fast5utils.iterate_fast5_reads: strand
     list, limit) as the dictionaries remap_reads takes.  `wanted(read_id)` False skips loading the
     samples of a read that will be rejected anyway; a read whose samples cannot be loaded is
     passed on with dacs None and reported as READ_ID_INFO_NOT_FOUND
     (prepare_mapping_funcs.py:62-68)."""
-    for filename, read_id in fast5utils.iterate_fast5_reads(
-            input_folder, limit=limit, strand_list=strand_list, recursive=recursive):
+    for index, (filename, read_id) in enumerate(fast5utils.iterate_fast5_reads(
+            input_folder, limit=limit, strand_list=strand_list, recursive=recursive)):
+        if not in_shard(index, shard):
+            continue
         read = {'read_id': read_id, 'dacs': None, 'offset': 0.0, 'range': 1.0, 'digitisation': 1.0}
         if wanted is None or wanted(read_id):
             try:
@@ -121,34 +140,78 @@ def iterate_fast5_reads(input_folder, limit=None, strand_list=None, recursive=Tr
         yield read
 
 
-def iterate_raw_reads(input_folder, limit=None, strand_list=None, recursive=True, wanted=None):
+def iterate_raw_reads(input_folder, limit=None, strand_list=None, recursive=True, wanted=None,
+                      shard=None):
+    """`shard` = (index, count): only the reads at positions index modulo count of the (limited,
+    strand-list filtered) input order; the samples of the others are not loaded."""
     if os.path.isdir(input_folder) and any(fn.endswith('.npz') for fn in os.listdir(input_folder)):
-        return iterate_npz_reads(input_folder, limit, strand_list)
-    return iterate_fast5_reads(input_folder, limit, strand_list, recursive, wanted)
+        return iterate_npz_reads(input_folder, limit, strand_list, shard)
+    return iterate_fast5_reads(input_folder, limit, strand_list, recursive, wanted, shard)
+
+
+def shard_of_process(args, environ=os.environ):
+    """((index, count) or None, launched by torchrun?)."""
+    if args.shard is not None:
+        index, count = args.shard
+        if not 0 <= index < count:
+            raise SystemExit('--shard index count: need 0 <= index < count')
+        return ((index, count) if count > 1 else None), False
+    world = int(environ.get('WORLD_SIZE', '1'))
+    if world > 1:
+        return (int(environ['RANK']), world), True
+    return None, False
+
+
+def shard_filename(output, shard):
+    return '{}.shard{}of{}'.format(output, *shard)
+
+
+def join_shards(output, shard_files, alphabet_info):
+    """All reads of the shard files, in shard order, into `output`; the shard files are removed."""
+    from taiyaki_b200.mapped_signal_files import MappedSignalReader, MappedSignalWriter
+    count = 0
+    with MappedSignalWriter(output, alphabet_info) as msw:
+        for fn in shard_files:
+            with MappedSignalReader(fn) as msr:
+                for read in msr.reads():
+                    msw.write_read(read.get_read_dictionary())
+                    count += 1
+    for fn in shard_files:
+        os.remove(fn)
+    return count
 
 
 def main(argv=None):
     args = get_parser().parse_args(argv)
     print('Running prepare_mapping using flip-flop remapping')
-    if not args.overwrite and os.path.exists(args.output):
-        print('Cowardly refusing to overwrite {}'.format(args.output))
-        sys.exit(1)
+    shard, launched = shard_of_process(args)
+    output = args.output if shard is None else shard_filename(args.output, shard)
+    for fn in {args.output, output}:
+        if not args.overwrite and os.path.exists(fn):
+            print('Cowardly refusing to overwrite {}'.format(fn))
+            sys.exit(1)
     alphabet_info = make_alphabet_info(args.alphabet, args.mod)
     print('Converting references to labels using {}'.format(str(alphabet_info)))
     import torch
-    device = torch.device(args.device)
+    device = args.device
+    if launched and 'LOCAL_RANK' in os.environ and device == get_parser().get_default('device'):
+        device = 'cuda:{}'.format(os.environ['LOCAL_RANK'])         # one process per GPU
+    device = torch.device(device)
     torch.cuda.set_device(device)
+    if launched:
+        import torch.distributed as dist
+        dist.init_process_group('gloo')          # barriers only: no data crosses between the shards
     per_read_params_dict = get_per_read_params_dict_from_tsv(args.input_per_read_params)
     model = helpers.load_model(args.model).to(device)
     stride = helpers.guess_model_stride(model)
     references = fasta_file_to_dict(args.references)
 
     def results():
-        pending = []
         def wanted(read_id):      # signals of reads without reference or parameters are not loaded
             return read_id in references and read_id in per_read_params_dict
+        pending = []
         for read in iterate_raw_reads(args.input_folder, args.limit, args.input_strand_list,
-                                      args.recursive, wanted):
+                                      args.recursive, wanted, shard):
             read['ref'] = references.get(read['read_id'])
             pending.append(read)
             if len(pending) >= args.reads_per_batch:
@@ -159,7 +222,16 @@ def main(argv=None):
             yield from remap_reads(pending, model, per_read_params_dict, alphabet_info,
                                    args.max_read_length, args.localpen, stride)
 
-    return generate_output_from_results(results(), args.output, alphabet_info)
+    done = generate_output_from_results(results(), output, alphabet_info)
+    if launched:
+        dist.barrier()
+        if shard[0] == 0:
+            total = join_shards(args.output, [shard_filename(args.output, (r, shard[1]))
+                                              for r in range(shard[1])], alphabet_info)
+            sys.stderr.write('* {} reads from {} shards joined into {}\n'.format(total, shard[1], args.output))
+        dist.barrier()
+        dist.destroy_process_group()
+    return done
 
 
 if __name__ == '__main__':

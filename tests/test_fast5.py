@@ -239,6 +239,87 @@ def test_basecall_cli_reads_fast5_input(g, tmp_path):
     assert cli.get_signal(os.path.join(reads_dir, 'batch_0.fast5'), 'not-a-read') is None
 
 
+def test_prepare_cli_shards_reads_by_position(g, tmp_path):
+    """--shard index count / torchrun ranks: disjoint shares that together are the input order;
+    the samples of other shards' reads are not touched."""
+    import argparse
+    cli = _load_cli('prepare_mapped_reads')
+    reads_dir, _, _ = fast5_fixture.write_inputs(tmp_path, g, multi=True)
+    order = [r['read_id'] for r in cli.iterate_raw_reads(reads_dir)]
+    shares = [[r['read_id'] for r in cli.iterate_raw_reads(reads_dir, shard=(i, 3))] for i in range(3)]
+    assert shares == [order[0::3], order[1::3], order[2::3]]
+    assert [r['read_id'] for r in cli.iterate_raw_reads(reads_dir, limit=3, shard=(1, 2))] == order[1:3:2]
+    ns = argparse.Namespace
+    assert cli.shard_of_process(ns(shard=None), {}) == (None, False)
+    assert cli.shard_of_process(ns(shard=[1, 4]), {'WORLD_SIZE': '8', 'RANK': '5'}) == ((1, 4), False)
+    assert cli.shard_of_process(ns(shard=[0, 1]), {}) == (None, False)
+    assert cli.shard_of_process(ns(shard=None), {'WORLD_SIZE': '8', 'RANK': '5'}) == ((5, 8), True)
+    assert cli.shard_of_process(ns(shard=None), {'WORLD_SIZE': '1', 'RANK': '0'}) == (None, False)
+    with pytest.raises(SystemExit):
+        cli.shard_of_process(ns(shard=[2, 2]), {})
+    assert cli.shard_filename('out.hdf5', (2, 8)) == 'out.hdf5.shard2of8'
+
+
+def _prepare_rank(rank, world, port, workdir, failed):
+    """One torchrun-style rank of bin/prepare_mapped_reads.py on the CPU: the device work
+    (network + alignment) is replaced by a stand-in mapping, everything else -- sharding of the
+    input, per-shard file, barrier, join on rank 0 -- is the script's own."""
+    try:
+        os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                          LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+        import taiyaki_b200.helpers as helpers
+        from taiyaki_b200.prepare_mapping_funcs import RemapResult
+        from taiyaki_b200.signal_mapping import SignalMapping
+        cli = _load_cli('prepare_mapped_reads')
+
+        def fake_remap(reads, model, params, alphabet_info, max_read_length, localpen, stride):
+            out = []
+            for read in reads:
+                if read.get('ref') is None:
+                    out.append((None, RemapResult.NO_REF_FOUND))
+                    continue
+                labels = SignalMapping.get_integer_reference(read['ref'], alphabet_info.alphabet)
+                bounds = np.linspace(0, len(read['dacs']), len(labels) + 1).astype(np.int32)
+                p = params[read['read_id']]
+                out.append((SignalMapping(read['dacs'], bounds, labels, read_id=read['read_id'],
+                                          shift_frompA=p['shift'], scale_frompA=p['scale'], range=read['range'],
+                                          offset=read['offset'], digitisation=read['digitisation']
+                                          ).get_read_dictionary(), RemapResult.SUCCESS))
+            return out
+        cli.remap_reads = fake_remap
+        helpers.load_model = lambda *a, **k: type('NoModel', (), {'to': lambda self, device: self})()
+        helpers.guess_model_stride = lambda model: 4
+        torch.cuda.set_device = lambda device: None
+        cli.main([os.path.join(workdir, 'reads'), os.path.join(workdir, 'readparams.tsv'),
+                  os.path.join(workdir, 'mapped.hdf5'), 'unused.checkpoint', os.path.join(workdir, 'refs.fasta')])
+    except BaseException as e:                                     # noqa: B902 -- reported to the parent
+        failed[rank] = repr(e)
+        raise
+
+
+def test_prepare_cli_under_torchrun_gloo_world2(g, tmp_path):
+    """Two ranks: each remaps its share into <output>.shard<r>of2, rank 0 joins them after the
+    barrier and removes the shard files."""
+    import torch.multiprocessing as mp
+    from taiyaki_b200 import mapped_signal_files
+    fast5_fixture.write_inputs(tmp_path, g, multi=False)
+    ctx = mp.get_context('spawn')
+    failed = ctx.Manager().dict()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_prepare_rank, args=(r, 2, port, str(tmp_path), failed)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert [p.exitcode for p in procs] == [0, 0], dict(failed)
+    assert sorted(os.listdir(tmp_path)) == ['mapped.hdf5', 'readparams.tsv', 'reads', 'refs.fasta']
+    with mapped_signal_files.MappedSignalReader(str(tmp_path / 'mapped.hdf5')) as msr:
+        assert sorted(msr.get_read_ids()) == MAPPED and msr.check() == 'pass'
+        for read in msr.reads():
+            np.testing.assert_array_equal(read.Dacs, g[read.read_id + '_dacs'])
+            np.testing.assert_array_equal(read.Reference, g[read.read_id + '_Reference'])
+
+
 def test_remap_reads_reports_unloadable_reads():
     """A read whose samples could not be loaded is READ_ID_INFO_NOT_FOUND
     (prepare_mapping_funcs.py:62-68) -- after the checks that need no samples, as in the
@@ -330,6 +411,30 @@ def test_prepare_mapped_reads_from_fast5_matches_reference_flow(g, dev, tmp_path
             # what the reference's acceptance test checks: a chunk with a plausible dwell
             chunk = read.get_chunk_with_sample_length(1000, start_sample=10000)
             assert 7 < chunk.sig_len / (chunk.seq_len + 0.0001) < 13
+
+
+@pytest.mark.gpu
+def test_prepare_mapped_reads_shards_join_to_the_unsharded_result(g, dev, tmp_path):
+    """--shard 0 2 and --shard 1 2 joined by misc/merge_mappedsignalfiles.py hold the reads of one
+    unsharded run, with the same mappings (each read is remapped on its own)."""
+    from taiyaki_b200 import helpers, mapped_signal_files
+    cli = _load_cli('prepare_mapped_reads')
+    sys.path.insert(0, os.path.join(ROOT, 'misc'))
+    import importlib
+    merge = importlib.import_module('merge_mappedsignalfiles')
+    reads_dir, tsv, fasta = fast5_fixture.write_inputs(tmp_path, g, multi=False)
+    ckpt, _ = helpers.save_model(remapping_model(g, dev), str(tmp_path))
+    whole, out = str(tmp_path / 'whole.hdf5'), str(tmp_path / 'sharded.hdf5')
+    assert cli.main([reads_dir, tsv, whole, ckpt, fasta])[0] == 3
+    counts = [cli.main(['--shard', str(i), '2', reads_dir, tsv, out, ckpt, fasta])[0] for i in range(2)]
+    assert sum(counts) == 3 and min(counts) >= 1
+    shards = [cli.shard_filename(out, (i, 2)) for i in range(2)]
+    assert merge.main([out, '--input', shards[0], 'None', '--input', shards[1], 'None']) == 3
+    with mapped_signal_files.MappedSignalReader(whole) as a, mapped_signal_files.MappedSignalReader(out) as b:
+        assert sorted(a.get_read_ids()) == sorted(b.get_read_ids()) == MAPPED
+        for rid in MAPPED:
+            np.testing.assert_array_equal(a.get_read(rid).Ref_to_signal, b.get_read(rid).Ref_to_signal)
+            np.testing.assert_array_equal(a.get_read(rid).Dacs, b.get_read(rid).Dacs)
 
 
 @pytest.mark.gpu
