@@ -25,12 +25,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from taiyaki_b200 import fast5utils  # noqa: E402
+from taiyaki_b200.cmdargs import AutoBool  # noqa: E402
 from taiyaki_b200.maths import med_mad  # noqa: E402
 from taiyaki_b200.signal import Signal  # noqa: E402
-
-
-def auto_bool(v):
-    return v if isinstance(v, bool) else str(v).lower() in ('1', 'true', 'yes', 'on')
 
 
 def non_negative_int(s):
@@ -48,7 +45,7 @@ def get_parser():
     p.add_argument('--limit', default=None, type=lambda s: None if s in ('None', 'none') else int(s),
                    help='Limit number of reads to process')
     p.add_argument('--output', default=None, metavar='filename', help='Write output to file')
-    p.add_argument('--recursive', default=True, type=auto_bool, nargs='?', const=True,
+    p.add_argument('--recursive', default=True, action=AutoBool,
                    help='Search for fast5s recursively within input_folder')
     p.add_argument('--jobs', default=1, type=int, help='Accepted for compatibility; reads are processed in turn')
     p.add_argument('--trim', default=(200, 50), nargs=2, type=non_negative_int, metavar=('beginning', 'end'),

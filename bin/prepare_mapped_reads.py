@@ -33,6 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from taiyaki_b200 import alphabet, fast5utils, helpers  # noqa: E402
+from taiyaki_b200.cmdargs import AutoBool  # noqa: E402
 from taiyaki_b200.signal import Signal  # noqa: E402
 from taiyaki_b200.prepare_mapping_funcs import (  # noqa: E402
     fasta_file_to_dict, generate_output_from_results, get_per_read_params_dict_from_tsv,
@@ -47,7 +48,7 @@ def get_parser():
     p.add_argument('--device', default='cuda:0')
     p.add_argument('--input_strand_list', default=None)
     p.add_argument('--limit', default=None, type=int)
-    p.add_argument('--overwrite', default=False, action='store_true')
+    p.add_argument('--overwrite', default=False, action=AutoBool, help='Whether to overwrite any output files')
     p.add_argument('--reads_per_batch', default=64, type=int, help='Reads aligned per launch')
     p.add_argument('--localpen', metavar='penalty', default=0.0, type=float,
                    help='Penalty for local mapping')
@@ -59,8 +60,7 @@ def get_parser():
     p.add_argument('--shard', nargs=2, type=int, default=None, metavar=('index', 'count'),
                    help='Remap only the reads whose position in the input order is index modulo count, '
                         'into <output>.shard<index>of<count> (set from RANK / WORLD_SIZE under torchrun)')
-    p.add_argument('--recursive', default=True, nargs='?', const=True,
-                   type=lambda v: str(v).lower() in ('1', 'true', 'yes', 'on'),
+    p.add_argument('--recursive', default=True, action=AutoBool,
                    help='Search for fast5s recursively within input_folder')
     p.add_argument('input_folder', help='Directory containing single or multi-read fast5 files '
                                         '(or <read_id>.npz raw reads)')
@@ -204,7 +204,9 @@ def main(argv=None):
     per_read_params_dict = get_per_read_params_dict_from_tsv(args.input_per_read_params)
     model = helpers.load_model(args.model).to(device)
     stride = helpers.guess_model_stride(model)
-    references = fasta_file_to_dict(args.references)
+    # references with a letter outside the alphabet are dropped, their reads reported as
+    # NO_REF_FOUND (bin/prepare_mapped_reads.py:119-120)
+    references = fasta_file_to_dict(args.references, alphabet=alphabet_info.alphabet)
 
     def results():
         def wanted(read_id):      # signals of reads without reference or parameters are not loaded

@@ -36,6 +36,7 @@ if ROOT not in sys.path:
 from taiyaki_b200 import (chunk_selection, device_batching, helpers, layers,  # noqa: E402
                           mapped_signal_files, maths, signal_mapping, training)
 from taiyaki_b200.alphabet import AlphabetInfo  # noqa: E402
+from taiyaki_b200.cmdargs import AutoBool  # noqa: E402
 
 DOTROWLENGTH = 50
 MODEL_LOG_FILENAME, BATCH_LOG_FILENAME, VAL_LOG_FILENAME = 'model.log', 'batch.log', 'validation.log'
@@ -57,12 +58,6 @@ SHARPEN = namedtuple('SHARPEN', ('min', 'max', 'niter'))
 MOD_FACTOR = namedtuple('MOD_FACTOR', ('start', 'final', 'niter'))
 LOGS = namedtuple('LOGS', ('main', 'batch', 'validation'))
 LOGS.__new__.__defaults__ = (None, None)
-
-
-def auto_bool(v):
-    if isinstance(v, bool):
-        return v
-    return str(v).lower() in ('1', 'true', 'yes', 'on')
 
 
 def get_train_flipflop_parser():
@@ -95,22 +90,24 @@ def get_train_flipflop_parser():
     g.add_argument('--filter_path_buffer', default=1.1, type=float)
     g.add_argument('--limit', default=None, type=int)
     g.add_argument('--input_strand_list', default=None)
-    g.add_argument('--reverse', default=False, type=auto_bool)
+    g.add_argument('--reverse', default=False, action=AutoBool, help='Reverse input sequence and current')
     g.add_argument('--sample_nreads_before_filtering', type=int, default=100000)
     g.add_argument('--chunk_len_min', default=3000, type=int)
     g.add_argument('--chunk_len_max', default=8000, type=int)
     g.add_argument('--min_sub_batch_size', default=128, type=int)
     g.add_argument('--reporting_sub_batches', default=100, type=int)
-    g.add_argument('--standardize', default=True, type=auto_bool)
+    g.add_argument('--standardize', default=True, action=AutoBool,
+                   help='Standardize currents for each read')
     g.add_argument('--sub_batches', default=1, type=int)
     g = p.add_argument_group('Compute Arguments')
     g.add_argument('--device', default='cuda:0')
     g.add_argument('--local_rank', type=int, default=None, help=argparse.SUPPRESS)
     g = p.add_argument_group('Output Arguments')
-    g.add_argument('--full_filter_status', default=False, type=auto_bool)
+    g.add_argument('--full_filter_status', default=False, action=AutoBool,
+                   help='Output full chunk filtering statistics')
     g.add_argument('--outdir', default='training')
-    g.add_argument('--overwrite', default=False, action='store_true')
-    g.add_argument('--quiet', default=False, action='store_true')
+    g.add_argument('--overwrite', default=False, action=AutoBool, help='Whether to overwrite any output files')
+    g.add_argument('--quiet', default=False, action=AutoBool, help="Don't print progress information to stdout")
     g.add_argument('--save_every', type=int, default=2500)
     g.add_argument('--cuda_graphs', default=False, action='store_true',
                    help='Replay forward + loss + backward as a CUDA graph once a batch shape has been '

@@ -24,13 +24,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from taiyaki_b200 import alphabet  # noqa: E402
+from taiyaki_b200.cmdargs import AutoBool  # noqa: E402
 from taiyaki_b200.mapped_signal_files import MappedSignalReader, MappedSignalWriter  # noqa: E402
 
 FILE_VERSION = 8        # mapped_signal_files._version
-
-
-def auto_bool(v):
-    return v if isinstance(v, bool) else str(v).lower() in ('1', 'true', 'yes', 'on')
 
 
 def get_parser():
@@ -41,7 +38,7 @@ def get_parser():
                    metavar=('mapped_signal_file', 'num_reads'),
                    help='Mapped signal filename and the number of reads to merge from this file. '
                         'Specify "None" to merge all reads from a file.')
-    p.add_argument('--load_in_mem', type=auto_bool, nargs='?', const=True, default=True,
+    p.add_argument('--load_in_mem', action=AutoBool, default=True,
                    help='Accepted for compatibility (input files are memory-mapped)')
     p.add_argument('--seed', default=None, type=lambda s: None if s in ('None', 'none') else int(s),
                    help='Seed for randomly selected reads when limits are set')

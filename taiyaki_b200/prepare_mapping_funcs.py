@@ -44,20 +44,37 @@ def get_per_read_params_dict_from_tsv(input_file):
     return out
 
 
-def fasta_file_to_dict(fasta_file_name):
-    """Record id (up to the first blank) -> sequence (taiyaki/bio.py fasta_file_to_dict)."""
-    references, name, parts = {}, None, []
+def fasta_file_to_dict(fasta_file_name, filter_ambig=True, flatten_ambig=True, alphabet='ACGT'):
+    """Record id (up to the first blank) -> sequence (taiyaki/bio.py:43-81).  Empty records are
+    dropped; with `filter_ambig` so are records holding a character outside `alphabet` (a count of
+    them goes to stderr); otherwise, with `flatten_ambig`, such characters become N."""
+    import re
+    notbase = re.compile('[^{}]'.format(re.escape(alphabet)))
+    references, skipped = {}, 0
+
+    def keep(name, parts):
+        nonlocal skipped
+        seq = ''.join(parts)
+        if name is None or len(seq) == 0:
+            return
+        if filter_ambig and notbase.search(seq) is not None:
+            skipped += 1
+            return
+        references[name] = notbase.sub('N', seq) if flatten_ambig else seq
+    name, parts = None, []
     with open(fasta_file_name) as fh:
         for line in fh:
             line = line.strip()
             if line.startswith('>'):
-                if name is not None:
-                    references[name] = ''.join(parts)
-                name, parts = line[1:].split()[0], []
+                keep(name, parts)
+                fields = line[1:].split()
+                name, parts = (fields[0] if fields else ''), []
             elif line:
                 parts.append(line)
-    if name is not None:
-        references[name] = ''.join(parts)
+    keep(name, parts)
+    if skipped > 0:
+        sys.stderr.write('* {} reference seqeunces contain ambiguous bases not found in the provided '
+                         'alphabet and will be skipped.\n'.format(skipped))
     return references
 
 

@@ -120,7 +120,7 @@ def test_basecall_cli_host_pieces(tmp_path):
     assert (a.chunk_size, a.overlap, a.max_concurrent_chunks, a.posterior, a.fastq, a.temperature,
             a.qscore_scale, a.qscore_offset, a.reverse, a.alphabet) == (
                 1000, 100, 128, True, False, 1.0, 1.0, 0.0, False, 'ACGT')
-    a = cli.get_parser().parse_args(['--fastq', '--posterior', 'false', '--chunk_size', '500', 'r', 'm'])
+    a = cli.get_parser().parse_args(['--fastq', '--no-posterior', '--chunk_size', '500', 'r', 'm'])
     assert a.fastq is True and a.posterior is False and a.chunk_size == 500
     folder = tmp_path / 'sig'
     folder.mkdir()

@@ -140,6 +140,44 @@ def test_train_cli_parser_defaults_match_reference():
     assert a.mod_prior_factor is None and a.num_mod_weight_reads == 5000
 
 
+def test_boolean_flag_pairs_parse_like_the_reference():
+    """taiyaki/cmdargs.py:90-127 AutoBool: `--flag` / `--no-flag`, neither takes a value -- so the
+    reference's command lines, where such a flag may stand right before the positional arguments
+    (`basecall.py --fastq reads/ model`), parse the same here."""
+    import argparse
+    import importlib
+    from taiyaki_b200.cmdargs import AutoBool
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    sys.path.insert(0, os.path.join(ROOT, 'misc'))
+    p = argparse.ArgumentParser()
+    p.add_argument('--thing', default=True, action=AutoBool, help='A thing')
+    p.add_argument('where')
+    assert p.parse_args(['x']).thing is True and p.parse_args(['--no-thing', 'x']).thing is False
+    assert p.parse_args(['--thing', 'x']).where == 'x' and '(Default: --thing)' in p.format_help()
+    with pytest.raises(ValueError):
+        argparse.ArgumentParser().add_argument('--nodefault', action=AutoBool)
+    bc = importlib.import_module('basecall').get_parser()
+    a = bc.parse_args(['--fastq', 'reads/', 'model.checkpoint'])
+    assert a.fastq is True and (a.input_folder, a.model) == ('reads/', 'model.checkpoint')
+    a = bc.parse_args(['--no-posterior', '--reverse', '--no-recursive', '--quiet', 'reads/', 'm'])
+    assert (a.posterior, a.reverse, a.recursive, a.quiet, a.fastq) == (False, True, False, True, False)
+    tf = importlib.import_module('train_flipflop').get_train_flipflop_parser()
+    a = tf.parse_args(['--no-standardize', '--reverse', '--full_filter_status', '--overwrite', 'model.py', 'in.hdf5'])
+    assert (a.standardize, a.reverse, a.full_filter_status, a.overwrite, a.quiet) == (False, True, True, True, False)
+    a = tf.parse_args(['--quiet', 'model.py', 'in.hdf5'])
+    assert a.quiet is True and a.standardize is True and a.model == 'model.py'
+    pm = importlib.import_module('prepare_mapped_reads').get_parser()
+    a = pm.parse_args(['--overwrite', 'reads/', 'p.tsv', 'out.hdf5', 'model', 'refs.fa'])
+    assert a.overwrite is True and a.recursive is True and a.input_folder == 'reads/'
+    gp = importlib.import_module('generate_per_read_params').get_parser()
+    assert gp.parse_args(['--no-recursive', 'reads/']).recursive is False
+    gr = importlib.import_module('get_refs_from_sam').get_parser()
+    a = gr.parse_args(['--reverse', '--complement', 'genome.fa', 'a.sam', 'b.sam'])
+    assert (a.reverse, a.complement, a.reference, a.input) == (True, True, 'genome.fa', ['a.sam', 'b.sam'])
+    mg = importlib.import_module('merge_mappedsignalfiles').get_parser()
+    assert mg.parse_args(['out', '--input', 'a', 'None', '--no-load_in_mem']).load_in_mem is False
+
+
 def test_train_cli_mod_prior_factor():
     """--mod_prior_factor: prior odds of the sampled reads raised to the factor
     (train_flipflop.py:312-326); without the flag every category weighs 1."""

@@ -118,8 +118,15 @@ def test_prepare_mapped_reads_host_pieces(tmp_path):
     params = pmf.get_per_read_params_dict_from_tsv(str(tsv))
     assert sorted(params) == ['read0', 'read1', 'read2']
     assert params['read2'] == {'trim_start': 100, 'trim_end': 20, 'shift': 85.0, 'scale': 14.0}
-    refs = pmf.fasta_file_to_dict(str(fa))
+    refs = pmf.fasta_file_to_dict(str(fa), alphabet='ACGTZ')
     assert {k: v for k, v in refs.items()} == {k: v[1] for k, v in reads.items()}
+    # taiyaki/bio.py:43-81: a record with a letter outside the alphabet is dropped (default ACGT;
+    # these references hold the modified base Z), or -- filter off -- the letter becomes N
+    assert pmf.fasta_file_to_dict(str(fa)) == {k: v[1] for k, v in reads.items() if 'Z' not in v[1]}
+    flat = pmf.fasta_file_to_dict(str(fa), filter_ambig=False)
+    assert {k: v for k, v in flat.items()} == {k: v[1].replace('Z', 'N') for k, v in reads.items()}
+    raw = pmf.fasta_file_to_dict(str(fa), filter_ambig=False, flatten_ambig=False)
+    assert raw == {k: v[1] for k, v in reads.items()}
     raw = list(cli.iterate_raw_reads(str(folder)))
     assert [r['read_id'] for r in raw] == ['orphan', 'read0', 'read1', 'read2']
     assert raw[1]['digitisation'] == 8192.0 and raw[1]['dacs'].dtype == np.int16
