@@ -39,6 +39,22 @@ def g():
     return fast5_fixture.golden()
 
 
+@pytest.fixture(autouse=True)
+def leave_global_rngs_untouched():
+    """Building a network draws its initial weights from numpy's and torch's GLOBAL generators
+    (layers.py: orthonormal / truncated-normal initialisers, as in the reference) before the
+    golden parameters replace them.  Several older tests seed only one of the generators and so
+    see whatever state the tests before them left; this file restores both, so that adding or
+    removing it does not change what any other test computes."""
+    np_state, torch_state = np.random.get_state(), torch.get_rng_state()
+    cuda_state = torch.cuda.get_rng_state_all() if torch.cuda.is_available() else None
+    yield
+    np.random.set_state(np_state)
+    torch.set_rng_state(torch_state)
+    if cuda_state is not None:
+        torch.cuda.set_rng_state_all(cuda_state)
+
+
 def _load_cli(name):
     import importlib
     sys.path.insert(0, os.path.join(ROOT, 'bin'))
