@@ -71,10 +71,12 @@ def get_parser():
     return p
 
 
-def get_signal(read_filename, read_id):
+def get_signal(read_filename, read_id, loader=None):
     """Current in pA of one read of a fast5 file, None when it cannot be read
-    (bin/basecall.py:92-116)."""
+    (bin/basecall.py:92-116).  `loader`: a fast5utils.ReadLoader shared by consecutive reads."""
     try:
+        if loader is not None:
+            return Signal(loader.get_read(read_filename, read_id)).current
         with fast5utils.get_fast5_file(read_filename, 'r') as f5file:
             return Signal(f5file.get_read(read_id)).current
     except Exception as e:
@@ -92,9 +94,10 @@ def _is_array_input(input_folder):
 def iterate_signals(input_folder, limit=None, strand_list=None, recursive=True):
     """Yield (read_id, signal) from fast5 files, a folder of .npy files or one .npz."""
     if not _is_array_input(input_folder):
-        for filename, read_id in fast5utils.iterate_fast5_reads(
-                input_folder, limit=limit, strand_list=strand_list, recursive=recursive):
-            yield read_id, get_signal(filename, read_id)
+        with fast5utils.ReadLoader() as loader:
+            for filename, read_id in fast5utils.iterate_fast5_reads(
+                    input_folder, limit=limit, strand_list=strand_list, recursive=recursive):
+                yield read_id, get_signal(filename, read_id, loader)
         return
     keep = None
     if strand_list is not None:

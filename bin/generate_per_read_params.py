@@ -54,13 +54,16 @@ def get_parser():
     return p
 
 
-def one_read_shift_scale(read_tuple):
+def one_read_shift_scale(read_tuple, loader=None):
     """(read id, shift, scale) of one (file, read id) pair; (None, None, None) when the signal
     cannot be read, NaNs for an empty signal (generate_per_read_params.py:33-76)."""
     read_filename, read_id = read_tuple
     try:
-        with fast5utils.get_fast5_file(read_filename, 'r') as f5file:
-            sig = Signal(f5file.get_read(read_id))
+        if loader is not None:
+            sig = Signal(loader.get_read(read_filename, read_id))
+        else:
+            with fast5utils.get_fast5_file(read_filename, 'r') as f5file:
+                sig = Signal(f5file.get_read(read_id))
     except Exception as e:
         sys.stderr.write('Unable to obtain signal for {} from {}.\n{}\n'.format(read_id, read_filename, repr(e)))
         return None, None, None
@@ -81,15 +84,17 @@ def main(argv=None):
                                            strand_list=args.input_strand_list, recursive=args.recursive)
     fh = sys.stdout if args.output is None else open(args.output, 'w')
     nrow = 0
+    loader = fast5utils.ReadLoader()
     try:
         writer = csv.writer(fh, delimiter='\t', lineterminator='\n')
         writer.writerow(['UUID', 'trim_start', 'trim_end', 'shift', 'scale'])
-        for result in map(one_read_shift_scale, reads):
+        for result in (one_read_shift_scale(r, loader) for r in reads):
             if all(result):         # as the reference: drops unreadable reads (and a shift of exactly 0)
                 read_id, shift, scale = result
                 writer.writerow([read_id, trim_start, trim_end, shift, scale])
                 nrow += 1
     finally:
+        loader.close()
         if fh is not sys.stdout:
             fh.close()
     return nrow

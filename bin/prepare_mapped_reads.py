@@ -123,21 +123,21 @@ def iterate_fast5_reads(input_folder, limit=None, strand_list=None, recursive=Tr
     samples of a read that will be rejected anyway; a read whose samples cannot be loaded is
     passed on with dacs None and reported as READ_ID_INFO_NOT_FOUND
     (prepare_mapping_funcs.py:62-68)."""
-    for index, (filename, read_id) in enumerate(fast5utils.iterate_fast5_reads(
-            input_folder, limit=limit, strand_list=strand_list, recursive=recursive)):
-        if not in_shard(index, shard):
-            continue
-        read = {'read_id': read_id, 'dacs': None, 'offset': 0.0, 'range': 1.0, 'digitisation': 1.0}
-        if wanted is None or wanted(read_id):
-            try:
-                with fast5utils.get_fast5_file(filename, 'r') as f5file:
-                    sig = Signal(f5file.get_read(read_id))
-                read.update(dacs=sig.untrimmed_dacs, offset=float(sig.offset), range=float(sig.range),
-                            digitisation=float(sig.digitisation))
-            except Exception as e:
-                sys.stderr.write('Unable to obtain signal for {} from {}.\n{}\n'.format(
-                    read_id, filename, repr(e)))
-        yield read
+    with fast5utils.ReadLoader() as loader:
+        for index, (filename, read_id) in enumerate(fast5utils.iterate_fast5_reads(
+                input_folder, limit=limit, strand_list=strand_list, recursive=recursive)):
+            if not in_shard(index, shard):
+                continue
+            read = {'read_id': read_id, 'dacs': None, 'offset': 0.0, 'range': 1.0, 'digitisation': 1.0}
+            if wanted is None or wanted(read_id):
+                try:
+                    sig = Signal(loader.get_read(filename, read_id))
+                    read.update(dacs=sig.untrimmed_dacs, offset=float(sig.offset), range=float(sig.range),
+                                digitisation=float(sig.digitisation))
+                except Exception as e:
+                    sys.stderr.write('Unable to obtain signal for {} from {}.\n{}\n'.format(
+                        read_id, filename, repr(e)))
+            yield read
 
 
 def iterate_raw_reads(input_folder, limit=None, strand_list=None, recursive=True, wanted=None,

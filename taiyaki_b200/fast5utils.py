@@ -106,6 +106,32 @@ def get_fast5_file(filename, mode='r'):
     return Fast5File(filename, mode)
 
 
+class ReadLoader:
+    """get_read(filename, read_id) that keeps the file of the previous call open: consecutive reads
+    of a multi-read file (4000 reads per file is usual) then share one parse of the file's root
+    group instead of repeating it per read."""
+
+    def __init__(self):
+        self._name, self._file = None, None
+
+    def get_read(self, filename, read_id):
+        if filename != self._name:
+            self.close()
+            self._file, self._name = get_fast5_file(filename, 'r'), filename
+        return self._file.get_read(read_id)
+
+    def close(self):
+        if self._file is not None:
+            self._file.close()
+        self._name, self._file = None, None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def get_fast5_file_list(path, recursive=False):
     """*.fast5 below `path` (a file is returned as it is); sorted, so that runs are repeatable."""
     if os.path.isfile(path):
@@ -126,17 +152,19 @@ def iterate_file_read_pairs(filepaths, read_ids, limit=None, verbose=0):
     """(file, read id) rows of a strand list: those whose file exists and holds the read
     (fast5utils.py:16-49)."""
     nyielded = 0
+    listed = (None, frozenset())          # read ids of the file of the previous row
     for filepath, read_id in zip(filepaths, read_ids):
         if not os.path.exists(filepath):
             sys.stderr.write('File {} does not exist, skipping\n'.format(filepath))
             continue
-        try:
-            with get_fast5_file(filepath, 'r') as f5file:
-                present = read_id in f5file.get_read_ids()
-        except Exception as e:
-            _skipped(e)
-            continue
-        if not present:
+        if filepath != listed[0]:
+            try:
+                with get_fast5_file(filepath, 'r') as f5file:
+                    listed = (filepath, frozenset(f5file.get_read_ids()))
+            except Exception as e:
+                _skipped(e)
+                continue
+        if read_id not in listed[1]:
             continue
         if verbose > 0:
             print('Reading', read_id, 'from', filepath)

@@ -151,6 +151,28 @@ def test_written_fast5_files_round_trip(g, tmp_path, multi):
     assert _ids(fast5utils.iterate_fast5_reads(one)) == (EXPECTED_READ_IDS if multi else [found[0][1]])
 
 
+def test_read_loader_keeps_one_file_open(g, tmp_path):
+    """Consecutive reads of one multi-read file share one open file (one parse of its root group);
+    another file name replaces it."""
+    from taiyaki_b200 import fast5utils
+    from taiyaki_b200.signal import Signal
+    multi_dir, _, _ = fast5_fixture.write_inputs(tmp_path / 'm', g, multi=True)
+    single_dir, _, _ = fast5_fixture.write_inputs(tmp_path / 's', g, multi=False)
+    batch = os.path.join(multi_dir, 'batch_0.fast5')
+    with fast5utils.ReadLoader() as loader:
+        a = loader.get_read(batch, EXPECTED_READ_IDS[0])
+        opened = loader._file
+        b = loader.get_read(batch, EXPECTED_READ_IDS[1])
+        assert loader._file is opened
+        np.testing.assert_array_equal(Signal(a).untrimmed_dacs, g[EXPECTED_READ_IDS[0] + '_dacs'])
+        np.testing.assert_array_equal(Signal(b).untrimmed_dacs, g[EXPECTED_READ_IDS[1] + '_dacs'])
+        c = loader.get_read(os.path.join(single_dir, EXPECTED_READ_IDS[2] + '.fast5'), EXPECTED_READ_IDS[2])
+        assert loader._file is not opened and Signal(c).read_id == EXPECTED_READ_IDS[2]
+        with pytest.raises(KeyError):
+            loader.get_read(batch, 'not-a-read')
+    assert loader._file is None
+
+
 def test_strand_lists_on_written_files(g, tmp_path):
     """The three kinds of strand list (fast5utils.py:121-134) and the files they may name."""
     from taiyaki_b200.fast5utils import iterate_fast5_reads
