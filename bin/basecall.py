@@ -26,7 +26,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from taiyaki_b200 import basecall, basecall_helpers, fast5utils, helpers  # noqa: E402
-from taiyaki_b200.cmdargs import AutoBool  # noqa: E402
+from taiyaki_b200.cmdargs import (AutoBool, DeviceAction, FileExists, Maybe, NonNegative,  # noqa: E402
+                                  Positive)
 from taiyaki_b200.flipflopfings import nstate_flipflop  # noqa: E402
 from taiyaki_b200.prepare_mapping_funcs import get_per_read_params_dict_from_tsv  # noqa: E402
 from taiyaki_b200.signal import Signal  # noqa: E402
@@ -36,22 +37,23 @@ def get_parser():
     p = argparse.ArgumentParser(description='Basecall reads using a taiyaki model',
                                 formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     p.add_argument('--alphabet', default='ACGT')
-    p.add_argument('--device', default='cuda:0')
-    p.add_argument('--limit', default=None, type=int, help='Limit number of reads to process')
+    p.add_argument('--device', default='cuda:0', action=DeviceAction,
+                   help='GPU to use: an integer, "cuda:2", "cuda2" or "cuda" (this path has no CPU mode)')
+    p.add_argument('--limit', default=None, type=Maybe(Positive(int)), help='Limit number of reads to process')
     p.add_argument('--output', default=None, help='Write output to file (default stdout)')
     p.add_argument('--quiet', default=False, action=AutoBool, help="Don't print progress information to stdout")
-    p.add_argument('--input_strand_list', default=None,
+    p.add_argument('--input_strand_list', default=None, action=FileExists,
                    help='File with a read_id column: only these reads are called')
-    p.add_argument('--chunk_size', type=int, metavar='blocks',
+    p.add_argument('--chunk_size', type=Positive(int), metavar='blocks',
                    default=basecall_helpers._DEFAULT_CHUNK_SIZE,
                    help='Size of signal chunks sent to GPU is chunk_size * model stride')
     p.add_argument('--fastq', default=False, action=AutoBool,
                    help='Write output in fastq format (default is fasta)')
-    p.add_argument('--max_concurrent_chunks', type=int, default=128,
+    p.add_argument('--max_concurrent_chunks', type=Positive(int), default=128,
                    help='Maximum number of chunks to call at once')
-    p.add_argument('--reads_per_batch', type=int, default=16,
+    p.add_argument('--reads_per_batch', type=Positive(int), default=16,
                    help='Reads whose chunks are pooled into shared batches')
-    p.add_argument('--overlap', type=int, metavar='blocks',
+    p.add_argument('--overlap', type=NonNegative(int), metavar='blocks',
                    default=basecall_helpers._DEFAULT_OVERLAP,
                    help='Overlap between signal chunks sent to GPU')
     p.add_argument('--posterior', default=True, action=AutoBool,
@@ -60,7 +62,7 @@ def get_parser():
     p.add_argument('--qscore_scale', type=float, default=1.0)
     p.add_argument('--reverse', default=False, action=AutoBool,
                    help='Reverse sequences in output')
-    p.add_argument('--scaling', default=None, help='Path to TSV containing per-read scaling params')
+    p.add_argument('--scaling', default=None, action=FileExists, help='Path to TSV containing per-read scaling params')
     p.add_argument('--temperature', default=1.0, type=float,
                    help='Scaling factor applied to network outputs before decoding')
     p.add_argument('--recursive', default=True, action=AutoBool,

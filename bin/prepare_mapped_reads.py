@@ -33,7 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from taiyaki_b200 import alphabet, fast5utils, helpers  # noqa: E402
-from taiyaki_b200.cmdargs import AutoBool  # noqa: E402
+from taiyaki_b200.cmdargs import AutoBool, DeviceAction, FileExists, Maybe, Positive  # noqa: E402
 from taiyaki_b200.signal import Signal  # noqa: E402
 from taiyaki_b200.prepare_mapping_funcs import (  # noqa: E402
     fasta_file_to_dict, generate_output_from_results, get_per_read_params_dict_from_tsv,
@@ -45,15 +45,15 @@ def get_parser():
         description='Prepare data for model training and save to hdf5 file by remapping with '
         'flip-flop model', formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     p.add_argument('--alphabet', default='ACGT')
-    p.add_argument('--device', default='cuda:0')
-    p.add_argument('--input_strand_list', default=None)
-    p.add_argument('--limit', default=None, type=int)
+    p.add_argument('--device', default='cuda:0', action=DeviceAction,
+                   help='GPU to use: an integer, "cuda:2", "cuda2" or "cuda" (this path has no CPU mode)')
+    p.add_argument('--input_strand_list', default=None, action=FileExists)
+    p.add_argument('--limit', default=None, type=Maybe(Positive(int)))
     p.add_argument('--overwrite', default=False, action=AutoBool, help='Whether to overwrite any output files')
-    p.add_argument('--reads_per_batch', default=64, type=int, help='Reads aligned per launch')
+    p.add_argument('--reads_per_batch', default=64, type=Positive(int), help='Reads aligned per launch')
     p.add_argument('--localpen', metavar='penalty', default=0.0, type=float,
                    help='Penalty for local mapping')
-    p.add_argument('--max_read_length', metavar='bases', default=None,
-                   type=lambda s: None if s in ('None', 'none') else int(s),
+    p.add_argument('--max_read_length', metavar='bases', default=None, type=Maybe(int),
                    help="Don't attempt remapping for reads longer than this")
     p.add_argument('--mod', nargs=3, metavar=('mod_base', 'canonical_base', 'mod_long_name'),
                    default=[], action='append', help='Modified base description')

@@ -36,7 +36,8 @@ if ROOT not in sys.path:
 from taiyaki_b200 import (chunk_selection, device_batching, helpers, layers,  # noqa: E402
                           mapped_signal_files, maths, signal_mapping, training)
 from taiyaki_b200.alphabet import AlphabetInfo  # noqa: E402
-from taiyaki_b200.cmdargs import AutoBool  # noqa: E402
+from taiyaki_b200.cmdargs import (AutoBool, Bounded, DeviceAction, FileExists, Maybe,  # noqa: E402
+                                  NonNegative, Positive)
 
 DOTROWLENGTH = 50
 MODEL_LOG_FILENAME, BATCH_LOG_FILENAME, VAL_LOG_FILENAME = 'model.log', 'batch.log', 'validation.log'
@@ -65,42 +66,42 @@ def get_train_flipflop_parser():
     p = argparse.ArgumentParser(description='Train flip-flop neural network',
                                 formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     g = p.add_argument_group('Model Arguments')
-    g.add_argument('--size', default=384, type=int, metavar='neurons')
-    g.add_argument('--stride', default=5, type=int, metavar='samples')
-    g.add_argument('--winlen', default=19, type=int)
+    g.add_argument('--size', default=384, type=Positive(int), metavar='neurons')
+    g.add_argument('--stride', default=5, type=Positive(int), metavar='samples')
+    g.add_argument('--winlen', default=19, type=Positive(int))
     g = p.add_argument_group('Training Arguments')
-    g.add_argument('--adam', nargs=2, default=[0.9, 0.999], type=float, metavar=('beta1', 'beta2'))
-    g.add_argument('--eps', default=1e-6, type=float)
-    g.add_argument('--niteration', default=150000, type=int)
-    g.add_argument('--weight_decay', default=0.01, type=float)
-    g.add_argument('--gradient_clip_num_mads', default=0,
-                   type=lambda s: None if s in ('None', 'none') else float(s))
-    g.add_argument('--lr_max', default=4.0e-3, type=float)
-    g.add_argument('--lr_min', default=1.0e-4, type=float)
-    g.add_argument('--lr_warmup', default=None, type=float)
-    g.add_argument('--min_momentum', default=None, type=float)
-    g.add_argument('--seed', default=None, type=int)
+    g.add_argument('--adam', nargs=2, default=[0.9, 0.999], type=NonNegative(float), metavar=('beta1', 'beta2'))
+    g.add_argument('--eps', default=1e-6, type=Positive(float))
+    g.add_argument('--niteration', default=150000, type=Positive(int))
+    g.add_argument('--weight_decay', default=0.01, type=NonNegative(float))
+    g.add_argument('--gradient_clip_num_mads', default=0, type=Maybe(NonNegative(float)))
+    g.add_argument('--lr_max', default=4.0e-3, type=Positive(float))
+    g.add_argument('--lr_min', default=1.0e-4, type=Positive(float))
+    g.add_argument('--lr_warmup', default=None, type=Positive(float))
+    g.add_argument('--min_momentum', default=None, type=Positive(float))
+    g.add_argument('--seed', default=None, type=Positive(int))
     g.add_argument('--sharpen', default=(1.0, 1.0, 25000), nargs=3, type=float,
                    metavar=('min', 'max', 'niter'))
     g.add_argument('--warmup_batches', type=int, default=200)
     g = p.add_argument_group('Data Arguments')
-    g.add_argument('--filter_max_dwell', default=10.0, type=float)
-    g.add_argument('--filter_mean_dwell', default=3.0, type=float)
-    g.add_argument('--filter_min_pass_fraction', default=0.5, type=float)
-    g.add_argument('--filter_path_buffer', default=1.1, type=float)
-    g.add_argument('--limit', default=None, type=int)
-    g.add_argument('--input_strand_list', default=None)
+    g.add_argument('--filter_max_dwell', default=10.0, type=Maybe(Positive(float)))
+    g.add_argument('--filter_mean_dwell', default=3.0, type=Maybe(Positive(float)))
+    g.add_argument('--filter_min_pass_fraction', default=0.5, type=Maybe(Positive(float)))
+    g.add_argument('--filter_path_buffer', default=1.1, type=Bounded(float, lower=1.0))
+    g.add_argument('--limit', default=None, type=Maybe(Positive(int)))
+    g.add_argument('--input_strand_list', default=None, action=FileExists)
     g.add_argument('--reverse', default=False, action=AutoBool, help='Reverse input sequence and current')
-    g.add_argument('--sample_nreads_before_filtering', type=int, default=100000)
-    g.add_argument('--chunk_len_min', default=3000, type=int)
-    g.add_argument('--chunk_len_max', default=8000, type=int)
-    g.add_argument('--min_sub_batch_size', default=128, type=int)
-    g.add_argument('--reporting_sub_batches', default=100, type=int)
+    g.add_argument('--sample_nreads_before_filtering', type=NonNegative(int), default=100000)
+    g.add_argument('--chunk_len_min', default=3000, type=Positive(int))
+    g.add_argument('--chunk_len_max', default=8000, type=Positive(int))
+    g.add_argument('--min_sub_batch_size', default=128, type=Positive(int))
+    g.add_argument('--reporting_sub_batches', default=100, type=Positive(int))
     g.add_argument('--standardize', default=True, action=AutoBool,
                    help='Standardize currents for each read')
-    g.add_argument('--sub_batches', default=1, type=int)
+    g.add_argument('--sub_batches', default=1, type=Positive(int))
     g = p.add_argument_group('Compute Arguments')
-    g.add_argument('--device', default='cuda:0')
+    g.add_argument('--device', default='cuda:0', action=DeviceAction,
+                   help='GPU to use: an integer, "cuda:2", "cuda2" or "cuda" (this path has no CPU mode)')
     g.add_argument('--local_rank', type=int, default=None, help=argparse.SUPPRESS)
     g = p.add_argument_group('Output Arguments')
     g.add_argument('--full_filter_status', default=False, action=AutoBool,
@@ -108,7 +109,7 @@ def get_train_flipflop_parser():
     g.add_argument('--outdir', default='training')
     g.add_argument('--overwrite', default=False, action=AutoBool, help='Whether to overwrite any output files')
     g.add_argument('--quiet', default=False, action=AutoBool, help="Don't print progress information to stdout")
-    g.add_argument('--save_every', type=int, default=2500)
+    g.add_argument('--save_every', type=Positive(int), default=2500)
     g.add_argument('--cuda_graphs', default=False, action='store_true',
                    help='Replay forward + loss + backward as a CUDA graph once a batch shape has been '
                         'seen three times (useful with --chunk_len_min == --chunk_len_max and short '

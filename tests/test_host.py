@@ -178,6 +178,56 @@ def test_boolean_flag_pairs_parse_like_the_reference():
     assert mg.parse_args(['out', '--input', 'a', 'None', '--no-load_in_mem']).load_in_mem is False
 
 
+def test_argument_types_follow_the_reference():
+    """taiyaki/cmdargs.py types, on the value lists of the reference's test/unit/test_cmdargs.py."""
+    import argparse
+    from taiyaki_b200 import cmdargs
+    eps = sys.float_info.epsilon
+
+    def refuses(f, values):
+        for x in values:
+            with pytest.raises(argparse.ArgumentTypeError):
+                f(x)
+    for x in [1e-30, eps, 1e-5, 1.0, 1e5, 1e30]:
+        assert cmdargs.Positive(float)(x) == x
+    refuses(cmdargs.Positive(float), [-1.0, -eps, -1e-5, 0.0])
+    assert [cmdargs.Positive(int)(x) for x in [1, 10, 10000]] == [1, 10, 10000]
+    refuses(cmdargs.Positive(int), [-1, 0])
+    for x in [1e-30, eps, 1e-5, 0.0, 1.0, 1e5, 1e30]:
+        assert cmdargs.NonNegative(float)(x) == x
+    refuses(cmdargs.NonNegative(float), [-1.0, -eps, -1e-5])
+    assert [cmdargs.NonNegative(int)(x) for x in [0, 1, 10, 10000]] == [0, 1, 10, 10000]
+    refuses(cmdargs.NonNegative(int), [-1, -10])
+    for x in [1e-30, eps, 1e-5, 0.0, 1.0, 1.0 - 1e-5, 1.0 - eps, 1.0 - 1e-30]:
+        assert cmdargs.proportion(x) == x
+    refuses(cmdargs.proportion, [-1e-30, -eps, -1e-5, 1.0 + 1e-5, 1.0 + eps])
+    assert [cmdargs.Bounded(int, 0, 10)(x) for x in range(11)] == list(range(11))
+    refuses(cmdargs.Bounded(int, 0, 10), [-2, -1, 11, 12])
+    assert cmdargs.Maybe(cmdargs.Positive(int))('None') is None and cmdargs.Maybe(int)('7') == 7
+    refuses(cmdargs.Maybe(cmdargs.Positive(int)), ['0', 'seven'])
+    p = argparse.ArgumentParser()
+    p.add_argument('device', action=cmdargs.DeviceAction)
+    p.add_argument('--table', action=cmdargs.FileExists)
+    p.add_argument('--fresh', action=cmdargs.FileAbsent)
+    assert [p.parse_args([d]).device for d in ('2', 'cuda2', 'cuda:2', 'cuda', 'cpu')] == [2, 2, 'cuda:2', 'cuda', 'cpu']
+    assert p.parse_args(['0', '--table', __file__]).table == __file__
+    with pytest.raises(RuntimeError):
+        p.parse_args(['0', '--table', __file__ + '.absent'])
+    with pytest.raises(RuntimeError):
+        p.parse_args(['0', '--fresh', __file__])
+    # the entry points use them: a value the reference refuses is refused here
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    import importlib
+    tf = importlib.import_module('train_flipflop').get_train_flipflop_parser()
+    for bad in (['--size', '0'], ['--lr_max', '-1'], ['--filter_path_buffer', '0.9'], ['--seed', '0'],
+                ['--chunk_len_min', '-5'], ['--sub_batches', '0']):
+        with pytest.raises(SystemExit):
+            tf.parse_args(bad + ['model.py', 'in.hdf5'])
+    a = tf.parse_args(['--gradient_clip_num_mads', 'None', '--filter_max_dwell', 'None', '--device', '3',
+                       'model.py', 'in.hdf5'])
+    assert a.gradient_clip_num_mads is None and a.filter_max_dwell is None and a.device == 3
+
+
 def test_train_cli_mod_prior_factor():
     """--mod_prior_factor: prior odds of the sampled reads raised to the factor
     (train_flipflop.py:312-326); without the flag every category weighs 1."""
