@@ -17,9 +17,9 @@ import taiyaki_b200
 __version__ = '5.3.0+b200.' + taiyaki_b200.__version__
 
 #: taiyaki.<name> -> taiyaki_b200.<name>
-ALIASED = ('activation', 'alphabet', 'basecall_helpers', 'chunk_selection', 'ctc', 'decode',
-           'flipflop_remap', 'flipflopfings', 'helpers', 'layers', 'mapped_signal_files',
-           'maths', 'prepare_mapping_funcs', 'qscores', 'signal_mapping')
+ALIASED = ('activation', 'alphabet', 'basecall_helpers', 'chunk_selection', 'cmdargs', 'ctc', 'decode',
+           'fast5utils', 'flipflop_remap', 'flipflopfings', 'helpers', 'layers', 'mapped_signal_files',
+           'maths', 'prepare_mapping_funcs', 'qscores', 'signal', 'signal_mapping')
 
 for _name in ALIASED:
     _mod = importlib.import_module('taiyaki_b200.' + _name)

@@ -29,6 +29,11 @@ def med_mad(data, factor=None, axis=None, keepdims=False):
     return np.squeeze(centre, axis), np.squeeze(spread, axis)
 
 
+def mad(data, factor=None, axis=None, keepdims=False):
+    """The spread half of `med_mad` (taiyaki/maths.py:35-52)."""
+    return med_mad(data, factor=factor, axis=axis, keepdims=keepdims)[1]
+
+
 class RollingMAD:
     """Cap = median + n_mads * MAD over the last `window` updates, one cap per parameter.
     Until the window has been filled once, `update` returns `default_to`.

@@ -178,6 +178,38 @@ def test_boolean_flag_pairs_parse_like_the_reference():
     assert mg.parse_args(['out', '--input', 'a', 'None', '--no-load_in_mem']).load_in_mem is False
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/test/unit'),
+                    reason='the reference tree is only in the build container')
+@pytest.mark.parametrize('name,ntests', [('test_cmdargs', 13), ('test_iterate_fast5_reads', 9), ('test_maths', 4)])
+def test_reference_unit_tests_pass_against_this_package(name, ntests):
+    """The reference's OWN unit tests of the host-side modules (test/unit/<name>.py, loaded from
+    where they lie, unmodified) with `taiyaki` resolving to this repository's alias package: what a
+    maintainer switching the import path would run first.  (The tests of the device operators --
+    test_ctc_loss, test_decode, test_flipflop_remap, test_layers -- need a GPU, and the GPU box has
+    no reference tree; tests/test_gpu_*.py restate their cases.)"""
+    import importlib.util
+    import io
+    import types
+    import unittest
+    import taiyaki
+    assert os.path.dirname(os.path.dirname(os.path.abspath(taiyaki.__file__))) == ROOT
+    pkg = types.ModuleType('reference_unit_tests')       # stands in for test/unit/__init__.py
+    pkg.__path__ = []
+    pkg.DATA_DIR = '/root/reference/test/data'
+    sys.modules['reference_unit_tests'] = pkg
+    spec = importlib.util.spec_from_file_location('reference_unit_tests.' + name,
+                                                  '/root/reference/test/unit/%s.py' % name)
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    state = np.random.get_state()                        # test_maths seeds the global generator
+    try:
+        result = unittest.TextTestRunner(stream=io.StringIO(), verbosity=0).run(
+            unittest.defaultTestLoader.loadTestsFromModule(module))
+    finally:
+        np.random.set_state(state)
+    assert result.testsRun == ntests and result.wasSuccessful(), result.failures + result.errors
+
+
 def test_argument_types_follow_the_reference():
     """taiyaki/cmdargs.py types, on the value lists of the reference's test/unit/test_cmdargs.py."""
     import argparse
