@@ -153,12 +153,16 @@ class BatchHDF5Reader(AbstractMappedSignalReader):
         return next(self._iter)
 
     def _some_reads(self, read_ids):
+        """The wanted reads batch by batch (each batch decoded once), in file order within a batch."""
         wanted = set(read_ids)
+        by_batch = {}
+        for read_id, name in self.read_id_to_batch_str.items():
+            if read_id in wanted:
+                by_batch.setdefault(name, []).append(read_id)
         for batch_name in self.batch_names:
-            batch = None
-            for read_id, name in self.read_id_to_batch_str.items():
-                if name == batch_name and read_id in wanted:
-                    batch = self._load_reads_batch(batch_name) if batch is None else batch
+            if batch_name in by_batch:
+                batch = self._load_reads_batch(batch_name)
+                for read_id in by_batch[batch_name]:
                     yield batch[read_id]
 
     def _load_reads_batch(self, batch_name):
