@@ -18,7 +18,7 @@ __version__ = '5.3.0+b200.' + taiyaki_b200.__version__
 
 #: taiyaki.<name> -> taiyaki_b200.<name>
 ALIASED = ('activation', 'alphabet', 'basecall_helpers', 'chunk_selection', 'cmdargs', 'ctc', 'decode',
-           'fast5utils', 'flipflop_remap', 'flipflopfings', 'helpers', 'layers', 'mapped_signal_files',
+           'fast5utils', 'flipflop_remap', 'flipflopfings', 'helpers', 'json', 'layers', 'mapped_signal_files',
            'maths', 'prepare_mapping_funcs', 'qscores', 'signal', 'signal_mapping')
 
 for _name in ALIASED:

@@ -656,6 +656,33 @@ def make_prepare():
            for r in ids})
 
 
+def make_model_json():
+    """Guppy-format JSON of the reference's shipped checkpoints -> tests/golden/model_json.npz (md5 and
+    length of the text only).  Each checkpoint is unpickled into the REFERENCE's taiyaki.layers classes
+    (as in make_trained) and dumped the way bin/dump_json.py:24-34 does: `model.json()` plus the file's
+    md5sum, `json.dump(..., indent=4, cls=taiyaki.json.JsonEncoder)` for the remapping model, and
+    compact (no indent) for the larger mLstm r9.4.1 model."""
+    import hashlib
+    import json
+    import warnings
+    from taiyaki.json import JsonEncoder
+    from taiyaki_b200.helpers import _legacy_rnn_pickles
+    out = {}
+    for name, indent in (('mGru_flipflop_remapping_model_r9_DNA', 4), ('mLstm_flipflop_model_r941_DNA', None)):
+        fn = os.path.join(REF, 'models', name + '.checkpoint')
+        with _legacy_rnn_pickles(), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            net = torch.load(fn, map_location='cpu', weights_only=False)
+        assert type(net).__module__ == 'taiyaki.layers'
+        json_out = net.json()
+        # helpers.file_md5 (taiyaki/helpers.py:302-317; the module needs `imp`, gone in 3.12): md5 of the file
+        json_out['md5sum'] = hashlib.md5(open(fn, 'rb').read()).hexdigest()
+        text = json.dumps(json_out, indent=indent, cls=JsonEncoder)
+        out[name] = np.array([hashlib.md5(text.encode()).hexdigest(), str(len(text)), json_out['md5sum']])
+        print(name, out[name])
+    np.savez_compressed(os.path.join(HERE, 'model_json.npz'), **out)
+
+
 MOD_WEIGHT_ALPHABETS = [('ACGTZ', 'ACGTC', ['5mC']), ('ACGTZY', 'ACGTCA', ['5mC', '6mA']),
                         ('ACGTZYX', 'ACGTCAC', ['5mC', '6mA', '5hmC'])]
 
@@ -698,6 +725,8 @@ if __name__ == '__main__':
         make_mod_weights()
     elif sys.argv[1:] == ['prepare']:
         make_prepare()
+    elif sys.argv[1:] == ['model_json']:
+        make_model_json()
     else:
         if sys.argv[1:] != ['decode']:
             main()
@@ -708,3 +737,4 @@ if __name__ == '__main__':
             make_remap()
             make_mod_weights()
             make_prepare()
+            make_model_json()

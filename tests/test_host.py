@@ -210,6 +210,69 @@ def test_reference_unit_tests_pass_against_this_package(name, ntests):
     assert result.testsRun == ntests and result.wasSuccessful(), result.failures + result.errors
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'),
+                    reason='the reference tree is only in the build container')
+def test_dump_json_of_the_shipped_checkpoints_matches_the_reference(tmp_path):
+    """bin/dump_json.py on the reference's shipped checkpoints: the text equals, byte for byte, what the
+    reference's own layer classes and JsonEncoder produce from the same files (md5 and length in
+    tests/golden/model_json.npz, make_golden.py model_json) -- layer descriptions, Guppy gate order of
+    the GRU parameters, every weight."""
+    import hashlib
+    import importlib
+    from taiyaki_b200 import helpers
+    from taiyaki_b200.json import JsonEncoder
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    cli = importlib.import_module('dump_json')
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'model_json.npz'))
+    name = 'mGru_flipflop_remapping_model_r9_DNA'
+    out = tmp_path / 'model.json'
+    cli.main(['--output', str(out), '/root/reference/models/%s.checkpoint' % name])
+    text = out.read_text()
+    assert [hashlib.md5(text.encode()).hexdigest(), str(len(text))] == list(gold[name][:2])
+    parsed = json.loads(text)
+    assert parsed['md5sum'] == gold[name][2] and parsed['type'] == 'serial' and len(parsed['sublayers']) == 7
+    with pytest.raises(RuntimeError):                   # FileAbsent: an existing output is not replaced
+        cli.main(['--output', str(out), '/root/reference/models/%s.checkpoint' % name])
+    name = 'mLstm_flipflop_model_r941_DNA'              # 58 MB of text: compared without indentation
+    fn = '/root/reference/models/%s.checkpoint' % name
+    json_out = helpers.load_model(fn).json()
+    json_out['md5sum'] = cli.file_md5(fn)
+    text = json.dumps(json_out, cls=JsonEncoder)
+    assert [hashlib.md5(text.encode()).hexdigest(), str(len(text)), json_out['md5sum']] == list(gold[name])
+
+
+def test_dump_json_cli_on_a_saved_model(tmp_path, capsys):
+    """dump_json.py on a checkpoint written by helpers.save_model: valid JSON on stdout, the layer
+    descriptions of the model and its parameters in Guppy's layout."""
+    import importlib
+    from taiyaki_b200 import helpers
+    from taiyaki_b200.alphabet import AlphabetInfo
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    cli = importlib.import_module('dump_json')
+    state = np.random.get_state()
+    try:
+        np.random.seed(5)
+        net = helpers.load_model(os.path.join(ROOT, 'models', 'mGru_flipflop.py'), size=32, stride=2,
+                                 winlen=19, insize=1, alphabet_info=AlphabetInfo('ACGT', 'ACGT'))
+    finally:
+        np.random.set_state(state)
+    ckpt, _ = helpers.save_model(net, str(tmp_path))
+    capsys.readouterr()
+    cli.main([ckpt])
+    parsed = json.loads(capsys.readouterr().out)
+    assert parsed['md5sum'] == cli.file_md5(ckpt)
+    kinds = [layer['type'] for layer in parsed['sublayers']]
+    assert kinds == ['convolution', 'reverse', 'GruMod', 'reverse', 'GruMod', 'reverse', 'GlobalNormTwoState']
+    gru = parsed['sublayers'][2]
+    assert (gru['size'], gru['insize'], gru['bias']) == (32, 32, True)
+    w = net.sublayers[2].cudnn_gru.weight_ih_l0.detach().numpy().reshape(3, 32, 32)     # cuDNN order r, z, n
+    np.testing.assert_array_equal(np.array(gru['params']['iW'], dtype='f4'), w[[1, 0, 2]])   # Guppy: z, r, n
+    conv = parsed['sublayers'][0]
+    assert (conv['winlen'], conv['stride'], conv['padding'], conv['activation']) == (19, 2, [9, 9], 'tanh')
+    np.testing.assert_array_equal(np.array(conv['params']['W'], dtype='f4'),
+                                  net.sublayers[0].conv.weight.detach().numpy())
+
+
 def test_argument_types_follow_the_reference():
     """taiyaki/cmdargs.py types, on the value lists of the reference's test/unit/test_cmdargs.py."""
     import argparse
