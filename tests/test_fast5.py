@@ -126,6 +126,40 @@ def test_generate_per_read_params_reproduces_the_reference_table(tmp_path, capsy
         cli.main(['--output', str(out), os.path.join(REF_DATA, 'reads')])
 
 
+@needs_ref_files
+def test_modified_base_inputs_of_the_reference_acceptance_flow():
+    """test/acceptance/test_prepare_remap.py::test_mod_prepare_remap feeds `--mod Z C 5mC --mod Y A 6mA`
+    and test/data/per_read_references.mod_bases.fasta: the alphabet built from the flags and the integer
+    labels of those references equal what the reference's own alphabet / signal_mapping modules give
+    (loaded from the reference tree for this comparison)."""
+    import importlib.util
+
+    def reference_module(name):
+        spec = importlib.util.spec_from_file_location('reference_' + name, '/root/reference/taiyaki/%s.py' % name)
+        module = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(module)
+        return module
+    from taiyaki_b200.prepare_mapping_funcs import fasta_file_to_dict
+    from taiyaki_b200.signal_mapping import SignalMapping
+    cli = _load_cli('prepare_mapped_reads')
+    mine = cli.make_alphabet_info('ACGT', [['Z', 'C', '5mC'], ['Y', 'A', '6mA']])
+    theirs = reference_module('alphabet').AlphabetInfo('ACGTZY', 'ACGTCA', ['5mC', '6mA'], do_reorder=True)
+    assert (mine.alphabet, mine.collapse_alphabet, mine.mod_long_names, str(mine)) == (
+        theirs.alphabet, theirs.collapse_alphabet, theirs.mod_long_names, str(theirs))
+    assert mine.alphabet == 'AYCZGT' and mine.can_bases == theirs.can_bases == 'ACGT'
+    np.testing.assert_array_equal(mine.collapse_labels, theirs.collapse_labels)
+    refs = fasta_file_to_dict(os.path.join(REF_DATA, 'per_read_references.mod_bases.fasta'), alphabet=mine.alphabet)
+    assert sorted(refs) == sorted(MAPPED)
+    ref_sm = reference_module('signal_mapping').SignalMapping
+    for rid, seq in refs.items():
+        assert 'Z' in seq
+        np.testing.assert_array_equal(SignalMapping.get_integer_reference(seq, mine.alphabet),
+                                      ref_sm.get_integer_reference(seq, theirs.alphabet))
+        assert mine.collapse_sequence(seq) == theirs.collapse_sequence(seq)
+    # with the default alphabet these references are dropped, as bio.fasta_file_to_dict drops them
+    assert fasta_file_to_dict(os.path.join(REF_DATA, 'per_read_references.mod_bases.fasta')) == {}
+
+
 # ---------------------------------------------------------------- the same reads, written here
 @pytest.mark.parametrize('multi', [False, True])
 def test_written_fast5_files_round_trip(g, tmp_path, multi):
