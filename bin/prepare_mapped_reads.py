@@ -186,7 +186,8 @@ def main(argv=None):
     print('Running prepare_mapping using flip-flop remapping')
     shard, launched = shard_of_process(args)
     output = args.output if shard is None else shard_filename(args.output, shard)
-    for fn in {args.output, output}:
+    # under torchrun rank 0 also writes the joined file; a share done by hand (--shard) only its own
+    for fn in ({args.output, output} if launched else {output}):
         if not args.overwrite and os.path.exists(fn):
             print('Cowardly refusing to overwrite {}'.format(fn))
             sys.exit(1)
